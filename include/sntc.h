@@ -1,0 +1,200 @@
+/*
+ * sntc.h -- C ABI of libsntc.so: the B200-native decode hot path of mandt-lab/shallow-ntc.
+ *
+ * The reference (pure Python / TensorFlow 2.10) has no FFI.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference repository root), i.e. what a
+ * ctypes / cffi binding added to the reference would call instead of the TF op sequence.
+ *
+ * Conventions
+ *   - every function returns an int status: SNTC_OK (0) or a negative SNTC_E_* code;
+ *     sntc_last_error() returns a human-readable message for the calling thread.
+ *   - tensors are described by `sntc_tensor`, which is layout-identical to DLPack's `DLTensor`
+ *     (dlpack.h v0.8): the `dl_tensor` member of a DLManagedTensor capsule can be passed by
+ *     pointer, zero-copy.  Tensors must be dense NHWC (strides NULL or contiguous).
+ *   - device_type kDLCUDA (2): used in place on the context's device, asynchronously on `stream`.
+ *     device_type kDLCPU (1) or kDLCUDAHost (3): staged through the context's device buffers
+ *     (host<->device copies are part of the call; the call returns after the outputs landed).
+ *   - the caller owns every input/output buffer; the context owns weights and workspace.
+ *   - there is no CPU fallback: every entry point fails with SNTC_E_CUDA if no sm_100 GPU is usable.
+ */
+#ifndef SNTC_H_
+#define SNTC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNTC_VERSION 100
+
+/* status codes */
+#define SNTC_OK 0
+#define SNTC_E_INVALID (-1)   /* bad argument / shape / dtype */
+#define SNTC_E_CUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define SNTC_E_STATE (-3)     /* call out of order (e.g. decode before finalize, missing weights) */
+#define SNTC_E_UNSUPPORTED (-4)
+
+/* DLPack device types / dtype codes (subset) */
+#define SNTC_DL_CPU 1
+#define SNTC_DL_CUDA 2
+#define SNTC_DL_CUDA_HOST 3
+#define SNTC_DL_INT 0
+#define SNTC_DL_UINT 1
+#define SNTC_DL_FLOAT 2
+
+typedef struct sntc_tensor { /* == DLTensor */
+  void* data;
+  int32_t device_type;
+  int32_t device_id;
+  int32_t ndim;
+  uint8_t dtype_code;
+  uint8_t dtype_bits;
+  uint16_t dtype_lanes;
+  int64_t* shape;
+  int64_t* strides; /* NULL = dense row-major */
+  uint64_t byte_offset;
+} sntc_tensor;
+
+/* Transform classes of the reference's registry, common/transforms.py:383-393 (class_builder). */
+enum sntc_transform_kind {
+  SNTC_T_NONE = 0,                 /* no hyperprior: factorized/models.py */
+  SNTC_T_HYPER_SYNTHESIS = 1,      /* HyperSynthesis            common/transforms.py:222-232 */
+  SNTC_T_JPEG_LIKE_HYPER = 2,      /* JPEGLikeHyperSynthesis    common/transforms.py:364-377 */
+  SNTC_T_HYPER_SMALL = 3,          /* HyperSynthesisSmall       common/transforms.py:250-262 */
+  SNTC_T_JPEG_LIKE_SYNTHESIS = 10, /* JPEGLikeSynthesis         common/transforms.py:265-295 */
+  SNTC_T_TWO_LAYER = 11,           /* TwoLayerSynthesis         common/transforms.py:298-317 */
+  SNTC_T_TWO_LAYER_RES = 12,       /* TwoLayerResSynthesis      common/transforms.py:320-361 (res_type="conv") */
+  SNTC_T_MBT2018 = 13,             /* MBT2018Synthesis          common/transforms.py:158-175 */
+  SNTC_T_BLS2017 = 14,             /* BLS2017Synthesis          common/transforms.py:115-134 */
+  SNTC_T_CNN = 15                  /* CNNSynthesis              common/transforms.py:195-206 */
+};
+
+/* get_activation_op, common/transforms.py:66-78 */
+enum sntc_activation {
+  SNTC_ACT_NONE = 0,
+  SNTC_ACT_RELU = 1,
+  SNTC_ACT_LEAKY_RELU = 2, /* tf.nn.leaky_relu, alpha 0.2 */
+  SNTC_ACT_IGDN1 = 3,      /* GDN1(inverse=True)  */
+  SNTC_ACT_GDN1 = 4        /* GDN1()              */
+};
+
+/* Constructor kwargs of one transform class (same meaning as the Python kwargs). */
+typedef struct sntc_transform_desc {
+  int32_t kind;            /* sntc_transform_kind */
+  int32_t in_channels;     /* channels of the latent fed to the transform (Cy, or Cz for hyper) */
+  int32_t channels[2];     /* two-layer: channels=(C1, Cout); mbt/cnn: (channels_base, output_channels);
+                              bls: (num_filters, 3); jpeg-like: (output_channels, 0);
+                              hyper: (bottleneck_size, 0) */
+  int32_t kernel_sizes[2]; /* two-layer: kernel_sizes; jpeg-like (hyper): (kernel_size, 0) */
+  int32_t strides[2];      /* two-layer: strides; jpeg-like: (strides, 0) */
+  int32_t activation;      /* sntc_activation (activation_type) */
+  int32_t n_layers;        /* MBT2018Synthesis n_layers (default 4) */
+  int32_t use_bias;        /* JPEGLikeSynthesis use_bias */
+  int32_t use_offset;      /* JPEGLikeSynthesis use_offset */
+} sntc_transform_desc;
+
+/* precision of the contraction kernels */
+#define SNTC_PRECISION_FP32 0      /* CUDA-core FFMA, fp32 throughout */
+#define SNTC_PRECISION_TC_F16X3 1  /* tcgen05 split-fp16 3-pass, fp32 accumulate in TMEM (fp32-class accuracy) */
+
+/* index rounding rule of the scale table row */
+#define SNTC_INDEX_RINT 0
+#define SNTC_INDEX_TRUNC 1
+
+/* Everything Model.__init__ / _init_transforms (mshyper/models.py:46-149, factorized/models.py:51-68)
+ * fixes about the decode path. */
+typedef struct sntc_model_desc {
+  int32_t struct_size;            /* sizeof(sntc_model_desc), for ABI evolution */
+  sntc_transform_desc hyper;      /* kind SNTC_T_NONE for the factorized model */
+  sntc_transform_desc synthesis;
+  int32_t num_scales;             /* NUM_SCALES, mshyper/models.py:28 (64) */
+  int32_t index_rounding;         /* SNTC_INDEX_* */
+  int32_t precision;              /* SNTC_PRECISION_* */
+  int32_t reserved;
+} sntc_model_desc;
+
+/* per-image decode metrics: mse_psnr(), common/image_utils.py:26-38 */
+typedef struct sntc_image_metrics {
+  double mse;
+  double psnr;
+  uint64_t ssd; /* exact integer sum of squared uint8 differences */
+} sntc_image_metrics;
+
+typedef struct sntc_ctx sntc_ctx;
+typedef struct sntc_model sntc_model;
+
+int sntc_version(void);
+const char* sntc_last_error(void);
+
+/* ---- context: one per GPU (one process per GPU in the multi-GPU driver) ---- */
+int sntc_create(int device, sntc_ctx** out);
+int sntc_destroy(sntc_ctx* ctx);
+int sntc_sync(sntc_ctx* ctx);                       /* cudaStreamSynchronize of the context stream + sticky error check */
+void* sntc_stream(sntc_ctx* ctx);                   /* the context's cudaStream_t (used when `stream` args are NULL) */
+int sntc_device_name(sntc_ctx* ctx, char* buf, size_t n);
+
+/* ---- model ----
+ * Replaces Model._init_transforms (mshyper/models.py:111-131): transform_builder.build(cls, **kwargs)
+ * for "synthesis" and "hyper_synthesis". */
+int sntc_model_create(sntc_ctx* ctx, const sntc_model_desc* desc, sntc_model** out);
+int sntc_model_destroy(sntc_model* m);
+/* Number of variables the model expects and their names/shapes (Keras variable layouts:
+ * Conv2DTranspose kernel [kh,kw,Cout,Cin]; SignalConv2D kernel [kh,kw,Cin,Cout]; GDN gamma [C,C], beta [C]). */
+int sntc_model_num_variables(sntc_model* m);
+int sntc_model_variable(sntc_model* m, int i, const char** name, int64_t shape[4], int* ndim);
+/* Replaces tf.train.Checkpoint.restore of the transform variables (common/eval_lib.py:43-45):
+ * float32 host array with the effective (de-reparameterised) values; copied, caller keeps ownership. */
+int sntc_model_load_weights(sntc_model* m, const char* name, const float* host, const int64_t* shape, int ndim);
+/* Packs and uploads all weights; fails with SNTC_E_STATE naming the first missing variable. */
+int sntc_model_finalize(sntc_model* m);
+
+/* ---- transform-level calls (the Keras-layer __call__ the model code makes) ----
+ * self._hyper_synthesis(z_hat)            mshyper/models.py:273  -> out f32 [B, hy, wy, 2*Cy]
+ * self._synthesis(y_hat, training=False)  mshyper/models.py:297, factorized/models.py:120-125
+ *                                                              -> out f32 [B, Hp, Wp, 3]           */
+int sntc_hyper_synthesis(sntc_model* m, const sntc_tensor* z_hat, sntc_tensor* out, void* stream);
+int sntc_synthesis(sntc_model* m, const sntc_tensor* y_hat, sntc_tensor* out, void* stream);
+
+/* ---- fused decode ----
+ * Replaces mshyper/models.py:269-317 with training=False (factorized/models.py:101-141 when the
+ * model has no hyperprior; then z_hat and out_idx must be NULL):
+ *   hs = hyper_synthesis(z_hat); mu, sigma = split(hs); i_c = clamp(exp(sigma), 0, S-1); idx = round(i_c)
+ *   y_hat = q_y + mu; x = synthesis(y_hat); x = x[:, :H, :W]; u8 = sat_u8(round((x + .5) * 255))
+ *   mse, psnr = mse_psnr(original_u8, u8)
+ * z_hat  f32 [B, hz, wz, Cz]   integer-valued hyper-latent symbols
+ * q_y    f32 | i16 | i8 [B, hy, wy, Cy]   integer latent symbols round(y - mu) from the range decoder
+ * out_u8 u8 [B, H, W, 3]; out_idx u8 [B, hy, wy, Cy] (nullable); out_yhat f32 [B, hy, wy, Cy] (nullable);
+ * out_f32 f32 [B, H, W, 3] cropped float reconstruction (nullable, debug);
+ * original_u8 u8 [B, H, W, 3] (nullable) and metrics[B] (nullable) -- both or neither. */
+int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q_y, int H, int W,
+                sntc_tensor* out_u8, sntc_tensor* out_idx, sntc_tensor* out_yhat, sntc_tensor* out_f32,
+                const sntc_tensor* original_u8, sntc_image_metrics* metrics, void* stream);
+
+/* ---- profile hook: profile_utils.with_timing (common/profile_utils.py:62-76) ----
+ * Device time in ms of the stages of the last sntc_decode on this model (CUDA events on the
+ * launching stream): [0] hyper_synthesis_time, [1] dequant/index, [2] synthesis_time, [3] total. */
+int sntc_last_stage_times_ms(sntc_model* m, float out[4]);
+/* Number of kernels this library has launched on the context since creation (bench "gpu_launches"). */
+uint64_t sntc_launch_count(sntc_ctx* ctx);
+
+/* ---- device / pinned memory helpers for hosts without a CUDA array library ---- */
+int sntc_malloc(sntc_ctx* ctx, size_t bytes, void** out);
+int sntc_free(sntc_ctx* ctx, void* p);
+int sntc_host_alloc(sntc_ctx* ctx, size_t bytes, void** out); /* pinned */
+int sntc_host_free(sntc_ctx* ctx, void* p);
+int sntc_memcpy_h2d(sntc_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream);
+int sntc_memcpy_d2h(sntc_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream);
+int sntc_memset(sntc_ctx* ctx, void* dst, int value, size_t bytes, void* stream);
+
+/* ---- CUDA-event timers on the launching stream (bench.py) ---- */
+int sntc_event_create(sntc_ctx* ctx, void** out);
+int sntc_event_destroy(sntc_ctx* ctx, void* ev);
+int sntc_event_record(sntc_ctx* ctx, void* ev, void* stream);
+int sntc_event_elapsed_ms(sntc_ctx* ctx, void* start, void* stop, float* ms); /* synchronizes on stop */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNTC_H_ */

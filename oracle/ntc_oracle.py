@@ -1,0 +1,391 @@
+"""CPU oracle for the shallow-ntc decode hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module is the checker, never the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it.  ``shallow_ntc_b200`` never does.
+
+PARITY UNPINNED at the TensorFlow / tensorflow-compression boundary: the
+reference (mandt-lab/shallow-ntc) has no tests or golden vectors for this path
+and its arithmetic lives in third-party packages that are absent from
+``/root/reference`` and cannot be installed offline (``requirements.txt:6-9``:
+tensorflow==2.10.0, tensorflow_compression==2.10.0,
+tensorflow_probability==0.18.0).  What IS pinned, and checked in
+``tests/test_oracle.py``:
+
+* the reference's own structural known-answers (``results/all_params.csv``,
+  ``results/flops_per_pixel.csv``, ``notebooks/get_flops.ipynb``): parameter
+  counts, FLOPs/pixel and tensor shapes of every transform restated here;
+* an independent implementation of each conv convention (torch-CPU
+  ``conv_transpose2d`` + crop, and the gradient-of-SAME-conv definition TF uses),
+  committed as fixtures under ``tests/golden/`` by ``tests/golden/make_golden.py``.
+
+Third-party semantics restated (assumptions A1-A8, each a single switch):
+
+A1  Keras ``Conv2DTranspose(padding="SAME")``: out[o] += in[n] * W[a] with
+    o = n*s + a - p, p = max(k-s,0)//2, output length n_in*s, kernel variable
+    layout [kh, kw, Cout, Cin]; then bias, then activation.
+A2  tfc ``SignalConv2D(corr=False, strides_up=s, padding="same_zeros")``: same
+    scatter form with p = (k-1)//2 (odd k), kernel layout [kh, kw, Cin, Cout].
+A3  ``tf.round`` is round-half-to-even.
+A4  ``tf.saturate_cast(x, uint8)`` clamps to [0, 255] then converts.
+A5  ``tfc.GDN(inverse=True)`` (alpha=2, epsilon=.5): x * sqrt(beta + x^2 @ gamma);
+    ``GDN1`` (``common/transforms.py:8-63``): x * (beta + |x| @ gamma) when inverse,
+    x / (...) otherwise; gamma indexed [in, out].
+A6  ``LocationScaleIndexedEntropyModel._normalize_indexes`` clamps the float
+    index to [0, num_scales-1]; the table row used by a range coder is
+    ``int32(round_half_even(.))`` (``index_rounding='rint'``; 'trunc' selectable).
+A7  ``ContinuousBatchedEntropyModel.quantize``: round(x - off) + off.
+A8  ``tf.nn.leaky_relu`` alpha = 0.2; Keras "relu" = max(x, 0).
+
+Two tiers share one code path, selected by ``dtype``:
+T0  float64, per-tap scatter definition  -> the truth used for parity.
+T1  float32, one BLAS GEMM [pixels x Cin] @ [Cin x k*k*Cout] + col2im slice adds
+    -> the timed CPU stand-in for the reference's TF-2.10 CPU decode.
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+
+# --------------------------------------------------------------------------
+# constants: mshyper/models.py:27-34
+NUM_SCALES = 64
+SCALE_MIN = 0.11
+SCALE_MAX = 256.0
+
+
+def scale_fn(i):
+  """mshyper/models.py:31-32  SCALE_FN(i) = exp(log(.11) + i*(log 256 - log .11)/63)."""
+  factor = (math.log(SCALE_MAX) - math.log(SCALE_MIN)) / (NUM_SCALES - 1.0)
+  return np.exp(math.log(SCALE_MIN) + factor * np.asarray(i, dtype=np.float64))
+
+
+# --------------------------------------------------------------------------
+# transposed convolutions (A1, A2)
+
+def keras_same_pad(k: int, s: int) -> int:
+  """pad_before of the SAME correlation whose input-gradient Keras' Conv2DTranspose is."""
+  return max(k - s, 0) // 2
+
+
+def tfc_same_pad(k: int) -> int:
+  return (k - 1) // 2
+
+
+def _valid_range(n_in: int, s: int, a: int, p: int):
+  """Input indices n with 0 <= n*s + a - p < n_in*s."""
+  lo = 0 if a >= p else -((a - p) // s)  # ceil((p-a)/s)
+  hi = min(n_in - 1, (n_in * s - 1 + p - a) // s)
+  return lo, hi
+
+
+def conv_transpose_scatter(x, w_oi, bias, s: int, p: int, dtype=np.float64, gemm_form=False):
+  """out[b, ny*s+ay-p, nx*s+ax-p, co] += x[b, ny, nx, ci] * w_oi[ay, ax, co, ci]; + bias.
+
+  ``w_oi`` is [kh, kw, Cout, Cin].  Output is [B, h*s, w*s, Cout].
+  ``gemm_form`` (tier T1): a single [B*h*w, Cin] @ [Cin, k*k*Cout] GEMM followed by
+  col2im slice adds, instead of one small matmul per tap (tier T0)."""
+  x = np.asarray(x, dtype=dtype)
+  w_oi = np.asarray(w_oi, dtype=dtype)
+  B, h, w, cin = x.shape
+  kh, kw, cout, cin2 = w_oi.shape
+  assert cin == cin2, (x.shape, w_oi.shape)
+  out = np.zeros((B, h * s, w * s, cout), dtype=dtype)
+  if gemm_form:
+    wm = np.ascontiguousarray(w_oi.transpose(3, 0, 1, 2).reshape(cin, kh * kw * cout))
+    cols = (x.reshape(-1, cin) @ wm).reshape(B, h, w, kh, kw, cout)
+  for ay in range(kh):
+    ylo, yhi = _valid_range(h, s, ay, p)
+    if yhi < ylo:
+      continue
+    for ax in range(kw):
+      xlo, xhi = _valid_range(w, s, ax, p)
+      if xhi < xlo:
+        continue
+      if gemm_form:
+        contrib = cols[:, ylo:yhi + 1, xlo:xhi + 1, ay, ax, :]
+      else:
+        contrib = x[:, ylo:yhi + 1, xlo:xhi + 1, :] @ w_oi[ay, ax].T
+      oy0 = ylo * s + ay - p
+      ox0 = xlo * s + ax - p
+      out[:, oy0:oy0 + (yhi - ylo) * s + 1:s, ox0:ox0 + (xhi - xlo) * s + 1:s, :] += contrib
+  if bias is not None:
+    out += np.asarray(bias, dtype=dtype)
+  return out
+
+
+def keras_conv2d_transpose(x, kernel, bias, strides: int, dtype=np.float64, gemm_form=False):
+  """tf.keras.layers.Conv2DTranspose(padding="SAME") (A1); kernel [kh,kw,Cout,Cin].
+  Call sites: common/transforms.py:85-90, 284, 307-313, 331-357, 371."""
+  k = kernel.shape[0]
+  return conv_transpose_scatter(x, kernel, bias, strides, keras_same_pad(k, strides), dtype, gemm_form)
+
+
+def tfc_signal_conv2d_up(x, kernel, bias, strides_up: int, dtype=np.float64, gemm_form=False):
+  """tfc.SignalConv2D(corr=False, strides_up=s, padding="same_zeros") (A2); kernel [kh,kw,Cin,Cout].
+  Call sites: common/transforms.py:122-133, 169-172, 254-261."""
+  k = kernel.shape[0]
+  assert k % 2 == 1, "only odd kernel supports are used on the hot path"
+  w_oi = np.asarray(kernel).transpose(0, 1, 3, 2)
+  return conv_transpose_scatter(x, w_oi, bias, strides_up, tfc_same_pad(k), dtype, gemm_form)
+
+
+# --------------------------------------------------------------------------
+# activations (A5, A8)
+
+def relu(x):
+  return np.maximum(x, 0)
+
+
+def leaky_relu(x, alpha=0.2):
+  return np.where(x >= 0, x, x * np.asarray(alpha, dtype=x.dtype))
+
+
+def gdn1(x, beta, gamma, inverse: bool):
+  """common/transforms.py:27-63 (GDN1.call): norm = beta + |x| @ gamma; x*norm or x/norm."""
+  dt = x.dtype
+  norm = np.abs(x) @ np.asarray(gamma, dtype=dt) + np.asarray(beta, dtype=dt)
+  return x * norm if inverse else x / norm
+
+
+def gdn_classic(x, beta, gamma, inverse: bool):
+  """tfc.GDN defaults (alpha=2, epsilon=.5): norm = sqrt(beta + x^2 @ gamma)."""
+  dt = x.dtype
+  norm = np.sqrt(np.square(x) @ np.asarray(gamma, dtype=dt) + np.asarray(beta, dtype=dt))
+  return x * norm if inverse else x / norm
+
+
+def apply_activation(x, act, weights=None, prefix=None):
+  """common/transforms.py:66-78 get_activation_op."""
+  if act is None:
+    return x
+  a = act.lower()
+  if a == "relu":
+    return relu(x)
+  if a in ("leaky_relu", "lrelu"):
+    return leaky_relu(x)
+  if a in ("igdn", "igdn1"):
+    return gdn1(x, weights[prefix + ".beta"], weights[prefix + ".gamma"], inverse=True)
+  if a in ("gdn", "gdn1"):
+    return gdn1(x, weights[prefix + ".beta"], weights[prefix + ".gamma"], inverse=False)
+  raise NotImplementedError(act)
+
+
+# --------------------------------------------------------------------------
+# transforms (weights: dict name -> ndarray in the reference's native layouts)
+
+def hyper_synthesis(wts, z_hat, activation_type="relu", dtype=np.float64, gemm_form=False, prefix="hyper_synthesis"):
+  """common/transforms.py:222-232 HyperSynthesis: ConvT k5s2 -> ConvT k5s2 -> ConvT k3s1."""
+  x = z_hat
+  for i, s in enumerate((2, 2, 1)):
+    x = keras_conv2d_transpose(x, wts[f"{prefix}.layer_{i}.kernel"], wts[f"{prefix}.layer_{i}.bias"], s, dtype, gemm_form)
+    if i < 2:
+      x = apply_activation(x, activation_type)
+  return x
+
+
+def jpeg_like_hyper_synthesis(wts, z_hat, dtype=np.float64, gemm_form=False, prefix="hyper_synthesis"):
+  """common/transforms.py:364-377: one ConvT(k, 4) to 2*C channels."""
+  return keras_conv2d_transpose(z_hat, wts[f"{prefix}.conv.kernel"], wts[f"{prefix}.conv.bias"], 4, dtype, gemm_form)
+
+
+def hyper_synthesis_small(wts, z_hat, dtype=np.float64, gemm_form=False, prefix="hyper_synthesis"):
+  """common/transforms.py:250-262: SignalConv 5x5 up2 + relu -> SignalConv 3x3 up1."""
+  x = tfc_signal_conv2d_up(z_hat, wts[f"{prefix}.layer_0.kernel"], wts[f"{prefix}.layer_0.bias"], 2, dtype, gemm_form)
+  x = relu(x)
+  return tfc_signal_conv2d_up(x, wts[f"{prefix}.layer_1.kernel"], wts[f"{prefix}.layer_1.bias"], 1, dtype, gemm_form)
+
+
+def jpeg_like_synthesis(wts, y_hat, strides=16, use_bias=True, use_offset=False, dtype=np.float64, gemm_form=False,
+                        prefix="synthesis"):
+  """common/transforms.py:265-295 JPEGLikeSynthesis."""
+  x = np.asarray(y_hat, dtype=dtype)
+  if use_offset:
+    x = np.concatenate([x, np.ones(x.shape[:3] + (1,), dtype=dtype)], axis=-1)
+  b = wts[f"{prefix}.conv.bias"] if use_bias else None
+  return keras_conv2d_transpose(x, wts[f"{prefix}.conv.kernel"], b, strides, dtype, gemm_form)
+
+
+def two_layer_synthesis(wts, y_hat, strides=(8, 2), activation_type="igdn", dtype=np.float64, gemm_form=False,
+                        prefix="synthesis"):
+  """common/transforms.py:298-317 TwoLayerSynthesis: conv2(act(conv1(z)))."""
+  x = keras_conv2d_transpose(y_hat, wts[f"{prefix}.conv1.kernel"], wts[f"{prefix}.conv1.bias"], strides[0], dtype, gemm_form)
+  x = apply_activation(x, activation_type, wts, f"{prefix}.activation")
+  return keras_conv2d_transpose(x, wts[f"{prefix}.conv2.kernel"], wts[f"{prefix}.conv2.bias"], strides[1], dtype, gemm_form)
+
+
+def two_layer_res_synthesis(wts, y_hat, strides=(8, 2), activation_type="igdn", dtype=np.float64, gemm_form=False,
+                            prefix="synthesis"):
+  """common/transforms.py:320-361 TwoLayerResSynthesis(res_type="conv"):
+  out_conv(act(base_conv(z)) + res(z)); the activation sits inside base_conv (:331-334)."""
+  base = keras_conv2d_transpose(y_hat, wts[f"{prefix}.base_conv.kernel"], wts[f"{prefix}.base_conv.bias"], strides[0], dtype, gemm_form)
+  base = apply_activation(base, activation_type, wts, f"{prefix}.activation")
+  res = keras_conv2d_transpose(y_hat, wts[f"{prefix}.res.kernel"], wts[f"{prefix}.res.bias"], strides[0], dtype, gemm_form)
+  return keras_conv2d_transpose(base + res, wts[f"{prefix}.out_conv.kernel"], wts[f"{prefix}.out_conv.bias"], strides[1], dtype, gemm_form)
+
+
+def mbt2018_synthesis(wts, y_hat, n_layers=4, dtype=np.float64, gemm_form=False, prefix="synthesis"):
+  """common/transforms.py:158-175: n_layers x SignalConv2D 5x5 up2, classic IGDN after all but the last."""
+  x = y_hat
+  for i in range(n_layers):
+    x = tfc_signal_conv2d_up(x, wts[f"{prefix}.layer_{i}.kernel"], wts[f"{prefix}.layer_{i}.bias"], 2, dtype, gemm_form)
+    if i + 1 < n_layers:
+      x = gdn_classic(x, wts[f"{prefix}.igdn_{i}.beta"], wts[f"{prefix}.igdn_{i}.gamma"], inverse=True)
+  return x
+
+
+def bls2017_synthesis(wts, y_hat, dtype=np.float64, gemm_form=False, prefix="synthesis"):
+  """common/transforms.py:115-134: 5x5 up2 + IGDN1, 5x5 up2 + IGDN1, 9x9 up4 (each layer its own GDN1)."""
+  x = y_hat
+  for i, s in enumerate((2, 2, 4)):
+    x = tfc_signal_conv2d_up(x, wts[f"{prefix}.layer_{i}.kernel"], wts[f"{prefix}.layer_{i}.bias"], s, dtype, gemm_form)
+    if i < 2:
+      x = gdn1(x, wts[f"{prefix}.igdn_{i}.beta"], wts[f"{prefix}.igdn_{i}.gamma"], inverse=True)
+  return x
+
+
+def cnn_synthesis(wts, y_hat, activation_type="leaky_relu", dtype=np.float64, gemm_form=False, prefix="synthesis"):
+  """common/transforms.py:195-206: 4 x Keras ConvT k5s2; ONE activation object shared by layers 0-2."""
+  x = y_hat
+  for i in range(4):
+    x = keras_conv2d_transpose(x, wts[f"{prefix}.layer_{i}.kernel"], wts[f"{prefix}.layer_{i}.bias"], 2, dtype, gemm_form)
+    if i < 3:
+      x = apply_activation(x, activation_type, wts, f"{prefix}.activation")
+  return x
+
+
+_SYNTHESIS = {
+  "JPEGLikeSynthesis": lambda w, y, kw, dt, g: jpeg_like_synthesis(
+    w, y, kw.get("strides", 16), kw.get("use_bias", True), kw.get("use_offset", False), dt, g),
+  "TwoLayerSynthesis": lambda w, y, kw, dt, g: two_layer_synthesis(
+    w, y, kw.get("strides", (8, 2)), kw.get("activation_type", "igdn"), dt, g),
+  "TwoLayerResSynthesis": lambda w, y, kw, dt, g: two_layer_res_synthesis(
+    w, y, kw.get("strides", (8, 2)), kw.get("activation_type", "igdn"), dt, g),
+  "MBT2018Synthesis": lambda w, y, kw, dt, g: mbt2018_synthesis(w, y, kw.get("n_layers", 4), dt, g),
+  "BLS2017Synthesis": lambda w, y, kw, dt, g: bls2017_synthesis(w, y, dt, g),
+  "CNNSynthesis": lambda w, y, kw, dt, g: cnn_synthesis(w, y, kw.get("activation_type", "leaky_relu"), dt, g),
+}
+
+_HYPER = {
+  "HyperSynthesis": lambda w, z, kw, dt, g: hyper_synthesis(w, z, kw.get("activation_type", "relu"), dt, g),
+  "JPEGLikeHyperSynthesis": lambda w, z, kw, dt, g: jpeg_like_hyper_synthesis(w, z, dt, g),
+  "HyperSynthesisSmall": lambda w, z, kw, dt, g: hyper_synthesis_small(w, z, dt, g),
+}
+
+
+def synthesis(cls, wts, y_hat, kwargs=None, dtype=np.float64, gemm_form=False):
+  return _SYNTHESIS[cls](wts, y_hat, kwargs or {}, dtype, gemm_form)
+
+
+def hyper_synthesis_by_name(cls, wts, z_hat, kwargs=None, dtype=np.float64, gemm_form=False):
+  return _HYPER[cls](wts, z_hat, kwargs or {}, dtype, gemm_form)
+
+
+# --------------------------------------------------------------------------
+# entropy-model glue and pixel epilogue
+
+def scale_indexes(raw_sigma, index_rounding="rint"):
+  """mshyper/models.py:274-276 + tfc index handling (A6).
+
+  Returns (i_c float64 clamped continuous index, idx uint8 table row, dist = distance
+  of i_c to the nearest rounding boundary -- used for the tie margin of SURVEY F8)."""
+  i_f = np.exp(np.asarray(raw_sigma, dtype=np.float64))
+  i_c = np.minimum(np.maximum(i_f, 0.0), NUM_SCALES - 1.0)
+  if index_rounding == "rint":
+    idx = np.rint(i_c)
+    dist = np.abs(np.abs(i_c - np.floor(i_c)) - 0.5)
+  elif index_rounding == "trunc":
+    idx = np.floor(i_c)
+    frac = i_c - np.floor(i_c)
+    dist = np.minimum(frac, 1.0 - frac)
+  else:
+    raise ValueError(index_rounding)
+  return i_c, idx.astype(np.uint8), dist
+
+
+def dequantize(q, mu):
+  """mshyper/models.py:278-283; latent_rvs_lib.py:95-102: y_hat = round(y - mu) + mu = q + mu, one fp32 add."""
+  return (np.asarray(q, dtype=np.float32) + np.asarray(mu, dtype=np.float32)).astype(np.float32)
+
+
+def quantize_latent(y, offset=0.0):
+  """A7 / A3: round_half_even(y - off) + off (the upstream definition of the integer symbols)."""
+  return np.rint(np.asarray(y) - offset) + offset
+
+
+def unpad_images(x, H, W):
+  """common/image_utils.py:69-71."""
+  return x[:, :H, :W, :]
+
+
+def floats_to_pixels(x):
+  """common/data_lib.py:28-29,48-52 + image_utils.py:22-23 (training=False), evaluated in float32
+  like the reference: saturate_cast_u8(round_half_even((x + 0.5) * 255))."""
+  x32 = np.asarray(x, dtype=np.float32)
+  v = (x32 + np.float32(0.5)) * np.float32(255.0)
+  return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
+def mse_psnr(a_u8, b_u8, max_val=255.0):
+  """common/image_utils.py:26-38: per-image mean squared difference and PSNR."""
+  a = np.asarray(a_u8, dtype=np.float64)
+  b = np.asarray(b_u8, dtype=np.float64)
+  mses = np.mean(np.square(a - b), axis=tuple(range(1, a.ndim)))
+  with np.errstate(divide="ignore"):
+    psnrs = -10.0 * (np.log(mses) - 2.0 * math.log(max_val)) / math.log(10.0)
+  return mses, psnrs
+
+
+def gaussian_bits(q, i_c):
+  """a7 (next row f2): bits under NoisyNormal(scale=SCALE_FN(i_c)) of integer symbol q (loc removed)."""
+  from scipy.special import ndtr
+  sig = scale_fn(i_c)
+  qq = np.abs(np.asarray(q, dtype=np.float64))
+  upper = ndtr((0.5 - qq) / sig)
+  lower = ndtr((-0.5 - qq) / sig)
+  like = np.maximum(upper - lower, 1e-300)
+  return -np.log2(like)
+
+
+def mshyper_decode(wts, synthesis_cls, z_hat, q_y, H, W, synthesis_kwargs=None,
+                   hyper_cls="HyperSynthesis", hyper_kwargs=None, original_u8=None,
+                   dtype=np.float64, gemm_form=False, index_rounding="rint"):
+  """mshyper/models.py:269-317 (training=False), from decoded symbols.
+
+  z_hat: [B, Hp/64, Wp/64, Cz] integer-valued; q_y = round(y - mu): [B, Hp/16, Wp/16, Cy]."""
+  hs = hyper_synthesis_by_name(hyper_cls, wts, z_hat, hyper_kwargs, dtype, gemm_form)
+  cy = hs.shape[-1] // 2
+  mu, raw_sigma = hs[..., :cy], hs[..., cy:]          # tf.split(..., 2, axis=-1)  :274
+  i_c, idx, dist = scale_indexes(raw_sigma, index_rounding)   # :275-276
+  y_hat = dequantize(q_y, mu)                           # :278
+  recon = synthesis(synthesis_cls, wts, y_hat.astype(dtype), synthesis_kwargs, dtype, gemm_form)   # :297
+  recon = unpad_images(recon, H, W)                     # :298
+  out = dict(mu=mu, raw_sigma=raw_sigma, i_c=i_c, idx=idx, idx_dist=dist, y_hat=y_hat,
+             recon=recon, recon_u8=floats_to_pixels(recon))                                       # :314
+  if original_u8 is not None:
+    out["mse"], out["psnr"] = mse_psnr(original_u8, out["recon_u8"])                              # :315
+  return out
+
+
+def factorized_decode(wts, synthesis_cls, q_y, H, W, synthesis_kwargs=None, original_u8=None,
+                      dtype=np.float64, gemm_form=False):
+  """factorized/models.py:101-141 (training=False): y_hat = round(y) (offset 0) -> synthesis -> crop -> u8."""
+  y_hat = np.asarray(q_y, dtype=np.float32)
+  recon = synthesis(synthesis_cls, wts, y_hat.astype(dtype), synthesis_kwargs, dtype, gemm_form)
+  recon = unpad_images(recon, H, W)
+  out = dict(y_hat=y_hat, recon=recon, recon_u8=floats_to_pixels(recon))
+  if original_u8 is not None:
+    out["mse"], out["psnr"] = mse_psnr(original_u8, out["recon_u8"])
+  return out
+
+
+# --------------------------------------------------------------------------
+# structural known-answers (parameter and MAC counts) -- checked against results/*.csv in tests
+
+def count_params(wts, prefix):
+  return int(sum(int(np.prod(v.shape)) for k, v in wts.items() if k.startswith(prefix + ".")))
+
+
+def convt_macs(h, w, k, s, cin, cout):
+  """MACs of a transposed conv as TF's profiler counts them: every (input pixel, tap) pair."""
+  return h * w * k * k * cin * cout

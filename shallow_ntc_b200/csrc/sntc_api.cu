@@ -1,0 +1,779 @@
+// libsntc.so -- C ABI implementation (see include/sntc.h).  One translation unit: host plan logic
+// (sntc_plan.hpp), fp32 CUDA-core kernels (sntc_kernels_f32.cuh), tcgen05 kernels (sntc_kernels_tc.cuh).
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <memory>
+
+#include "../../include/sntc.h"
+#include "sntc_plan.hpp"
+#include "sntc_kernels_f32.cuh"
+#include "sntc_kernels_tc.cuh"
+
+using namespace sntc;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(SNTC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+  } while (0)
+
+#define TRY(expr)            \
+  do {                       \
+    int r__ = (expr);        \
+    if (r__ != SNTC_OK) return r__; \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return SNTC_OK;
+    if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return fail(SNTC_E_CUDA, std::string("cudaFree: ") + cudaGetErrorString(e)); }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; return fail(SNTC_E_CUDA, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e)); }
+    cap = want;
+    return SNTC_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct sntc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  cudaDeviceProp prop{};
+  TcDriver tc;   // cuTensorMapEncodeTiled entry point etc.
+};
+
+struct sntc_model {
+  sntc_ctx* ctx = nullptr;
+  sntc_model_desc desc{};
+  Transform hyper, syn;
+  bool has_hyper = false, has_syn = true;
+  std::vector<VarSpec> vars;
+  HostWeights hw;
+  bool finalized = false;
+  std::vector<void*> owned;            // device allocations (weights)
+  DevBuf ws_a, ws_b, ws_c;             // ping-pong activations + misc
+  DevBuf st_z, st_q, st_u8, st_idx, st_yhat, st_f32, st_orig;   // staging for host tensors
+  DevBuf d_hs, d_yhat, d_ssd;
+  TcModelState tc;                      // tensor-core plan state (tensor maps, fp16 planes)
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+  unsigned long long* h_ssd = nullptr;  // pinned
+  int h_ssd_cap = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int sntc_version(void) { return SNTC_VERSION; }
+extern "C" const char* sntc_last_error(void) { return g_err.c_str(); }
+
+extern "C" int sntc_create(int device, sntc_ctx** out) {
+  if (!out) return fail(SNTC_E_INVALID, "sntc_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SNTC_E_CUDA, std::string("sntc_create: no CUDA device (") + cudaGetErrorString(e) + "); libsntc has no CPU fallback");
+  if (device < 0 || device >= n) return fail(SNTC_E_INVALID, "sntc_create: device index out of range");
+  CU_TRY(cudaSetDevice(device));
+  auto ctx = std::make_unique<sntc_ctx>();
+  ctx->device = device;
+  CU_TRY(cudaGetDeviceProperties(&ctx->prop, device));
+  if (ctx->prop.major != 10)
+    return fail(SNTC_E_CUDA, "sntc_create: device is sm_" + std::to_string(ctx->prop.major * 10 + ctx->prop.minor) +
+                                 "; libsntc is built for sm_100a (B200) only");
+  CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->tc.init();   // resolves the driver entry points lazily; failure is reported when the TC path is requested
+  *out = ctx.release();
+  return SNTC_OK;
+}
+
+extern "C" int sntc_destroy(sntc_ctx* ctx) {
+  if (!ctx) return SNTC_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  delete ctx;
+  return SNTC_OK;
+}
+
+extern "C" int sntc_sync(sntc_ctx* ctx) {
+  if (!ctx) return fail(SNTC_E_INVALID, "sntc_sync: ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  CU_TRY(cudaGetLastError());
+  return SNTC_OK;
+}
+
+extern "C" void* sntc_stream(sntc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" int sntc_device_name(sntc_ctx* ctx, char* buf, size_t n) {
+  if (!ctx || !buf || n == 0) return fail(SNTC_E_INVALID, "sntc_device_name: bad argument");
+  snprintf(buf, n, "%s", ctx->prop.name);
+  return SNTC_OK;
+}
+
+extern "C" uint64_t sntc_launch_count(sntc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// memory / event helpers
+extern "C" int sntc_malloc(sntc_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return fail(SNTC_E_INVALID, "sntc_malloc: bad argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaMalloc(out, bytes ? bytes : 1));
+  return SNTC_OK;
+}
+extern "C" int sntc_free(sntc_ctx* ctx, void* p) {
+  if (!ctx) return fail(SNTC_E_INVALID, "sntc_free: ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaFree(p));
+  return SNTC_OK;
+}
+extern "C" int sntc_host_alloc(sntc_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return fail(SNTC_E_INVALID, "sntc_host_alloc: bad argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return SNTC_OK;
+}
+extern "C" int sntc_host_free(sntc_ctx* ctx, void* p) {
+  if (!ctx) return fail(SNTC_E_INVALID, "sntc_host_free: ctx is NULL");
+  CU_TRY(cudaFreeHost(p));
+  return SNTC_OK;
+}
+static cudaStream_t pick_stream(sntc_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+extern "C" int sntc_memcpy_h2d(sntc_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream) {
+  if (!ctx) return fail(SNTC_E_INVALID, "sntc_memcpy_h2d: ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pick_stream(ctx, stream)));
+  return SNTC_OK;
+}
+extern "C" int sntc_memcpy_d2h(sntc_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream) {
+  if (!ctx) return fail(SNTC_E_INVALID, "sntc_memcpy_d2h: ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, pick_stream(ctx, stream)));
+  return SNTC_OK;
+}
+extern "C" int sntc_memset(sntc_ctx* ctx, void* dst, int value, size_t bytes, void* stream) {
+  if (!ctx) return fail(SNTC_E_INVALID, "sntc_memset: ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaMemsetAsync(dst, value, bytes, pick_stream(ctx, stream)));
+  return SNTC_OK;
+}
+extern "C" int sntc_event_create(sntc_ctx* ctx, void** out) {
+  if (!ctx || !out) return fail(SNTC_E_INVALID, "sntc_event_create: bad argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaEvent_t ev;
+  CU_TRY(cudaEventCreate(&ev));
+  *out = ev;
+  return SNTC_OK;
+}
+extern "C" int sntc_event_destroy(sntc_ctx* ctx, void* ev) {
+  if (!ctx) return fail(SNTC_E_INVALID, "sntc_event_destroy: ctx is NULL");
+  CU_TRY(cudaEventDestroy((cudaEvent_t)ev));
+  return SNTC_OK;
+}
+extern "C" int sntc_event_record(sntc_ctx* ctx, void* ev, void* stream) {
+  if (!ctx || !ev) return fail(SNTC_E_INVALID, "sntc_event_record: bad argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaEventRecord((cudaEvent_t)ev, pick_stream(ctx, stream)));
+  return SNTC_OK;
+}
+extern "C" int sntc_event_elapsed_ms(sntc_ctx* ctx, void* start, void* stop, float* ms) {
+  if (!ctx || !start || !stop || !ms) return fail(SNTC_E_INVALID, "sntc_event_elapsed_ms: bad argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaEventSynchronize((cudaEvent_t)stop));
+  CU_TRY(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return SNTC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model
+static void mark_final_op(Transform& t) {
+  // The last conv of a synthesis transform with <= 3 output channels and only tiny bands runs on the
+  // cell kernel (all phases per thread); otherwise it stays a band GEMM with the pixel epilogue.
+  if (t.ops.empty()) return;
+  Op& last = t.ops.back();
+  if (last.type != OP_CONVT) return;
+  ConvLayer& c = t.convs[last.conv];
+  int maxN = 0;
+  for (auto& b : c.bands) maxN = std::max(maxN, b.N);
+  if (c.cout <= 3 && maxN < 64 && (c.s == 1 || c.s == 2 || c.s == 4)) last.type = OP_CONVT_RGB;
+}
+
+extern "C" int sntc_model_create(sntc_ctx* ctx, const sntc_model_desc* desc, sntc_model** out) {
+  if (!ctx || !desc || !out) return fail(SNTC_E_INVALID, "sntc_model_create: bad argument");
+  *out = nullptr;
+  if (desc->struct_size != (int32_t)sizeof(sntc_model_desc))
+    return fail(SNTC_E_INVALID, "sntc_model_create: desc.struct_size mismatch (ABI)");
+  if (desc->precision != SNTC_PRECISION_FP32 && desc->precision != SNTC_PRECISION_TC_F16X3)
+    return fail(SNTC_E_INVALID, "sntc_model_create: unknown precision");
+  auto m = std::make_unique<sntc_model>();
+  m->ctx = ctx;
+  m->desc = *desc;
+  if (m->desc.num_scales <= 0) m->desc.num_scales = 64;
+  try {
+    m->has_hyper = desc->hyper.kind != SNTC_T_NONE;
+    if (m->has_hyper) {
+      if (desc->hyper.kind < SNTC_T_HYPER_SYNTHESIS || desc->hyper.kind > SNTC_T_HYPER_SMALL)
+        return fail(SNTC_E_INVALID, "sntc_model_create: hyper.kind is not a hyper-synthesis class");
+      m->hyper = build_transform(desc->hyper, "hyper_synthesis");
+    }
+    m->has_syn = desc->synthesis.kind != SNTC_T_NONE;   // hyper-only models serve the standalone transform call
+    if (!m->has_syn && !m->has_hyper) return fail(SNTC_E_INVALID, "sntc_model_create: model has no transform");
+    if (m->has_syn) {
+      if (desc->synthesis.kind < SNTC_T_JPEG_LIKE_SYNTHESIS)
+        return fail(SNTC_E_INVALID, "sntc_model_create: synthesis.kind is not a synthesis class");
+      m->syn = build_transform(desc->synthesis, "synthesis");
+    }
+  } catch (const std::exception& e) {
+    return fail(SNTC_E_INVALID, std::string("sntc_model_create: ") + e.what());
+  }
+  if (m->has_hyper && m->has_syn && m->hyper.out_channels != 2 * m->syn.in_channels)
+    return fail(SNTC_E_INVALID, "sntc_model_create: hyper-synthesis must output 2*Cy channels (mu || sigma)");
+  if (m->has_syn && m->syn.in_channels % 4 != 0) return fail(SNTC_E_UNSUPPORTED, "sntc_model_create: latent channels must be a multiple of 4");
+  if (m->has_syn && m->syn.out_channels > 3) return fail(SNTC_E_UNSUPPORTED, "sntc_model_create: more than 3 image channels");
+  if (m->has_syn) mark_final_op(m->syn);
+  for (Transform* t : {&m->hyper, &m->syn})
+    for (auto& c : t->convs)
+      if (!c.append_ones && c.cin % 4 != 0)
+        return fail(SNTC_E_UNSUPPORTED, "sntc_model_create: layer input channels must be a multiple of 4");
+  if (m->has_hyper) for (auto& v : transform_variables(m->hyper)) m->vars.push_back(v);
+  if (m->has_syn) for (auto& v : transform_variables(m->syn)) m->vars.push_back(v);
+  *out = m.release();
+  return SNTC_OK;
+}
+
+extern "C" int sntc_model_destroy(sntc_model* m) {
+  if (!m) return SNTC_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  for (void* p : m->owned) cudaFree(p);
+  for (DevBuf* b : {&m->ws_a, &m->ws_b, &m->ws_c, &m->st_z, &m->st_q, &m->st_u8, &m->st_idx, &m->st_yhat, &m->st_f32,
+                    &m->st_orig, &m->d_hs, &m->d_yhat, &m->d_ssd})
+    b->release();
+  m->tc.release();
+  for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  if (m->h_ssd) cudaFreeHost(m->h_ssd);
+  delete m;
+  return SNTC_OK;
+}
+
+extern "C" int sntc_model_num_variables(sntc_model* m) { return m ? (int)m->vars.size() : 0; }
+
+extern "C" int sntc_model_variable(sntc_model* m, int i, const char** name, int64_t shape[4], int* ndim) {
+  if (!m || i < 0 || i >= (int)m->vars.size()) return fail(SNTC_E_INVALID, "sntc_model_variable: index out of range");
+  if (name) *name = m->vars[i].name.c_str();
+  if (ndim) *ndim = (int)m->vars[i].shape.size();
+  if (shape) for (size_t d = 0; d < m->vars[i].shape.size() && d < 4; ++d) shape[d] = m->vars[i].shape[d];
+  return SNTC_OK;
+}
+
+extern "C" int sntc_model_load_weights(sntc_model* m, const char* name, const float* host, const int64_t* shape, int ndim) {
+  if (!m || !name || !host || !shape) return fail(SNTC_E_INVALID, "sntc_model_load_weights: bad argument");
+  if (m->finalized) return fail(SNTC_E_STATE, "sntc_model_load_weights: model already finalized");
+  for (auto& v : m->vars) {
+    if (v.name != name) continue;
+    if ((int)v.shape.size() != ndim) return fail(SNTC_E_INVALID, std::string("sntc_model_load_weights: rank mismatch for ") + name);
+    size_t n = 1;
+    for (int d = 0; d < ndim; ++d) {
+      if (shape[d] != v.shape[d])
+        return fail(SNTC_E_INVALID, std::string("sntc_model_load_weights: shape mismatch for ") + name + " (dim " +
+                                      std::to_string(d) + ": got " + std::to_string(shape[d]) + ", expected " + std::to_string(v.shape[d]) + ")");
+      n *= (size_t)shape[d];
+    }
+    for (size_t i = 0; i < n; ++i)
+      if (!std::isfinite(host[i])) return fail(SNTC_E_INVALID, std::string("sntc_model_load_weights: non-finite value in ") + name);
+    m->hw[name] = {std::vector<int64_t>(shape, shape + ndim), std::vector<float>(host, host + n)};
+    return SNTC_OK;
+  }
+  return fail(SNTC_E_INVALID, std::string("sntc_model_load_weights: unknown variable ") + name);
+}
+
+static int upload(sntc_model* m, const void* host, size_t bytes, void** dptr) {
+  CU_TRY(cudaMalloc(dptr, bytes ? bytes : 4));
+  m->owned.push_back(*dptr);
+  CU_TRY(cudaMemcpy(*dptr, host, bytes, cudaMemcpyHostToDevice));
+  return SNTC_OK;
+}
+
+extern "C" int sntc_model_finalize(sntc_model* m) {
+  if (!m) return fail(SNTC_E_INVALID, "sntc_model_finalize: model is NULL");
+  if (m->finalized) return SNTC_OK;
+  for (auto& v : m->vars)
+    if (!m->hw.count(v.name)) return fail(SNTC_E_STATE, "sntc_model_finalize: missing variable " + v.name);
+  CU_TRY(cudaSetDevice(m->ctx->device));
+  for (Transform* t : {&m->hyper, &m->syn}) {
+    for (auto& op : t->ops) {
+      if (op.type == OP_CONVT || op.type == OP_CONVT_RGB) {
+        ConvLayer& c = t->convs[op.conv];
+        std::vector<float> b = pack_bias(c, m->hw);
+        TRY(upload(m, b.data(), b.size() * 4, (void**)&c.d_bias));
+        if (op.type == OP_CONVT) {
+          std::vector<float> w = pack_band_weights(c, m->hw);
+          TRY(upload(m, w.data(), w.size() * 4, (void**)&c.d_w));
+        } else {
+          std::vector<float> w = pack_rgb_weights(c, m->hw);
+          TRY(upload(m, w.data(), w.size() * 4, (void**)&c.d_w_rgb));
+        }
+      }
+      if (op.gdn >= 0) {
+        GdnLayer& g = t->gdns[op.gdn];
+        const auto& beta = m->hw.at(g.beta).second;
+        const auto& gamma = m->hw.at(g.gamma).second;
+        g.Npad = (g.C + 3) / 4 * 4;
+        std::vector<float> gp((size_t)g.C * g.Npad, 0.f);
+        for (int i = 0; i < g.C; ++i) for (int j = 0; j < g.C; ++j) gp[(size_t)i * g.Npad + j] = gamma[(size_t)i * g.C + j];
+        TRY(upload(m, beta.data(), beta.size() * 4, (void**)&g.d_beta));
+        TRY(upload(m, gp.data(), gp.size() * 4, (void**)&g.d_gamma));
+      }
+    }
+  }
+  if (m->desc.precision == SNTC_PRECISION_TC_F16X3) {
+    std::string err;
+    if (!tc_finalize(m->ctx->tc, m->tc, m->has_hyper ? &m->hyper : nullptr, m->has_syn ? &m->syn : nullptr, m->hw, m->owned, &err))
+      return fail(SNTC_E_CUDA, "sntc_model_finalize (tensor-core path): " + err);
+  }
+  for (auto& e : m->ev) CU_TRY(cudaEventCreate(&e));
+  m->hw.clear();
+  m->finalized = true;
+  return SNTC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor checks
+static size_t tensor_elems(const sntc_tensor* t) {
+  size_t n = 1;
+  for (int i = 0; i < t->ndim; ++i) n *= (size_t)t->shape[i];
+  return n;
+}
+
+static int check_tensor(const sntc_tensor* t, const char* what, int code, int bits, int ndim) {
+  if (!t) return fail(SNTC_E_INVALID, std::string(what) + ": tensor is NULL");
+  if (!t->data && tensor_elems(t) != 0) return fail(SNTC_E_INVALID, std::string(what) + ": data is NULL");
+  if (t->ndim != ndim || !t->shape) return fail(SNTC_E_INVALID, std::string(what) + ": expected rank " + std::to_string(ndim));
+  if (t->dtype_lanes != 1 || t->dtype_code != code || t->dtype_bits != bits)
+    return fail(SNTC_E_INVALID, std::string(what) + ": wrong dtype (code " + std::to_string(t->dtype_code) + ", bits " +
+                                  std::to_string(t->dtype_bits) + ")");
+  for (int i = 0; i < ndim; ++i)
+    if (t->shape[i] < 0) return fail(SNTC_E_INVALID, std::string(what) + ": negative dimension");
+  if (t->strides) {
+    int64_t expect = 1;
+    for (int i = ndim - 1; i >= 0; --i) {
+      if (t->shape[i] != 1 && t->strides[i] != expect) return fail(SNTC_E_INVALID, std::string(what) + ": tensor must be dense NHWC");
+      expect *= t->shape[i];
+    }
+  }
+  if (t->device_type != SNTC_DL_CPU && t->device_type != SNTC_DL_CUDA && t->device_type != SNTC_DL_CUDA_HOST)
+    return fail(SNTC_E_INVALID, std::string(what) + ": unsupported device type");
+  return SNTC_OK;
+}
+
+static bool on_device(const sntc_tensor* t) { return t->device_type == SNTC_DL_CUDA; }
+static void* tdata(const sntc_tensor* t) { return (char*)t->data + t->byte_offset; }
+
+static int expect_shape(const sntc_tensor* t, const char* what, int64_t a, int64_t b, int64_t c, int64_t d) {
+  if (t->shape[0] != a || t->shape[1] != b || t->shape[2] != c || t->shape[3] != d)
+    return fail(SNTC_E_INVALID, std::string(what) + ": shape [" + std::to_string(t->shape[0]) + "," + std::to_string(t->shape[1]) + "," +
+                                  std::to_string(t->shape[2]) + "," + std::to_string(t->shape[3]) + "] != expected [" + std::to_string(a) +
+                                  "," + std::to_string(b) + "," + std::to_string(c) + "," + std::to_string(d) + "]");
+  return SNTC_OK;
+}
+
+// Resolve an input tensor to a device pointer (staging host tensors).
+static int stage_in(sntc_model* m, const sntc_tensor* t, size_t bytes, DevBuf& st, cudaStream_t s, const void** dptr) {
+  if (on_device(t)) {
+    if (t->device_id != m->ctx->device) return fail(SNTC_E_INVALID, "tensor lives on a different GPU than the context");
+    *dptr = tdata(t);
+    return SNTC_OK;
+  }
+  TRY(st.ensure(bytes));
+  CU_TRY(cudaMemcpyAsync(st.p, tdata(t), bytes, cudaMemcpyHostToDevice, s));
+  *dptr = st.p;
+  return SNTC_OK;
+}
+// Resolve an output tensor to a device pointer (a staging buffer for host tensors; copied back by unstage_out).
+static int stage_out(sntc_model* m, const sntc_tensor* t, size_t bytes, DevBuf& st, void** dptr) {
+  if (on_device(t)) {
+    if (t->device_id != m->ctx->device) return fail(SNTC_E_INVALID, "tensor lives on a different GPU than the context");
+    *dptr = tdata(t);
+    return SNTC_OK;
+  }
+  TRY(st.ensure(bytes));
+  *dptr = st.p;
+  return SNTC_OK;
+}
+static int unstage_out(const sntc_tensor* t, size_t bytes, const void* dptr, cudaStream_t s, bool* need_sync) {
+  if (on_device(t)) return SNTC_OK;
+  CU_TRY(cudaMemcpyAsync(tdata(t), dptr, bytes, cudaMemcpyDeviceToHost, s));
+  *need_sync = true;
+  return SNTC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 execution of a transform
+struct FinalOut {
+  float* full = nullptr;     // [B, hout, wout, C] f32 (transform-level call)
+  uint8_t* u8 = nullptr;     // [B, H, W, C] cropped pixels
+  float* crop = nullptr;     // [B, H, W, C] cropped floats
+  int H = 0, W = 0;
+};
+
+static int launch_band_gemm(sntc_ctx* ctx, const BandGemmParams& P, cudaStream_t s) {
+  int M = P.B * P.cnty * P.cntx;
+  if (M <= 0 || P.N <= 0) return SNTC_OK;
+  if (P.N >= 96) {
+    dim3 grid((M + 127) / 128, (P.N + 127) / 128);
+    band_gemm_f32_kernel<128, 128, 8, 8, 8><<<grid, 256, 0, s>>>(P);
+  } else {
+    dim3 grid((M + 63) / 64, (P.N + 31) / 32);
+    band_gemm_f32_kernel<64, 32, 16, 4, 4><<<grid, 128, 0, s>>>(P);
+  }
+  ctx->launches++;
+  CU_TRY(cudaGetLastError());
+  return SNTC_OK;
+}
+
+static int run_conv_f32(sntc_ctx* ctx, const ConvLayer& c, const float* in, int B, int h, int w, float* out,
+                        const FinalOut* fin, cudaStream_t s) {
+  for (size_t yi = 0, bi = 0; yi < c.by.size(); ++yi)
+    for (size_t xi = 0; xi < c.bx.size(); ++xi, ++bi) {
+      const Band& b = c.bands[bi];
+      BandGemmParams P{};
+      P.x = in; P.B = B; P.hin = h; P.win = w; P.cin = c.cin_pad; P.a_transform = A_NONE;
+      P.w = c.d_w + b.w_off; P.K = b.K; P.N = b.N; P.Npad = b.Npad;
+      P.bias = c.d_bias; P.cout = c.cout;
+      P.s = c.s; P.p = c.p; P.phy0 = b.phy0; P.nphx = b.nphx; P.phx0 = b.phx0; P.Ty = b.Ty; P.Tx = b.Tx;
+      cell_range(c.by[yi], c.s, c.p, h, &P.mloy, &P.cnty);
+      cell_range(c.bx[xi], c.s, c.p, w, &P.mlox, &P.cntx);
+      P.act = c.act;
+      P.out = out; P.hout = h * c.s; P.wout = w * c.s; P.cstride = c.cout;
+      if (fin) { P.out_u8 = fin->u8; P.out_crop = fin->crop; P.H = fin->H; P.W = fin->W; }
+      P.gx = nullptr; P.gdn_mode = G_NONE;
+      TRY(launch_band_gemm(ctx, P, s));
+    }
+  return SNTC_OK;
+}
+
+static int run_rgb_f32(sntc_ctx* ctx, const ConvLayer& c, const float* in, int B, int h, int w, const FinalOut* fin, cudaStream_t s) {
+  RgbCellParams P{};
+  P.x = in; P.B = B; P.hin = h; P.win = w; P.cin = c.cin_pad; P.w = c.d_w_rgb; P.bias = c.d_bias;
+  P.cout = c.cout; P.k = c.k; P.s = c.s; P.p = c.p;
+  P.cnty = floor_div(c.s * h - 1 + c.p, c.s) + 1;
+  P.cntx = floor_div(c.s * w - 1 + c.p, c.s) + 1;
+  int cc = (40 * 1024) / (c.k * c.k * 16);
+  cc = std::max(4, cc / 4 * 4);
+  cc = std::min(cc, c.cin_pad);
+  P.cc = cc;
+  P.hout = h * c.s; P.wout = w * c.s;
+  if (fin) { P.out = fin->full; P.out_u8 = fin->u8; P.out_crop = fin->crop; P.H = fin->H; P.W = fin->W; }
+  size_t smem = (size_t)c.k * c.k * cc * 16;
+  dim3 grid((P.cnty * P.cntx + 127) / 128, B);
+  if (c.s == 1) convt_rgb_cell_kernel<1><<<grid, 128, smem, s>>>(P);
+  else if (c.s == 2) convt_rgb_cell_kernel<2><<<grid, 128, smem, s>>>(P);
+  else if (c.s == 4) convt_rgb_cell_kernel<4><<<grid, 128, smem, s>>>(P);
+  else return fail(SNTC_E_UNSUPPORTED, "rgb cell kernel: stride must be 1, 2 or 4");
+  ctx->launches++;
+  CU_TRY(cudaGetLastError());
+  return SNTC_OK;
+}
+
+static int run_gdn_f32(sntc_ctx* ctx, const GdnLayer& g, const float* in, size_t npix, float* out, cudaStream_t s) {
+  if (g.C <= 64) {
+    ActResParams P{};
+    P.in = in; P.in_stride = g.C; P.out = out; P.npix = npix; P.C = g.C;
+    P.act = g.inverse ? SNTC_ACT_IGDN1 : SNTC_ACT_GDN1; P.has_res = 0;
+    P.beta = g.d_beta; P.gamma = g.d_gamma; P.gamma_stride = g.Npad; P.inverse = g.inverse;
+    if (g.kind != GDN_1) return fail(SNTC_E_UNSUPPORTED, "classic GDN with C <= 64 is not on any decode path");
+    size_t smem = ((size_t)g.C * g.C + g.C + 128 * (g.C + 1)) * 4;
+    act_res_kernel<<<(unsigned)((npix + 127) / 128), 128, smem, s>>>(P);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return SNTC_OK;
+  }
+  // norm = beta + f(x) @ gamma as a 1x1 band GEMM; epilogue multiplies / divides x
+  BandGemmParams P{};
+  P.x = in; P.B = 1; P.hin = 1; P.win = (int)npix; P.cin = g.C;
+  P.a_transform = g.kind == GDN_1 ? A_ABS : A_SQUARE;
+  P.w = g.d_gamma; P.K = g.C; P.N = g.C; P.Npad = g.Npad; P.bias = g.d_beta; P.cout = g.C;
+  P.s = 1; P.p = 0; P.phy0 = 0; P.nphx = 1; P.phx0 = 0; P.Ty = 1; P.Tx = 1;
+  P.mloy = 0; P.cnty = 1; P.mlox = 0; P.cntx = (int)npix;
+  P.act = SNTC_ACT_NONE; P.out = out; P.hout = 1; P.wout = (int)npix; P.cstride = g.C;
+  P.gx = in;
+  P.gdn_mode = g.kind == GDN_1 ? (g.inverse ? G_MUL : G_DIV) : (g.inverse ? G_MUL_SQRT : G_DIV_SQRT);
+  return launch_band_gemm(ctx, P, s);
+}
+
+// Runs `t` on `in` [B,h,w,Cin].  Intermediates ping-pong in the model workspace.  The final op writes
+// to fin (pixel epilogue) and/or fin->full.
+static int run_transform_f32(sntc_model* m, Transform& t, const float* in, int B, int h, int w, const FinalOut* fin, cudaStream_t s) {
+  sntc_ctx* ctx = m->ctx;
+  // workspace sizing
+  size_t maxbytes = 0;
+  {
+    int ch = h, cw = w;
+    for (auto& op : t.ops) {
+      if (op.type == OP_CONVT || op.type == OP_CONVT_RGB) {
+        const ConvLayer& c = t.convs[op.conv];
+        if (c.append_ones) maxbytes = std::max(maxbytes, (size_t)B * ch * cw * c.cin_pad * 4);
+        ch *= c.s; cw *= c.s;
+        maxbytes = std::max(maxbytes, (size_t)B * ch * cw * c.cout * 4);
+      }
+    }
+  }
+  TRY(m->ws_a.ensure(maxbytes));
+  TRY(m->ws_b.ensure(maxbytes));
+  const float* cur = in;
+  int ch = h, cw = w, cc = t.in_channels;
+  int flip = 0;
+  auto next_buf = [&]() { float* p = (float*)(flip ? m->ws_b.p : m->ws_a.p); flip ^= 1; return p; };
+  for (size_t i = 0; i < t.ops.size(); ++i) {
+    Op& op = t.ops[i];
+    bool last = i + 1 == t.ops.size();
+    if (op.type == OP_CONVT || op.type == OP_CONVT_RGB) {
+      const ConvLayer& c = t.convs[op.conv];
+      if (c.append_ones) {
+        float* tmp = next_buf();
+        size_t n = (size_t)B * ch * cw * c.cin_pad;
+        append_ones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cur, c.cin, tmp, c.cin_pad, (size_t)B * ch * cw);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        cur = tmp;
+      }
+      float* dst = last ? (fin ? fin->full : nullptr) : next_buf();
+      if (op.type == OP_CONVT) TRY(run_conv_f32(ctx, c, cur, B, ch, cw, dst, last ? fin : nullptr, s));
+      else TRY(run_rgb_f32(ctx, c, cur, B, ch, cw, fin, s));
+      ch *= c.s; cw *= c.s; cc = c.cout;
+      cur = dst;
+    } else if (op.type == OP_GDN) {
+      float* dst = next_buf();
+      TRY(run_gdn_f32(ctx, t.gdns[op.gdn], cur, (size_t)B * ch * cw, dst, s));
+      cur = dst;
+    } else if (op.type == OP_ACT_RES) {
+      int C = cc / 2;
+      float* dst = next_buf();
+      ActResParams P{};
+      P.in = cur; P.in_stride = cc; P.out = dst; P.npix = (size_t)B * ch * cw; P.C = C; P.act = op.act; P.has_res = 1;
+      if (op.gdn >= 0) { const GdnLayer& g = t.gdns[op.gdn]; P.beta = g.d_beta; P.gamma = g.d_gamma; P.gamma_stride = g.Npad; P.inverse = g.inverse; }
+      if (C > 64) return fail(SNTC_E_UNSUPPORTED, "two-layer hidden width > 64");
+      size_t smem = ((size_t)C * C + C + 128 * (C + 1)) * 4;
+      act_res_kernel<<<(unsigned)((P.npix + 127) / 128), 128, smem, s>>>(P);
+      ctx->launches++;
+      CU_TRY(cudaGetLastError());
+      cur = dst; cc = C;
+    }
+  }
+  return SNTC_OK;
+}
+
+static int run_transform(sntc_model* m, Transform& t, bool is_hyper, const float* in, int B, int h, int w, const FinalOut* fin, cudaStream_t s) {
+  if (m->desc.precision == SNTC_PRECISION_TC_F16X3) {
+    std::string err;
+    int r = tc_run_transform(m->ctx->tc, m->tc, t, is_hyper, in, B, h, w, fin ? fin->full : nullptr, fin ? fin->u8 : nullptr,
+                             fin ? fin->crop : nullptr, fin ? fin->H : 0, fin ? fin->W : 0, s, &m->ctx->launches, &err);
+    if (r == TC_OK) return SNTC_OK;
+    if (r != TC_NOT_HANDLED) return fail(SNTC_E_CUDA, "tensor-core path: " + err);
+  }
+  return run_transform_f32(m, t, in, B, h, w, fin, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int sntc_hyper_synthesis(sntc_model* m, const sntc_tensor* z_hat, sntc_tensor* out, void* stream) {
+  if (!m) return fail(SNTC_E_INVALID, "sntc_hyper_synthesis: model is NULL");
+  if (!m->finalized) return fail(SNTC_E_STATE, "sntc_hyper_synthesis: model not finalized");
+  if (!m->has_hyper) return fail(SNTC_E_STATE, "sntc_hyper_synthesis: model has no hyperprior");
+  TRY(check_tensor(z_hat, "z_hat", SNTC_DL_FLOAT, 32, 4));
+  TRY(check_tensor(out, "out", SNTC_DL_FLOAT, 32, 4));
+  int B = (int)z_hat->shape[0], h = (int)z_hat->shape[1], w = (int)z_hat->shape[2];
+  if (z_hat->shape[3] != m->hyper.in_channels) return fail(SNTC_E_INVALID, "z_hat: wrong channel count");
+  TRY(expect_shape(out, "out", B, (int64_t)h * m->hyper.upsample, (int64_t)w * m->hyper.upsample, m->hyper.out_channels));
+  if (tensor_elems(z_hat) == 0) return SNTC_OK;
+  CU_TRY(cudaSetDevice(m->ctx->device));
+  cudaStream_t s = pick_stream(m->ctx, stream);
+  const void* dz; void* dout; bool need_sync = false;
+  TRY(stage_in(m, z_hat, tensor_elems(z_hat) * 4, m->st_z, s, &dz));
+  TRY(stage_out(m, out, tensor_elems(out) * 4, m->d_hs, &dout));
+  FinalOut fin; fin.full = (float*)dout;
+  TRY(run_transform(m, m->hyper, true, (const float*)dz, B, h, w, &fin, s));
+  TRY(unstage_out(out, tensor_elems(out) * 4, dout, s, &need_sync));
+  if (need_sync) CU_TRY(cudaStreamSynchronize(s));
+  return SNTC_OK;
+}
+
+extern "C" int sntc_synthesis(sntc_model* m, const sntc_tensor* y_hat, sntc_tensor* out, void* stream) {
+  if (!m) return fail(SNTC_E_INVALID, "sntc_synthesis: model is NULL");
+  if (!m->finalized) return fail(SNTC_E_STATE, "sntc_synthesis: model not finalized");
+  if (!m->has_syn) return fail(SNTC_E_STATE, "sntc_synthesis: model has no synthesis transform");
+  TRY(check_tensor(y_hat, "y_hat", SNTC_DL_FLOAT, 32, 4));
+  TRY(check_tensor(out, "out", SNTC_DL_FLOAT, 32, 4));
+  int B = (int)y_hat->shape[0], h = (int)y_hat->shape[1], w = (int)y_hat->shape[2];
+  if (y_hat->shape[3] != m->syn.in_channels) return fail(SNTC_E_INVALID, "y_hat: wrong channel count");
+  TRY(expect_shape(out, "out", B, (int64_t)h * m->syn.upsample, (int64_t)w * m->syn.upsample, m->syn.out_channels));
+  if (tensor_elems(y_hat) == 0) return SNTC_OK;
+  CU_TRY(cudaSetDevice(m->ctx->device));
+  cudaStream_t s = pick_stream(m->ctx, stream);
+  const void* dy; void* dout; bool need_sync = false;
+  TRY(stage_in(m, y_hat, tensor_elems(y_hat) * 4, m->st_q, s, &dy));
+  TRY(stage_out(m, out, tensor_elems(out) * 4, m->st_f32, &dout));
+  FinalOut fin; fin.full = (float*)dout;
+  TRY(run_transform(m, m->syn, false, (const float*)dy, B, h, w, &fin, s));
+  TRY(unstage_out(out, tensor_elems(out) * 4, dout, s, &need_sync));
+  if (need_sync) CU_TRY(cudaStreamSynchronize(s));
+  return SNTC_OK;
+}
+
+extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q_y, int H, int W,
+                           sntc_tensor* out_u8, sntc_tensor* out_idx, sntc_tensor* out_yhat, sntc_tensor* out_f32,
+                           const sntc_tensor* original_u8, sntc_image_metrics* metrics, void* stream) {
+  if (!m) return fail(SNTC_E_INVALID, "sntc_decode: model is NULL");
+  if (!m->finalized) return fail(SNTC_E_STATE, "sntc_decode: model not finalized (weights missing?)");
+  if (!m->has_syn) return fail(SNTC_E_STATE, "sntc_decode: model has no synthesis transform");
+  if (!q_y) return fail(SNTC_E_INVALID, "sntc_decode: q_y is NULL");
+  if (!q_y->shape || q_y->ndim != 4) return fail(SNTC_E_INVALID, "q_y: expected rank 4");
+  int q_kind;
+  if (q_y->dtype_code == SNTC_DL_FLOAT && q_y->dtype_bits == 32) q_kind = 0;
+  else if (q_y->dtype_code == SNTC_DL_INT && q_y->dtype_bits == 16) q_kind = 1;
+  else if (q_y->dtype_code == SNTC_DL_INT && q_y->dtype_bits == 8) q_kind = 2;
+  else return fail(SNTC_E_INVALID, "q_y: dtype must be float32, int16 or int8");
+  TRY(check_tensor(q_y, "q_y", q_y->dtype_code, q_y->dtype_bits, 4));
+  const int q_bytes = q_kind == 0 ? 4 : (q_kind == 1 ? 2 : 1);
+  const int B = (int)q_y->shape[0], hy = (int)q_y->shape[1], wy = (int)q_y->shape[2], Cy = (int)q_y->shape[3];
+  if (Cy != m->syn.in_channels) return fail(SNTC_E_INVALID, "q_y: channel count does not match the synthesis transform");
+  const int Hp = hy * m->syn.upsample, Wp = wy * m->syn.upsample, Co = m->syn.out_channels;
+  if (H <= 0 || W <= 0 || H > Hp || W > Wp)
+    return fail(SNTC_E_INVALID, "sntc_decode: image size " + std::to_string(H) + "x" + std::to_string(W) + " does not fit the latent grid (" +
+                                  std::to_string(Hp) + "x" + std::to_string(Wp) + " padded)");
+  int hz = 0, wz = 0;
+  if (m->has_hyper) {
+    TRY(check_tensor(z_hat, "z_hat", SNTC_DL_FLOAT, 32, 4));
+    hz = (int)z_hat->shape[1]; wz = (int)z_hat->shape[2];
+    if (z_hat->shape[0] != B || z_hat->shape[3] != m->hyper.in_channels || hz * m->hyper.upsample != hy || wz * m->hyper.upsample != wy)
+      return fail(SNTC_E_INVALID, "z_hat: shape does not match q_y through the hyper-synthesis (x" + std::to_string(m->hyper.upsample) + ")");
+  } else {
+    if (z_hat) return fail(SNTC_E_INVALID, "sntc_decode: factorized model takes no z_hat");
+    if (out_idx) return fail(SNTC_E_INVALID, "sntc_decode: factorized model has no scale indexes");
+  }
+  TRY(check_tensor(out_u8, "out_u8", SNTC_DL_UINT, 8, 4));
+  TRY(expect_shape(out_u8, "out_u8", B, H, W, Co));
+  if (out_idx) { TRY(check_tensor(out_idx, "out_idx", SNTC_DL_UINT, 8, 4)); TRY(expect_shape(out_idx, "out_idx", B, hy, wy, Cy)); }
+  if (out_yhat) { TRY(check_tensor(out_yhat, "out_yhat", SNTC_DL_FLOAT, 32, 4)); TRY(expect_shape(out_yhat, "out_yhat", B, hy, wy, Cy)); }
+  if (out_f32) { TRY(check_tensor(out_f32, "out_f32", SNTC_DL_FLOAT, 32, 4)); TRY(expect_shape(out_f32, "out_f32", B, H, W, Co)); }
+  if ((original_u8 != nullptr) != (metrics != nullptr)) return fail(SNTC_E_INVALID, "sntc_decode: original_u8 and metrics go together");
+  if (original_u8) { TRY(check_tensor(original_u8, "original_u8", SNTC_DL_UINT, 8, 4)); TRY(expect_shape(original_u8, "original_u8", B, H, W, Co)); }
+  if (B == 0) return SNTC_OK;
+
+  sntc_ctx* ctx = m->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick_stream(ctx, stream);
+  bool need_sync = false;
+  const size_t n_lat = (size_t)B * hy * wy * Cy, n_img = (size_t)B * H * W * Co;
+
+  const void* d_q; const void* d_z = nullptr; void* d_u8; void* d_idx = nullptr; void* d_f32 = nullptr; const void* d_orig = nullptr;
+  TRY(stage_in(m, q_y, n_lat * q_bytes, m->st_q, s, &d_q));
+  if (m->has_hyper) TRY(stage_in(m, z_hat, tensor_elems(z_hat) * 4, m->st_z, s, &d_z));
+  TRY(stage_out(m, out_u8, n_img, m->st_u8, &d_u8));
+  if (out_idx) TRY(stage_out(m, out_idx, n_lat, m->st_idx, &d_idx));
+  if (out_f32) TRY(stage_out(m, out_f32, n_img * 4, m->st_f32, &d_f32));
+  if (original_u8) TRY(stage_in(m, original_u8, n_img, m->st_orig, s, &d_orig));
+  // y_hat always materialises on the device (it is the synthesis input)
+  void* d_yhat;
+  if (out_yhat && on_device(out_yhat)) d_yhat = tdata(out_yhat);
+  else { TRY(m->d_yhat.ensure(n_lat * 4)); d_yhat = m->d_yhat.p; }
+
+  CU_TRY(cudaEventRecord(m->ev[0], s));
+  if (m->has_hyper) {
+    TRY(m->d_hs.ensure(n_lat * 2 * 4));
+    bool fused = false;
+    if (m->desc.precision == SNTC_PRECISION_TC_F16X3) {
+      // tensor-core path fuses split/exp/clamp/round and q + mu into the last hyper-synthesis GEMM
+      std::string err;
+      int r = tc_run_hyper_fused(ctx->tc, m->tc, m->hyper, (const float*)d_z, B, hz, wz, d_q, q_kind, (float*)d_yhat, (uint8_t*)d_idx,
+                                 (float)(m->desc.num_scales - 1), m->desc.index_rounding == SNTC_INDEX_TRUNC, s, &ctx->launches, &err);
+      if (r == TC_OK) fused = true;
+      else if (r != TC_NOT_HANDLED) return fail(SNTC_E_CUDA, "tensor-core path: " + err);
+    }
+    if (!fused) {
+      FinalOut fin; fin.full = (float*)m->d_hs.p;
+      TRY(run_transform(m, m->hyper, true, (const float*)d_z, B, hz, wz, &fin, s));
+      CU_TRY(cudaEventRecord(m->ev[1], s));
+      DequantParams P{};
+      P.hs = (const float*)m->d_hs.p; P.q = d_q; P.q_kind = q_kind; P.npix = (size_t)B * hy * wy; P.C = Cy;
+      P.max_index = (float)(m->desc.num_scales - 1); P.trunc = m->desc.index_rounding == SNTC_INDEX_TRUNC;
+      P.y_hat = (float*)d_yhat; P.idx = (uint8_t*)d_idx;
+      size_t n = P.npix * (Cy / 4);
+      dequant_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(P);
+      ctx->launches++;
+      CU_TRY(cudaGetLastError());
+    } else {
+      CU_TRY(cudaEventRecord(m->ev[1], s));
+    }
+  } else {
+    CU_TRY(cudaEventRecord(m->ev[1], s));
+    if (q_kind == 0) {
+      d_yhat = const_cast<void*>(d_q);   // y_hat = q, already float32
+    } else {
+      convert_q_kernel<<<(unsigned)((n_lat / 4 + 255) / 256), 256, 0, s>>>(d_q, q_kind, (float*)d_yhat, n_lat / 4);
+      ctx->launches++;
+      CU_TRY(cudaGetLastError());
+    }
+  }
+  CU_TRY(cudaEventRecord(m->ev[2], s));
+  {
+    FinalOut fin; fin.u8 = (uint8_t*)d_u8; fin.crop = (float*)d_f32; fin.H = H; fin.W = W;
+    TRY(run_transform(m, m->syn, false, (const float*)d_yhat, B, hy, wy, &fin, s));
+  }
+  if (original_u8) {
+    TRY(m->d_ssd.ensure((size_t)B * 8));
+    if (m->h_ssd_cap < B) {
+      if (m->h_ssd) cudaFreeHost(m->h_ssd);
+      CU_TRY(cudaHostAlloc((void**)&m->h_ssd, (size_t)B * 8, cudaHostAllocDefault));
+      m->h_ssd_cap = B;
+    }
+    CU_TRY(cudaMemsetAsync(m->d_ssd.p, 0, (size_t)B * 8, s));
+    size_t per = (size_t)H * W * Co;
+    dim3 grid((unsigned)std::min<size_t>((per + 256 * 16 - 1) / (256 * 16), 1024), B);
+    ssd_kernel<<<grid, 256, 0, s>>>((const uint8_t*)d_orig, (const uint8_t*)d_u8, per, (unsigned long long*)m->d_ssd.p);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(m->h_ssd, m->d_ssd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    need_sync = true;
+  }
+  CU_TRY(cudaEventRecord(m->ev[3], s));
+  m->ev_valid = true;
+  TRY(unstage_out(out_u8, n_img, d_u8, s, &need_sync));
+  if (out_idx) TRY(unstage_out(out_idx, n_lat, d_idx, s, &need_sync));
+  if (out_f32) TRY(unstage_out(out_f32, n_img * 4, d_f32, s, &need_sync));
+  if (out_yhat && !on_device(out_yhat)) TRY(unstage_out(out_yhat, n_lat * 4, d_yhat, s, &need_sync));
+  if (need_sync) CU_TRY(cudaStreamSynchronize(s));
+  if (metrics) {
+    double npx = (double)H * W * Co;
+    for (int b = 0; b < B; ++b) {
+      metrics[b].ssd = m->h_ssd[b];
+      metrics[b].mse = (double)m->h_ssd[b] / npx;
+      // psnr = -10 * (ln mse - 2 ln 255) / ln 10        image_utils.py:37
+      metrics[b].psnr = -10.0 * (std::log(metrics[b].mse) - 2.0 * std::log(255.0)) / std::log(10.0);
+    }
+  }
+  return SNTC_OK;
+}
+
+extern "C" int sntc_last_stage_times_ms(sntc_model* m, float out[4]) {
+  if (!m || !out) return fail(SNTC_E_INVALID, "sntc_last_stage_times_ms: bad argument");
+  if (!m->ev_valid) return fail(SNTC_E_STATE, "sntc_last_stage_times_ms: no decode recorded yet");
+  CU_TRY(cudaSetDevice(m->ctx->device));
+  CU_TRY(cudaEventSynchronize(m->ev[3]));
+  CU_TRY(cudaEventElapsedTime(&out[0], m->ev[0], m->ev[1]));
+  CU_TRY(cudaEventElapsedTime(&out[1], m->ev[1], m->ev[2]));
+  CU_TRY(cudaEventElapsedTime(&out[2], m->ev[2], m->ev[3]));
+  CU_TRY(cudaEventElapsedTime(&out[3], m->ev[0], m->ev[3]));
+  return SNTC_OK;
+}

@@ -1,0 +1,69 @@
+"""Shared helpers for the parity tests: run a config through libsntc and through the oracle."""
+import numpy as np
+
+from shallow_ntc_b200 import build_config, synthetic
+from oracle import ntc_oracle as O
+
+# tolerances (BASELINE.json north_star): float reconstruction 1e-3 max-abs in pixel space [-0.5, 0.5]
+# (same scale as [0,1]); PSNR delta 0.01 dB; uint8 within 1 LSB; scale-table rows exact outside the
+# tie margin |i_c - (k + .5)| < IDX_MARGIN * max(1, i_c)
+RECON_TOL = 1e-3
+PSNR_TOL = 0.01
+IDX_MARGIN = 1e-3
+MU_TOL = 1e-4
+
+
+def syn_kwargs(model):
+  cfg = model._transform_config["synthesis"]
+  return cfg["cls"], {k: v for k, v in cfg.items() if k != "cls"}
+
+
+def hyper_kwargs(model):
+  cfg = model._transform_config.get("hyper_synthesis")
+  if cfg is None:
+    return "HyperSynthesis", {}
+  return cfg["cls"], {k: v for k, v in cfg.items() if k not in ("cls", "bottleneck_size")}
+
+
+def make_case(name, B, H, W, kind="stress", precision="fp32", ctx=None, first_index=0, index_rounding="rint"):
+  model = build_config(name, precision=precision, ctx=ctx, index_rounding=index_rounding)
+  cls, _ = syn_kwargs(model)
+  wts = synthetic.make_weights(model.variable_shapes(), kind, synthesis_cls=cls)
+  model.load_weights(wts)
+  zs, ys = model.latent_shapes(B, H, W)
+  z, q = synthetic.make_latents(zs, ys, first_index=first_index)
+  return model, wts, z, q
+
+
+def oracle_decode(model, wts, z, q, H, W, original=None, dtype=np.float64, gemm_form=False, index_rounding="rint"):
+  cls, kw = syn_kwargs(model)
+  if model.hyperprior:
+    hcls, hkw = hyper_kwargs(model)
+    return O.mshyper_decode(wts, cls, z, q, H, W, kw, hcls, hkw, original, dtype, gemm_form, index_rounding)
+  return O.factorized_decode(wts, cls, q, H, W, kw, original, dtype, gemm_form)
+
+
+def check_against_oracle(got, ref, hyper=True, recon_tol=RECON_TOL):
+  """The correctness gates of SURVEY 8(d).  Returns a dict of measured deviations."""
+  rep = {}
+  err = np.abs(got["float"].astype(np.float64) - ref["recon"])
+  rep["recon_max_abs"] = float(err.max())
+  assert rep["recon_max_abs"] < recon_tol, rep
+  d = np.abs(got["image"].astype(np.int16) - ref["recon_u8"].astype(np.int16))
+  rep["u8_max_diff"] = int(d.max())
+  rep["u8_frac_diff"] = float((d > 0).mean())
+  assert rep["u8_max_diff"] <= 1 and rep["u8_frac_diff"] < 1e-3, rep
+  if hyper:
+    # y_hat = q + mu is a single fp32 add: mu_gpu is recovered exactly as y_hat - q when |q| small
+    mu_err = np.abs(got["y_hat"].astype(np.float64) - ref["y_hat"].astype(np.float64))
+    rep["yhat_max_abs"] = float(mu_err.max())
+    assert rep["yhat_max_abs"] < MU_TOL * np.maximum(1.0, np.abs(ref["y_hat"]).max() / 64), rep
+    margin = IDX_MARGIN * np.maximum(1.0, ref["i_c"])
+    far = ref["idx_dist"] > margin
+    rep["idx_in_margin"] = int((~far).sum())
+    rep["idx_mismatch_outside_margin"] = int((got["idx"][far] != ref["idx"][far]).sum())
+    rep["idx_mismatch_in_margin"] = int((got["idx"][~far] != ref["idx"][~far]).sum())
+    assert rep["idx_mismatch_outside_margin"] == 0, rep
+    assert rep["idx_in_margin"] < 0.01 * far.size, rep
+    assert np.abs(got["idx"].astype(int) - ref["idx"].astype(int)).max() <= 1, "a boundary flip moves the row by at most one"
+  return rep

@@ -1,0 +1,131 @@
+"""-m gpu: libsntc (through the C ABI / ctypes) against the float64 oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from shallow_ntc_b200 import synthetic
+from helpers import make_case, oracle_decode, check_against_oracle, PSNR_TOL
+
+pytestmark = pytest.mark.gpu
+
+SMALL = [  # (config, B, H, W)
+  ("jpegl", 2, 128, 192),
+  ("two_layer_syn", 2, 128, 192),
+  ("two_layer_syn2", 1, 100, 150),       # C1 = 12, needs reflect-pad geometry (Hp=128, Wp=192) + crop
+  ("two_layer_syn2:24", 1, 128, 128),
+  ("two_layer_syn2:48", 1, 64, 128),
+  ("mbt2018", 1, 64, 128),
+  ("bls2017", 2, 48, 80),
+]
+
+
+@pytest.mark.parametrize("kind", ["init", "stress"])
+@pytest.mark.parametrize("name,B,H,W", SMALL)
+def test_decode_matches_oracle_fp32(gpu_ctx, name, B, H, W, kind):
+  model, wts, z, q = make_case(name, B, H, W, kind, "fp32", gpu_ctx)
+  ref = oracle_decode(model, wts, z, q, H, W)
+  orig = synthetic.make_original(ref["recon_u8"])
+  ref_mse, ref_psnr = __import__("oracle.ntc_oracle", fromlist=["x"]).mse_psnr(orig, ref["recon_u8"])
+  got = model.decompress(z, q, (H, W), return_float=True, return_yhat=True, original=orig)
+  rep = check_against_oracle(got, ref, hyper=model.hyperprior)
+  assert np.all(np.abs(got["psnr"] - ref_psnr) < PSNR_TOL), (got["psnr"], ref_psnr)
+  print(name, kind, rep)
+
+
+def test_yhat_is_bit_exact_single_add(gpu_ctx):
+  """y_hat = q + mu must be exactly fl32(q + mu_gpu): decode twice with q and with q = 0 (-> mu)."""
+  model, wts, z, q = make_case("two_layer_syn", 1, 64, 64, "stress", "fp32", gpu_ctx)
+  mu = model.decompress(z, np.zeros_like(q), (64, 64), return_yhat=True)["y_hat"]
+  yh = model.decompress(z, q, (64, 64), return_yhat=True)["y_hat"]
+  assert np.array_equal(yh, (q + mu).astype(np.float32))
+
+
+def test_hyper_synthesis_and_synthesis_transform_calls(gpu_ctx):
+  """The Keras-layer call convention: hyper_synthesis(z_hat) and synthesis(y_hat) on their own."""
+  from oracle import ntc_oracle as O
+  model, wts, z, q = make_case("two_layer_syn", 1, 64, 128, "stress", "fp32", gpu_ctx)
+  hs = model.hyper_synthesis(z)
+  ref = O.hyper_synthesis(wts, z)
+  assert hs.shape == ref.shape and np.abs(hs - ref).max() < 1e-4
+  y_hat = (q + hs[..., :320]).astype(np.float32)
+  x = model.synthesis(y_hat)
+  refx = O.two_layer_res_synthesis(wts, y_hat.astype(np.float64))
+  assert x.shape == refx.shape == (1, 64, 128, 3) and np.abs(x - refx).max() < 1e-3
+
+
+def test_int8_int16_latents_match_float(gpu_ctx):
+  model, wts, z, q = make_case("two_layer_syn", 2, 64, 64, "stress", "fp32", gpu_ctx)
+  a = model.decompress(z, q, (64, 64))
+  b = model.decompress(z, q.astype(np.int16), (64, 64))
+  c = model.decompress(z, q.astype(np.int8), (64, 64))
+  for k in ("image", "idx"):
+    assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k])
+
+
+def test_device_resident_zero_copy_matches_host(gpu_ctx):
+  model, wts, z, q = make_case("two_layer_syn", 2, 64, 128, "stress", "fp32", gpu_ctx)
+  host = model.decompress(z, q, (64, 128))
+  dz, dq = gpu_ctx.to_device(z), gpu_ctx.to_device(q)
+  dev = model.decompress(dz, dq, (64, 128))
+  assert np.array_equal(dev["image"].to_host(), host["image"])
+  assert np.array_equal(dev["idx"].to_host(), host["idx"])
+
+
+def test_batch_independence_and_determinism(gpu_ctx):
+  """Images are independent units: decoding a shard equals the slice of the full batch."""
+  model, wts, z, q = make_case("two_layer_syn", 4, 64, 64, "stress", "fp32", gpu_ctx)
+  full = model.decompress(z, q, (64, 64))
+  again = model.decompress(z, q, (64, 64))
+  assert np.array_equal(full["image"], again["image"]) and np.array_equal(full["idx"], again["idx"])
+  part = model.decompress(z[1:3], q[1:3], (64, 64))
+  assert np.array_equal(part["image"], full["image"][1:3]) and np.array_equal(part["idx"], full["idx"][1:3])
+
+
+def test_zero_latents_give_bias_image(gpu_ctx):
+  """vis_syn_filters.ipynb cells 28-29: synthesis(zeros) equals the bias broadcast (JPEG-like)."""
+  model, wts, z, q = make_case("jpegl", 1, 64, 64, "stress", "fp32", gpu_ctx)
+  x = model.synthesis(np.zeros((1, 4, 4, 320), np.float32))
+  assert np.allclose(x, wts["synthesis.conv.bias"].reshape(1, 1, 1, 3), atol=1e-7)
+
+
+def test_jpegl_linearity(gpu_ctx):
+  """vis_syn_filters.ipynb cells 36-41: g(k e_i) - g(0) = k (g(e_i) - g(0)) for the one-layer synthesis."""
+  model, wts, z, q = make_case("jpegl", 1, 64, 64, "init", "fp32", gpu_ctx)
+  e = np.zeros((1, 4, 4, 320), np.float32)
+  e[0, 1, 2, 17] = 1.0
+  g0 = model.synthesis(np.zeros_like(e))
+  g1 = model.synthesis(e)
+  g5 = model.synthesis(5 * e)
+  assert np.abs((g5 - g0) - 5 * (g1 - g0)).max() < 1e-5
+  # support of one latent pixel: an 18x18 patch at (16*1 - 1, 16*2 - 1)
+  nz = np.argwhere(np.abs(g1 - g0)[0].sum(-1) > 0)
+  assert nz[:, 0].min() >= 15 and nz[:, 0].max() <= 32 and nz[:, 1].min() >= 31 and nz[:, 1].max() <= 48
+
+
+def test_argument_errors_are_loud(gpu_ctx):
+  from shallow_ntc_b200 import SntcError
+  model, wts, z, q = make_case("two_layer_syn", 1, 64, 64, "init", "fp32", gpu_ctx)
+  with pytest.raises(SntcError):
+    model.decompress(z, q[..., :100].copy(), (64, 64))          # wrong channel count
+  with pytest.raises(SntcError):
+    model.decompress(z, q, (65, 64))                              # image larger than the latent grid
+  with pytest.raises(SntcError):
+    model.decompress(z[:, :0], q, (64, 64))                       # z / y geometry mismatch
+  empty = model.decompress(z[:0], q[:0], (64, 64))                # empty batch is a no-op
+  assert empty["image"].shape == (0, 64, 64, 3)
+
+
+def test_full_size_config2_properties(gpu_ctx):
+  """BASELINE config 2 (two_layer_syn, 24 x 512x768): oracle on 2 of the 24 images + size-independent
+  properties (shard independence, exact integer SSD / PSNR against a host recomputation)."""
+  B, H, W = 24, 512, 768
+  model, wts, z, q = make_case("two_layer_syn", B, H, W, "stress", "fp32", gpu_ctx)
+  got = model.decompress(z, q, (H, W), return_float=True, return_yhat=True)
+  for b in (0, 23):
+    ref = oracle_decode(model, wts, z[b:b + 1], q[b:b + 1], H, W)
+    sub = {k: v[b:b + 1] for k, v in got.items()}
+    print(b, check_against_oracle(sub, ref))
+  orig = synthetic.make_original(got["image"])
+  m = model.decompress(z, q, (H, W), original=orig)
+  ssd = ((m["image"].astype(np.int64) - orig.astype(np.int64)) ** 2).reshape(B, -1).sum(1)
+  assert np.array_equal(m["ssd"].astype(np.int64), ssd)
+  assert np.array_equal(m["image"], got["image"])
