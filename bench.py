@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- decoded Mpx/s of the shallow-ntc decode hot path on N B200s (one process per GPU).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--config two_layer_syn] [--batch 24]
+
+Workload (BASELINE.json configs[1]): mshyper two_layer_syn decode of a batch of 24 synthetic
+Kodak-shaped 768x512 images per GPU ("weak" scaling: every rank decodes its own 24-image shard of the
+seeded image list, no data-path collective; NCCL only sums the PSNR at the end).  A step = one
+sntc_decode of the batch.  `value` = un-padded pixels decoded by all ranks / max-over-ranks device time
+with inputs resident in HBM; `e2e` = the same through the public API with pinned HOST buffers
+(host->device of the symbols and device->host of image + index map inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+H, W = 512, 768
+FLOP_PER_PX = {"two_layer_syn": 40940.0}   # 2*MAC of the convs, reference counting
+
+
+def load_peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    d = json.load(open(p))
+    return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), tflops_burst=d["bf16_tflops"], source="measured")
+  return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source="fallback")
+
+
+class ClockSampler:
+  """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index):
+    self.gpu, self.rows, self.proc = gpu_index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.t = threading.Thread(target=self._read, daemon=True)
+      self.t.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(",")])
+
+  def stop(self):
+    if not self.proc:
+      return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for r in self.rows:
+      try:
+        sm.append(float(r[1])); mx.append(float(r[2]))
+        for n, v in zip(names, r[5:9]):
+          if v.lower().startswith("active"):
+            reasons.add(n)
+      except Exception:
+        pass
+    busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+    return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=max(mx) if mx else None,
+                reasons=sorted(reasons), samples=len(sm))
+
+
+def dist_init(n_gpus):
+  """torch.distributed is plumbing only (barrier, max-over-ranks, final PSNR sum)."""
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if world == 1:
+    return None, 0, 1, 0
+  import torch
+  import torch.distributed as dist
+  torch.cuda.set_device(local)
+  os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+  return dist, rank, world, local
+
+
+def cpu_reference_run(config, n_images, steps, warmup):
+  """Times the oracle's float32 GEMM-form restatement (tier T1) of the same decode on the host cores:
+  the stand-in for the reference's TF-2.10 CPU decode, which cannot be installed here."""
+  from shallow_ntc_b200 import build_config, synthetic
+  from oracle import ntc_oracle as O
+  model = build_config(config)
+  cfg = model._transform_config["synthesis"]
+  kw = {k: v for k, v in cfg.items() if k != "cls"}
+  wts = synthetic.make_weights(model.variable_shapes(), "stress", synthesis_cls=cfg["cls"])
+  zs, ys = model.latent_shapes(n_images, H, W)
+  z, q = synthetic.make_latents(zs, ys)
+
+  def one():
+    return O.mshyper_decode(wts, cfg["cls"], z, q, H, W, kw, dtype=np.float32, gemm_form=True)
+  for _ in range(warmup):
+    one()
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    one()
+  dt = time.perf_counter() - t0
+  return n_images * H * W * steps / dt / 1e6, dt / steps
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="native", choices=["native", "reference"])
+  ap.add_argument("--config", default="two_layer_syn")
+  ap.add_argument("--batch", type=int, default=24)
+  ap.add_argument("--precision", default=os.environ.get("SNTC_PRECISION", "auto"))
+  ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through (working set > L2)")
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+  cores = os.cpu_count()
+
+  if args.impl == "reference":
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+      return 0
+    n_img = 2
+    v, sec = cpu_reference_run(args.config, n_img, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = dict(impl="reference", metric="decoded Mpx/s", value=v, unit="Mpx/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=f"mshyper {args.config} decode, 768x512, random-init weights", images_per_step=n_img),
+                cpu_baseline=dict(value=v, unit="Mpx/s", cores=cores, kind="port",
+                                  sample=f"{n_img} of the {args.batch} images per step, oracle tier T1 (numpy float32 GEMM-form, BLAS threads = all cores); "
+                                         "TF-2.10 itself is not installable offline"),
+                e2e=dict(value=v, unit="Mpx/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+    return 0
+
+  dist, rank, world, local = dist_init(args.gpus)
+  from shallow_ntc_b200 import build_config, synthetic, Context
+  ctx = Context(local)
+  B = args.batch
+  peaks = load_peaks()
+
+  def make_model(precision):
+    m = build_config(args.config, precision=precision, ctx=ctx)
+    cfg = m._transform_config["synthesis"]
+    m.load_weights(synthetic.make_weights(m.variable_shapes(), "stress", synthesis_cls=cfg["cls"]))
+    m._ensure_native()
+    return m
+
+  precision = args.precision
+  if precision == "auto":
+    try:
+      model = make_model("tc")
+      precision = "tc"
+    except Exception as e:   # tensor-core kernels unavailable: the fp32 CUDA-core path is still a GPU path
+      if rank == 0:
+        print(f"[bench] tensor-core path unavailable ({e}); using fp32 CUDA-core kernels", file=sys.stderr)
+      model = make_model("fp32")
+      precision = "fp32"
+  else:
+    model = make_model(precision)
+
+  zs, ys = model.latent_shapes(B, H, W)
+  # this rank's shard of the seeded image list; `rotate` distinct batches so consecutive steps never reuse inputs
+  sets = []
+  for r in range(args.rotate):
+    z, q = synthetic.make_latents(zs, ys, first_index=(rank * args.rotate + r) * B)
+    sets.append((z, q))
+  dev = [(ctx.to_device(z), ctx.to_device(q)) for z, q in sets]
+  out_dev = dict(image=ctx.empty((B, H, W, 3), np.uint8), idx=ctx.empty(ys, np.uint8))
+
+  def step_dev(i):
+    dz, dq = dev[i % args.rotate]
+    model.decompress(dz, dq, (H, W), out=out_dev, sync=False)
+
+  def barrier():
+    ctx.sync()
+    if dist is not None:
+      dist.barrier()
+
+  for i in range(args.warmup):
+    step_dev(i)
+  barrier()
+  sampler = ClockSampler(local)
+  sampler.start()
+  model.profile_layers(True)
+  l0 = ctx.launch_count
+  e0, e1 = ctx.event(), ctx.event()
+  barrier()
+  e0.record()
+  for i in range(args.steps):
+    step_dev(i)
+  e1.record()
+  ctx.sync()
+  ms = e0.elapsed_ms(e1)
+  barrier()
+  launches = ctx.launch_count - l0
+  model.profile_layers(False)
+  prof = model.layer_profile()
+  clocks = sampler.stop()
+
+  # ---- e2e: pinned host buffers through the public API, copies inside the timed region ----
+  pin = [(ctx.pinned_like(z), ctx.pinned_like(q)) for z, q in sets[:2]]
+  out_host = dict(image=ctx.pinned_empty((B, H, W, 3), np.uint8), idx=ctx.pinned_empty(ys, np.uint8))
+  for i in range(2):
+    model.decompress(pin[i % 2][0], pin[i % 2][1], (H, W), out=out_host)
+  barrier()
+  f0, f1 = ctx.event(), ctx.event()
+  f0.record()
+  for i in range(args.steps):
+    model.decompress(pin[i % 2][0], pin[i % 2][1], (H, W), out=out_host)
+  f1.record()
+  ctx.sync()
+  ms_e2e = f0.elapsed_ms(f1)
+  h2d = int(sets[0][0].nbytes + sets[0][1].nbytes)
+  d2h = int(out_host["image"].nbytes + out_host["idx"].nbytes)
+
+  # final quality sum over ranks (the only collective; NCCL all-reduce of 3 doubles)
+  orig = synthetic.make_original(out_host["image"][:2], first_index=rank * B)
+  met = model.decompress(sets[(args.steps - 1) % 2][0][:2], sets[(args.steps - 1) % 2][1][:2], (H, W), original=orig)
+  qsum = np.array([met["psnr"].sum(), met["mse"].sum(), float(len(met["psnr"]))])
+  if dist is not None:
+    import torch
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    tq = torch.tensor(qsum, dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(tq, op=dist.ReduceOp.SUM)
+    qsum = tq.cpu().numpy()
+
+  if rank == 0:
+    px_step = world * B * H * W
+    value = px_step * args.steps / (ms * 1e-3) / 1e6
+    e2e = px_step * args.steps / (ms_e2e * 1e-3) / 1e6
+    # dominant kernel = the layer with the largest share of device time
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
+    roof = None
+    if dom[0] is not None and dom[1]["macs"] > 0:
+      per_launch_ms = dom[1]["ms"] / dom[1]["n"]
+      ach = 2.0 * dom[1]["macs"] / (per_launch_ms * 1e-3) / 1e12
+      roof = dict(bound="tensor", kernel=dom[0], achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"],
+                  traffic=None, peak_source=peaks["source"] + " bf16 dense sustained", share_of_step=dom[1]["ms"] / ms,
+                  ms_per_launch=per_launch_ms, algorithmic_flops_per_launch=2.0 * dom[1]["macs"],
+                  hbm_view=dict(algorithmic_gbs=world * B * 3760128 * args.steps / (ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"]))
+    line = dict(metric="decoded Mpx/s", value=value, unit="Mpx/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32" if precision == "fp32" else "f16x3-split/f32-accum", data="synthetic",
+                config=dict(workload=f"mshyper {args.config} decode (BASELINE configs[1]): {B} x 768x512 per GPU, random-init 'stress' weights",
+                            images_per_gpu=B, precision=precision, l2="inputs rotate over %d distinct batches; per-step working set > 126 MB L2" % args.rotate,
+                            layers_ms={k: round(v["ms"] / max(v["n"], 1), 4) for k, v in prof.items()},
+                            mean_psnr_db=float(qsum[0] / qsum[2])),
+                clocks=clocks, gpu_launches=int(launches),
+                e2e=dict(value=e2e, unit="Mpx/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps),
+                roofline=roof)
+    if world == 1 and not args.no_cpu_baseline:
+      n_img = 2
+      v, sec = cpu_reference_run(args.config, n_img, 3, 1)
+      line["cpu_baseline"] = dict(value=v, unit="Mpx/s", cores=cores, kind="port",
+                                  sample=f"{n_img} of the {B} images x 3 steps, oracle tier T1 (numpy float32 GEMM-form + col2im), {sec:.2f} s/step")
+    print(json.dumps(line), flush=True)
+  if dist is not None:
+    dist.barrier()
+    dist.destroy_process_group()
+  return 0
+
+
+if __name__ == "__main__":
+  sys.exit(main())

@@ -176,6 +176,15 @@ int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q_y,
  * Device time in ms of the stages of the last sntc_decode on this model (CUDA events on the
  * launching stream): [0] hyper_synthesis_time, [1] dequant/index, [2] synthesis_time, [3] total. */
 int sntc_last_stage_times_ms(sntc_model* m, float out[4]);
+/* Per-layer device timing (CUDA events on the launching stream around each layer of the plan).
+ * enable(1) clears the records; while enabled every transform / decode call appends records.
+ * Records are aggregated by label ("hyper_synthesis.layer_2", "synthesis.base_conv", "dequant_index", ...):
+ * total ms, number of timed intervals, and the algorithmic MACs of ONE interval (reference counting:
+ * B*h*w*k*k*Cin*Cout, as in results/flops_per_pixel.csv; 0 for pointwise stages). */
+int sntc_profile_enable(sntc_model* m, int on);
+int sntc_profile_count(sntc_model* m);
+int sntc_profile_get(sntc_model* m, int i, const char** label, float* total_ms, int* intervals, double* macs_per_interval);
+
 /* Number of kernels this library has launched on the context since creation (bench "gpu_launches"). */
 uint64_t sntc_launch_count(sntc_ctx* ctx);
 

@@ -71,6 +71,9 @@ _PROTOS = {
   "sntc_decode": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor),
                             C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(ImageMetrics), _P]),
   "sntc_last_stage_times_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+  "sntc_profile_enable": (C.c_int, [_P, C.c_int]),
+  "sntc_profile_count": (C.c_int, [_P]),
+  "sntc_profile_get": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
   "sntc_launch_count": (C.c_uint64, [_P]),
   "sntc_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
   "sntc_free": (C.c_int, [_P, _P]),

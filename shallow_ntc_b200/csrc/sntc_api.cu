@@ -54,8 +54,16 @@ struct sntc_ctx {
   TcDriver tc;   // cuTensorMapEncodeTiled entry point etc.
 };
 
+struct ProfRec { std::string label; cudaEvent_t a = nullptr, b = nullptr; double macs = 0; };
+struct ProfAgg { std::string label; float ms = 0; int n = 0; double macs = 0; };
+
 struct sntc_model {
   sntc_ctx* ctx = nullptr;
+  bool prof_on = false;
+  std::vector<ProfRec> prof;            // appended while profiling is enabled
+  std::vector<cudaEvent_t> prof_pool;   // recycled events
+  std::vector<ProfAgg> prof_agg;
+  bool prof_agg_valid = false;
   sntc_model_desc desc{};
   Transform hyper, syn;
   bool has_hyper = false, has_syn = true;
@@ -263,6 +271,8 @@ extern "C" int sntc_model_destroy(sntc_model* m) {
     b->release();
   m->tc.release();
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  for (auto& r : m->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& e : m->prof_pool) cudaEventDestroy(e);
   if (m->h_ssd) cudaFreeHost(m->h_ssd);
   delete m;
   return SNTC_OK;
@@ -420,6 +430,70 @@ static int unstage_out(const sntc_tensor* t, size_t bytes, const void* dptr, cud
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-layer profiling
+static cudaEvent_t prof_event(sntc_model* m) {
+  if (!m->prof_pool.empty()) { cudaEvent_t e = m->prof_pool.back(); m->prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {
+  sntc_model* m; cudaStream_t s; int idx = -1;
+  ProfScope(sntc_model* m_, cudaStream_t s_, const std::string& label, double macs) : m(m_), s(s_) {
+    if (!m->prof_on) return;
+    ProfRec r; r.label = label; r.macs = macs; r.a = prof_event(m); r.b = prof_event(m);
+    cudaEventRecord(r.a, s);
+    m->prof.push_back(r); idx = (int)m->prof.size() - 1; m->prof_agg_valid = false;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(m->prof[idx].b, s); }
+};
+static double conv_macs(const ConvLayer& c, int B, int h, int w) {
+  return (double)B * h * w * c.k * c.k * (c.cin + (c.append_ones ? 1 : 0)) * c.cout;
+}
+
+extern "C" int sntc_profile_enable(sntc_model* m, int on) {
+  if (!m) return fail(SNTC_E_INVALID, "sntc_profile_enable: model is NULL");
+  CU_TRY(cudaSetDevice(m->ctx->device));
+  if (on) {
+    CU_TRY(cudaStreamSynchronize(m->ctx->stream));
+    for (auto& r : m->prof) { m->prof_pool.push_back(r.a); m->prof_pool.push_back(r.b); }
+    m->prof.clear(); m->prof_agg.clear(); m->prof_agg_valid = false;
+  }
+  m->prof_on = on != 0;
+  return SNTC_OK;
+}
+static int prof_aggregate(sntc_model* m) {
+  if (m->prof_agg_valid) return SNTC_OK;
+  CU_TRY(cudaSetDevice(m->ctx->device));
+  m->prof_agg.clear();
+  for (auto& r : m->prof) {
+    CU_TRY(cudaEventSynchronize(r.b));
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+    ProfAgg* a = nullptr;
+    for (auto& x : m->prof_agg) if (x.label == r.label) { a = &x; break; }
+    if (!a) { m->prof_agg.push_back({r.label, 0.f, 0, r.macs}); a = &m->prof_agg.back(); }
+    a->ms += ms; a->n += 1;
+  }
+  m->prof_agg_valid = true;
+  return SNTC_OK;
+}
+extern "C" int sntc_profile_count(sntc_model* m) {
+  if (!m || prof_aggregate(m) != SNTC_OK) return 0;
+  return (int)m->prof_agg.size();
+}
+extern "C" int sntc_profile_get(sntc_model* m, int i, const char** label, float* total_ms, int* intervals, double* macs) {
+  if (!m) return fail(SNTC_E_INVALID, "sntc_profile_get: model is NULL");
+  TRY(prof_aggregate(m));
+  if (i < 0 || i >= (int)m->prof_agg.size()) return fail(SNTC_E_INVALID, "sntc_profile_get: index out of range");
+  if (label) *label = m->prof_agg[i].label.c_str();
+  if (total_ms) *total_ms = m->prof_agg[i].ms;
+  if (intervals) *intervals = m->prof_agg[i].n;
+  if (macs) *macs = m->prof_agg[i].macs;
+  return SNTC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 execution of a transform
 struct FinalOut {
   float* full = nullptr;     // [B, hout, wout, C] f32 (transform-level call)
@@ -550,13 +624,17 @@ static int run_transform_f32(sntc_model* m, Transform& t, const float* in, int B
         cur = tmp;
       }
       float* dst = last ? (fin ? fin->full : nullptr) : next_buf();
+      std::string lbl = c.sources[0].kernel.substr(0, c.sources[0].kernel.size() - 7);
+      ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
       if (op.type == OP_CONVT) TRY(run_conv_f32(ctx, c, cur, B, ch, cw, dst, last ? fin : nullptr, s));
       else TRY(run_rgb_f32(ctx, c, cur, B, ch, cw, fin, s));
       ch *= c.s; cw *= c.s; cc = c.cout;
       cur = dst;
     } else if (op.type == OP_GDN) {
       float* dst = next_buf();
-      TRY(run_gdn_f32(ctx, t.gdns[op.gdn], cur, (size_t)B * ch * cw, dst, s));
+      const GdnLayer& gl = t.gdns[op.gdn];
+      ProfScope ps(m, s, gl.beta.substr(0, gl.beta.size() - 5), (double)B * ch * cw * gl.C * gl.C);
+      TRY(run_gdn_f32(ctx, gl, cur, (size_t)B * ch * cw, dst, s));
       cur = dst;
     } else if (op.type == OP_ACT_RES) {
       int C = cc / 2;
@@ -565,6 +643,7 @@ static int run_transform_f32(sntc_model* m, Transform& t, const float* in, int B
       P.in = cur; P.in_stride = cc; P.out = dst; P.npix = (size_t)B * ch * cw; P.C = C; P.act = op.act; P.has_res = 1;
       if (op.gdn >= 0) { const GdnLayer& g = t.gdns[op.gdn]; P.beta = g.d_beta; P.gamma = g.d_gamma; P.gamma_stride = g.Npad; P.inverse = g.inverse; }
       if (C > 64) return fail(SNTC_E_UNSUPPORTED, "two-layer hidden width > 64");
+      ProfScope ps(m, s, "synthesis.activation+res", (double)P.npix * C * C);
       size_t smem = ((size_t)C * C + C + 128 * (C + 1)) * 4;
       act_res_kernel<<<(unsigned)((P.npix + 127) / 128), 128, smem, s>>>(P);
       ctx->launches++;
@@ -705,6 +784,7 @@ extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_t
       FinalOut fin; fin.full = (float*)m->d_hs.p;
       TRY(run_transform(m, m->hyper, true, (const float*)d_z, B, hz, wz, &fin, s));
       CU_TRY(cudaEventRecord(m->ev[1], s));
+      ProfScope ps(m, s, "dequant_index", 0);
       DequantParams P{};
       P.hs = (const float*)m->d_hs.p; P.q = d_q; P.q_kind = q_kind; P.npix = (size_t)B * hy * wy; P.C = Cy;
       P.max_index = (float)(m->desc.num_scales - 1); P.trunc = m->desc.index_rounding == SNTC_INDEX_TRUNC;

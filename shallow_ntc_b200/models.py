@@ -216,6 +216,21 @@ class Model:
       out["synthesis_time"] = t[2] * 1e-3
     return out
 
+  def profile_layers(self, on: bool):
+    """Per-layer CUDA-event timing inside libsntc (sntc_profile_enable)."""
+    self._ensure_native()
+    check(lib.sntc_profile_enable(self._native.handle, int(bool(on))))
+
+  def layer_profile(self) -> dict:
+    """label -> dict(ms total, n intervals, macs per interval)."""
+    self._ensure_native()
+    out = {}
+    for i in range(lib.sntc_profile_count(self._native.handle)):
+      name, ms, n, macs = C.c_char_p(), C.c_float(), C.c_int(), C.c_double()
+      check(lib.sntc_profile_get(self._native.handle, i, C.byref(name), C.byref(ms), C.byref(n), C.byref(macs)))
+      out[name.value.decode()] = dict(ms=float(ms.value), n=int(n.value), macs=float(macs.value))
+    return out
+
   def hyper_synthesis(self, z_hat, out=None):
     """self._hyper_synthesis(z_hat) (mshyper/models.py:273) -> [B, hy, wy, 2*Cy] = mu || raw sigma."""
     self._ensure_native()
@@ -250,7 +265,13 @@ class FactorizedModel(Model):
     kw.pop("hyperprior", None)
     super().__init__(transform_config, hyperprior=False, **kw)
 
-  def decompress(self, q_y, image_hw, **kw):
+  def decompress(self, *args, **kw):
+    """decompress(q_y, image_hw, ...) -- also accepts the mshyper form decompress(None, q_y, image_hw, ...)."""
+    if len(args) == 3:
+      if args[0] is not None:
+        raise ValueError("the factorized model takes no z_hat")
+      args = args[1:]
+    q_y, image_hw = args
     return super().decompress(None, q_y, image_hw, **kw)
 
 

@@ -9,7 +9,7 @@ from oracle import ntc_oracle as O
 # tie margin |i_c - (k + .5)| < IDX_MARGIN * max(1, i_c)
 RECON_TOL = 1e-3
 PSNR_TOL = 0.01
-IDX_MARGIN = 1e-3
+IDX_MARGIN = {"fp32": 5e-5, "tc": 2e-4}   # relative to max(1, i_c): d i_c = i_c * d raw_sigma
 MU_TOL = 1e-4
 
 
@@ -43,7 +43,7 @@ def oracle_decode(model, wts, z, q, H, W, original=None, dtype=np.float64, gemm_
   return O.factorized_decode(wts, cls, q, H, W, kw, original, dtype, gemm_form)
 
 
-def check_against_oracle(got, ref, hyper=True, recon_tol=RECON_TOL):
+def check_against_oracle(got, ref, hyper=True, recon_tol=RECON_TOL, precision="fp32"):
   """The correctness gates of SURVEY 8(d).  Returns a dict of measured deviations."""
   rep = {}
   err = np.abs(got["float"].astype(np.float64) - ref["recon"])
@@ -58,12 +58,12 @@ def check_against_oracle(got, ref, hyper=True, recon_tol=RECON_TOL):
     mu_err = np.abs(got["y_hat"].astype(np.float64) - ref["y_hat"].astype(np.float64))
     rep["yhat_max_abs"] = float(mu_err.max())
     assert rep["yhat_max_abs"] < MU_TOL * np.maximum(1.0, np.abs(ref["y_hat"]).max() / 64), rep
-    margin = IDX_MARGIN * np.maximum(1.0, ref["i_c"])
+    margin = IDX_MARGIN[precision] * np.maximum(1.0, ref["i_c"])
     far = ref["idx_dist"] > margin
     rep["idx_in_margin"] = int((~far).sum())
     rep["idx_mismatch_outside_margin"] = int((got["idx"][far] != ref["idx"][far]).sum())
     rep["idx_mismatch_in_margin"] = int((got["idx"][~far] != ref["idx"][~far]).sum())
     assert rep["idx_mismatch_outside_margin"] == 0, rep
-    assert rep["idx_in_margin"] < 0.01 * far.size, rep
+    assert rep["idx_in_margin"] < 0.02 * far.size, rep
     assert np.abs(got["idx"].astype(int) - ref["idx"].astype(int)).max() <= 1, "a boundary flip moves the row by at most one"
   return rep
