@@ -587,60 +587,134 @@ static int run_gdn_f32(sntc_ctx* ctx, const GdnLayer& g, const float* in, size_t
   return launch_band_gemm(ctx, P, s);
 }
 
-// Runs `t` on `in` [B,h,w,Cin].  Intermediates ping-pong in the model workspace.  The final op writes
-// to fin (pixel epilogue) and/or fin->full.
-static int run_transform_f32(sntc_model* m, Transform& t, const float* in, int B, int h, int w, const FinalOut* fin, cudaStream_t s) {
+// What the executor currently holds: an fp32 tensor and/or its fp16 hi/lo planes.
+struct Cur { const float* f32 = nullptr; const __half* hi = nullptr; const __half* lo = nullptr; };
+
+// Fusion of the entropy-model glue into the last hyper-synthesis GEMM (tensor-core path only).
+struct HyperFuse {
+  const void* q = nullptr; int q_kind = 0; int Cy = 0; float max_index = 63.f; bool trunc = false;
+  float* y_hat = nullptr; uint8_t* idx = nullptr;
+  bool done = false; const __half* yh_hi = nullptr; const __half* yh_lo = nullptr;   // out: planes of y_hat
+};
+
+static bool op_on_tc(sntc_model* m, Transform& t, bool is_hyper, size_t i) {
+  if (m->desc.precision != SNTC_PRECISION_TC_F16X3) return false;
+  const Op& op = t.ops[i];
+  if (op.type != OP_CONVT) return false;
+  const std::vector<TcConv>& tc = is_hyper ? m->tc.hyper : m->tc.syn;
+  return op.conv < (int)tc.size() && tc[op.conv].ok;
+}
+
+// Runs `t` on `cur` [B,h,w,Cin].  Conv layers run on the tensor cores when the model was created with
+// SNTC_PRECISION_TC_F16X3 (and the layer is TMA-addressable), otherwise on the fp32 CUDA-core kernels;
+// pointwise stages and the tiny final conv always run on CUDA cores.  Intermediates ping-pong in the
+// model workspace.  The final op writes to fin (pixel epilogue / fin->full) or, for the hyper transform
+// with `hf`, straight into y_hat / idx.
+static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, int B, int h, int w, const FinalOut* fin,
+                         HyperFuse* hf, cudaStream_t s) {
   sntc_ctx* ctx = m->ctx;
-  // workspace sizing
-  size_t maxbytes = 0;
+  size_t max_f32 = 0, max_pl = 0;
   {
     int ch = h, cw = w;
-    for (auto& op : t.ops) {
+    for (size_t i = 0; i < t.ops.size(); ++i) {
+      const Op& op = t.ops[i];
       if (op.type == OP_CONVT || op.type == OP_CONVT_RGB) {
         const ConvLayer& c = t.convs[op.conv];
-        if (c.append_ones) maxbytes = std::max(maxbytes, (size_t)B * ch * cw * c.cin_pad * 4);
+        if (c.append_ones) max_f32 = std::max(max_f32, (size_t)B * ch * cw * c.cin_pad * 4);
+        if (op_on_tc(m, t, is_hyper, i)) max_pl = std::max(max_pl, (size_t)B * ch * cw * c.cin * 2);
         ch *= c.s; cw *= c.s;
-        maxbytes = std::max(maxbytes, (size_t)B * ch * cw * c.cout * 4);
+        max_f32 = std::max(max_f32, (size_t)B * ch * cw * c.cout * 4);
+        max_pl = std::max(max_pl, (size_t)B * ch * cw * c.cout * 2);
       }
     }
   }
-  TRY(m->ws_a.ensure(maxbytes));
-  TRY(m->ws_b.ensure(maxbytes));
-  const float* cur = in;
+  TRY(m->ws_a.ensure(max_f32));
+  TRY(m->ws_b.ensure(max_f32));
+  const bool any_tc = m->desc.precision == SNTC_PRECISION_TC_F16X3;
+  if (any_tc)
+    for (auto& pb : m->tc.plane)
+      if (!pb.ensure(max_pl)) return fail(SNTC_E_CUDA, "cudaMalloc failed for the fp16 activation planes");
   int ch = h, cw = w, cc = t.in_channels;
-  int flip = 0;
+  int flip = 0, pflip = 0;
   auto next_buf = [&]() { float* p = (float*)(flip ? m->ws_b.p : m->ws_a.p); flip ^= 1; return p; };
+  auto next_planes = [&](__half** hi, __half** lo) { *hi = (__half*)m->tc.plane[pflip * 2].p; *lo = (__half*)m->tc.plane[pflip * 2 + 1].p; pflip ^= 1; };
   for (size_t i = 0; i < t.ops.size(); ++i) {
     Op& op = t.ops[i];
-    bool last = i + 1 == t.ops.size();
+    const bool last = i + 1 == t.ops.size();
     if (op.type == OP_CONVT || op.type == OP_CONVT_RGB) {
       const ConvLayer& c = t.convs[op.conv];
+      std::string lbl = c.sources[0].kernel.substr(0, c.sources[0].kernel.size() - 7);
+      if (op_on_tc(m, t, is_hyper, i)) {
+        // ---- tensor-core band GEMM ----
+        if (!cur.hi) {   // first tensor-core layer of a chain: split the fp32 input into fp16 planes
+          if (!cur.f32) return fail(SNTC_E_STATE, "executor: no input for the tensor-core layer");
+          __half *hi, *lo;
+          next_planes(&hi, &lo);
+          size_t n8 = (size_t)B * ch * cw * c.cin / 8;
+          ProfScope ps(m, s, lbl + ".split_input", 0);
+          split_planes_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>(cur.f32, hi, lo, n8);
+          ctx->launches++;
+          CU_TRY(cudaGetLastError());
+          cur.hi = hi; cur.lo = lo;
+        }
+        const TcConv& tcv = (is_hyper ? m->tc.hyper : m->tc.syn)[op.conv];
+        TcConvOut o;
+        Cur nxt;
+        const bool next_tc = !last && op_on_tc(m, t, is_hyper, i + 1);
+        if (last && hf) {
+          o.hyper_final = true; o.q = hf->q; o.q_kind = hf->q_kind; o.Cy = hf->Cy; o.max_index = hf->max_index; o.trunc = hf->trunc;
+          o.y_hat = hf->y_hat; o.idx = hf->idx;
+          size_t pl = (size_t)B * ch * c.s * cw * c.s * hf->Cy * 2;
+          if (!m->tc.yh[0].ensure(pl) || !m->tc.yh[1].ensure(pl)) return fail(SNTC_E_CUDA, "cudaMalloc failed for the y_hat planes");
+          o.hi = (__half*)m->tc.yh[0].p; o.lo = (__half*)m->tc.yh[1].p;
+          hf->done = true; hf->yh_hi = o.hi; hf->yh_lo = o.lo;
+        } else if (last) {
+          if (fin) { o.f32 = fin->full; o.u8 = fin->u8; o.crop = fin->crop; o.H = fin->H; o.W = fin->W; }
+        } else if (next_tc) {
+          __half *hi, *lo;
+          next_planes(&hi, &lo);
+          o.hi = hi; o.lo = lo; nxt.hi = hi; nxt.lo = lo;
+        } else {
+          float* dst = next_buf();
+          o.f32 = dst; nxt.f32 = dst;
+        }
+        std::string err;
+        ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
+        if (tc_run_conv(ctx->tc, c, tcv, cur.hi, cur.lo, B, ch, cw, o, s, &ctx->launches, &err) != TC_OK)
+          return fail(SNTC_E_CUDA, "tensor-core path: " + err);
+        ch *= c.s; cw *= c.s; cc = c.cout;
+        cur = nxt;
+        continue;
+      }
+      // ---- fp32 CUDA-core kernels ----
+      if (!cur.f32) return fail(SNTC_E_STATE, "executor: fp32 layer follows a tensor-core layer that produced planes only");
       if (c.append_ones) {
         float* tmp = next_buf();
         size_t n = (size_t)B * ch * cw * c.cin_pad;
-        append_ones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cur, c.cin, tmp, c.cin_pad, (size_t)B * ch * cw);
+        append_ones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cur.f32, c.cin, tmp, c.cin_pad, (size_t)B * ch * cw);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
-        cur = tmp;
+        cur.f32 = tmp;
       }
       float* dst = last ? (fin ? fin->full : nullptr) : next_buf();
-      std::string lbl = c.sources[0].kernel.substr(0, c.sources[0].kernel.size() - 7);
       ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
-      if (op.type == OP_CONVT) TRY(run_conv_f32(ctx, c, cur, B, ch, cw, dst, last ? fin : nullptr, s));
-      else TRY(run_rgb_f32(ctx, c, cur, B, ch, cw, fin, s));
+      if (op.type == OP_CONVT) TRY(run_conv_f32(ctx, c, cur.f32, B, ch, cw, dst, last ? fin : nullptr, s));
+      else TRY(run_rgb_f32(ctx, c, cur.f32, B, ch, cw, fin, s));
       ch *= c.s; cw *= c.s; cc = c.cout;
-      cur = dst;
+      cur = Cur{}; cur.f32 = dst;
     } else if (op.type == OP_GDN) {
+      if (!cur.f32) return fail(SNTC_E_STATE, "executor: GDN needs an fp32 input");
       float* dst = next_buf();
       const GdnLayer& gl = t.gdns[op.gdn];
       ProfScope ps(m, s, gl.beta.substr(0, gl.beta.size() - 5), (double)B * ch * cw * gl.C * gl.C);
-      TRY(run_gdn_f32(ctx, gl, cur, (size_t)B * ch * cw, dst, s));
-      cur = dst;
+      TRY(run_gdn_f32(ctx, gl, cur.f32, (size_t)B * ch * cw, dst, s));
+      cur = Cur{}; cur.f32 = dst;
     } else if (op.type == OP_ACT_RES) {
+      if (!cur.f32) return fail(SNTC_E_STATE, "executor: activation stage needs an fp32 input");
       int C = cc / 2;
       float* dst = next_buf();
       ActResParams P{};
-      P.in = cur; P.in_stride = cc; P.out = dst; P.npix = (size_t)B * ch * cw; P.C = C; P.act = op.act; P.has_res = 1;
+      P.in = cur.f32; P.in_stride = cc; P.out = dst; P.npix = (size_t)B * ch * cw; P.C = C; P.act = op.act; P.has_res = 1;
       if (op.gdn >= 0) { const GdnLayer& g = t.gdns[op.gdn]; P.beta = g.d_beta; P.gamma = g.d_gamma; P.gamma_stride = g.Npad; P.inverse = g.inverse; }
       if (C > 64) return fail(SNTC_E_UNSUPPORTED, "two-layer hidden width > 64");
       ProfScope ps(m, s, "synthesis.activation+res", (double)P.npix * C * C);
@@ -648,21 +722,10 @@ static int run_transform_f32(sntc_model* m, Transform& t, const float* in, int B
       act_res_kernel<<<(unsigned)((P.npix + 127) / 128), 128, smem, s>>>(P);
       ctx->launches++;
       CU_TRY(cudaGetLastError());
-      cur = dst; cc = C;
+      cur = Cur{}; cur.f32 = dst; cc = C;
     }
   }
   return SNTC_OK;
-}
-
-static int run_transform(sntc_model* m, Transform& t, bool is_hyper, const float* in, int B, int h, int w, const FinalOut* fin, cudaStream_t s) {
-  if (m->desc.precision == SNTC_PRECISION_TC_F16X3) {
-    std::string err;
-    int r = tc_run_transform(m->ctx->tc, m->tc, t, is_hyper, in, B, h, w, fin ? fin->full : nullptr, fin ? fin->u8 : nullptr,
-                             fin ? fin->crop : nullptr, fin ? fin->H : 0, fin ? fin->W : 0, s, &m->ctx->launches, &err);
-    if (r == TC_OK) return SNTC_OK;
-    if (r != TC_NOT_HANDLED) return fail(SNTC_E_CUDA, "tensor-core path: " + err);
-  }
-  return run_transform_f32(m, t, in, B, h, w, fin, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -682,7 +745,7 @@ extern "C" int sntc_hyper_synthesis(sntc_model* m, const sntc_tensor* z_hat, snt
   TRY(stage_in(m, z_hat, tensor_elems(z_hat) * 4, m->st_z, s, &dz));
   TRY(stage_out(m, out, tensor_elems(out) * 4, m->d_hs, &dout));
   FinalOut fin; fin.full = (float*)dout;
-  TRY(run_transform(m, m->hyper, true, (const float*)dz, B, h, w, &fin, s));
+  { Cur c0; c0.f32 = (const float*)dz; TRY(run_transform(m, m->hyper, true, c0, B, h, w, &fin, nullptr, s)); }
   TRY(unstage_out(out, tensor_elems(out) * 4, dout, s, &need_sync));
   if (need_sync) CU_TRY(cudaStreamSynchronize(s));
   return SNTC_OK;
@@ -704,7 +767,7 @@ extern "C" int sntc_synthesis(sntc_model* m, const sntc_tensor* y_hat, sntc_tens
   TRY(stage_in(m, y_hat, tensor_elems(y_hat) * 4, m->st_q, s, &dy));
   TRY(stage_out(m, out, tensor_elems(out) * 4, m->st_f32, &dout));
   FinalOut fin; fin.full = (float*)dout;
-  TRY(run_transform(m, m->syn, false, (const float*)dy, B, h, w, &fin, s));
+  { Cur c0; c0.f32 = (const float*)dy; TRY(run_transform(m, m->syn, false, c0, B, h, w, &fin, nullptr, s)); }
   TRY(unstage_out(out, tensor_elems(out) * 4, dout, s, &need_sync));
   if (need_sync) CU_TRY(cudaStreamSynchronize(s));
   return SNTC_OK;
@@ -769,20 +832,28 @@ extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_t
   else { TRY(m->d_yhat.ensure(n_lat * 4)); d_yhat = m->d_yhat.p; }
 
   CU_TRY(cudaEventRecord(m->ev[0], s));
+  Cur ycur;
   if (m->has_hyper) {
-    TRY(m->d_hs.ensure(n_lat * 2 * 4));
     bool fused = false;
-    if (m->desc.precision == SNTC_PRECISION_TC_F16X3) {
-      // tensor-core path fuses split/exp/clamp/round and q + mu into the last hyper-synthesis GEMM
-      std::string err;
-      int r = tc_run_hyper_fused(ctx->tc, m->tc, m->hyper, (const float*)d_z, B, hz, wz, d_q, q_kind, (float*)d_yhat, (uint8_t*)d_idx,
-                                 (float)(m->desc.num_scales - 1), m->desc.index_rounding == SNTC_INDEX_TRUNC, s, &ctx->launches, &err);
-      if (r == TC_OK) fused = true;
-      else if (r != TC_NOT_HANDLED) return fail(SNTC_E_CUDA, "tensor-core path: " + err);
+    const bool tc = m->desc.precision == SNTC_PRECISION_TC_F16X3;
+    if (tc && op_on_tc(m, m->hyper, true, m->hyper.ops.size() - 1)) {
+      // tensor-core path: split/exp/clamp/round and q + mu are the epilogue of the last hyper-synthesis GEMM
+      HyperFuse hf;
+      hf.q = d_q; hf.q_kind = q_kind; hf.Cy = Cy; hf.max_index = (float)(m->desc.num_scales - 1);
+      hf.trunc = m->desc.index_rounding == SNTC_INDEX_TRUNC;
+      const bool syn_tc = op_on_tc(m, m->syn, false, 0);
+      hf.y_hat = (out_yhat || !syn_tc) ? (float*)d_yhat : nullptr;   // fp32 y_hat only if someone reads it
+      hf.idx = (uint8_t*)d_idx;
+      Cur c0; c0.f32 = (const float*)d_z;
+      TRY(run_transform(m, m->hyper, true, c0, B, hz, wz, nullptr, &hf, s));
+      fused = hf.done;
+      if (fused) { ycur.f32 = hf.y_hat; ycur.hi = hf.yh_hi; ycur.lo = hf.yh_lo; }
     }
     if (!fused) {
+      TRY(m->d_hs.ensure(n_lat * 2 * 4));
       FinalOut fin; fin.full = (float*)m->d_hs.p;
-      TRY(run_transform(m, m->hyper, true, (const float*)d_z, B, hz, wz, &fin, s));
+      Cur c0; c0.f32 = (const float*)d_z;
+      TRY(run_transform(m, m->hyper, true, c0, B, hz, wz, &fin, nullptr, s));
       CU_TRY(cudaEventRecord(m->ev[1], s));
       ProfScope ps(m, s, "dequant_index", 0);
       DequantParams P{};
@@ -793,6 +864,7 @@ extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_t
       dequant_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(P);
       ctx->launches++;
       CU_TRY(cudaGetLastError());
+      ycur.f32 = (const float*)d_yhat;
     } else {
       CU_TRY(cudaEventRecord(m->ev[1], s));
     }
@@ -805,11 +877,12 @@ extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_t
       ctx->launches++;
       CU_TRY(cudaGetLastError());
     }
+    ycur.f32 = (const float*)d_yhat;
   }
   CU_TRY(cudaEventRecord(m->ev[2], s));
   {
     FinalOut fin; fin.u8 = (uint8_t*)d_u8; fin.crop = (float*)d_f32; fin.H = H; fin.W = W;
-    TRY(run_transform(m, m->syn, false, (const float*)d_yhat, B, hy, wy, &fin, s));
+    TRY(run_transform(m, m->syn, false, ycur, B, hy, wy, &fin, nullptr, s));
   }
   if (original_u8) {
     TRY(m->d_ssd.ensure((size_t)B * 8));

@@ -26,22 +26,26 @@ enum GdnKind { GDN_NONE = 0, GDN_1 = 1 /* beta + |x| gamma */, GDN_CLASSIC = 2 /
 
 struct Band1D {
   int phi0, nphi, T;   // phases [phi0, phi0+nphi), taps j in [0,T)
+  int mlo;             // first cell: outputs of phase phi sit at o = s*(mlo + i) + phi - p, i in [0, n_in)
 };
-
-inline std::vector<Band1D> bands_1d(int k, int s) {
-  std::vector<Band1D> out;
-  for (int phi = 0; phi < s; ++phi) {
-    int T = phi < k ? (k - phi + s - 1) / s : 0;
-    if (!out.empty() && out.back().T == T) out.back().nphi++;
-    else out.push_back({phi, 1, T});
-  }
-  return out;
-}
 
 inline int ceil_div_floor(int a, int b) {  // ceil(a/b) for b>0, any sign of a
   return a >= 0 ? (a + b - 1) / b : -((-a) / b);
 }
 inline int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+// Phases are grouped into a band when they share the tap count T AND the first cell mlo; every phase
+// owns exactly n_in outputs, so every band is a GEMM over exactly h*w cells per image (no ragged tiles).
+inline std::vector<Band1D> bands_1d(int k, int s, int p) {
+  std::vector<Band1D> out;
+  for (int phi = 0; phi < s; ++phi) {
+    int T = phi < k ? (k - phi + s - 1) / s : 0;
+    int mlo = std::max(0, ceil_div_floor(p - phi, s));
+    if (!out.empty() && out.back().T == T && out.back().mlo == mlo) out.back().nphi++;
+    else out.push_back({phi, 1, T, mlo});
+  }
+  return out;
+}
 
 struct Band {
   int phy0, nphy, Ty, phx0, nphx, Tx;
@@ -50,13 +54,11 @@ struct Band {
   // cell ranges for an input of n_in rows/cols are computed per call (depend on h, w)
 };
 
-// cell range [mlo, mlo+cnt) of a 1-D band for n_in input samples
+// cell range [mlo, mlo+cnt) of a 1-D band for n_in input samples: always exactly n_in cells
 inline void cell_range(const Band1D& b, int s, int p, int n_in, int* mlo, int* cnt) {
-  int lo = ceil_div_floor(p - (b.phi0 + b.nphi - 1), s);
-  if (lo < 0) lo = 0;
-  int hi = floor_div(s * n_in - 1 + p - b.phi0, s);
-  *mlo = lo;
-  *cnt = hi >= lo ? hi - lo + 1 : 0;
+  (void)s; (void)p;
+  *mlo = b.mlo;
+  *cnt = n_in;
 }
 
 struct ConvSource { std::string kernel, bias; int cout; };
@@ -112,8 +114,8 @@ inline int tfc_pad(int k) { return (k - 1) / 2; }
 
 inline void finish_conv(ConvLayer& c) {
   c.cin_pad = ((c.cin + (c.append_ones ? 1 : 0)) + 3) / 4 * 4;
-  c.by = bands_1d(c.k, c.s);
-  c.bx = bands_1d(c.k, c.s);
+  c.by = bands_1d(c.k, c.s, c.p);
+  c.bx = bands_1d(c.k, c.s, c.p);
   c.bands.clear();
   size_t off = 0;
   for (auto& y : c.by) for (auto& x : c.bx) {

@@ -11,6 +11,7 @@ RECON_TOL = 1e-3
 PSNR_TOL = 0.01
 IDX_MARGIN = {"fp32": 5e-5, "tc": 2e-4}   # relative to max(1, i_c): d i_c = i_c * d raw_sigma
 MU_TOL = 1e-4
+U8_FLIP_FRAC = {"fp32": 1e-3, "tc": 5e-3}
 
 
 def syn_kwargs(model):
@@ -52,7 +53,9 @@ def check_against_oracle(got, ref, hyper=True, recon_tol=RECON_TOL, precision="f
   d = np.abs(got["image"].astype(np.int16) - ref["recon_u8"].astype(np.int16))
   rep["u8_max_diff"] = int(d.max())
   rep["u8_frac_diff"] = float((d > 0).mean())
-  assert rep["u8_max_diff"] <= 1 and rep["u8_frac_diff"] < 1e-3, rep
+  # a pixel flips by one LSB iff its float value sits within the float error of a rounding boundary:
+  # expected fraction ~ 2 * 255 * mean|err| (fp32 path ~1e-4, split-fp16 tensor path a few 1e-3 on the deep decoders)
+  assert rep["u8_max_diff"] <= 1 and rep["u8_frac_diff"] < U8_FLIP_FRAC[precision], rep
   if hyper:
     # y_hat = q + mu is a single fp32 add: mu_gpu is recovered exactly as y_hat - q when |q| small
     mu_err = np.abs(got["y_hat"].astype(np.float64) - ref["y_hat"].astype(np.float64))

@@ -18,17 +18,19 @@ SMALL = [  # (config, B, H, W)
 ]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
 @pytest.mark.parametrize("kind", ["init", "stress"])
 @pytest.mark.parametrize("name,B,H,W", SMALL)
-def test_decode_matches_oracle_fp32(gpu_ctx, name, B, H, W, kind):
-  model, wts, z, q = make_case(name, B, H, W, kind, "fp32", gpu_ctx)
+def test_decode_matches_oracle(gpu_ctx, name, B, H, W, kind, precision):
+  """precision 'fp32' = CUDA-core FFMA kernels; 'tc' = tcgen05 split-fp16 (3-pass) kernels."""
+  model, wts, z, q = make_case(name, B, H, W, kind, precision, gpu_ctx)
   ref = oracle_decode(model, wts, z, q, H, W)
   orig = synthetic.make_original(ref["recon_u8"])
   ref_mse, ref_psnr = __import__("oracle.ntc_oracle", fromlist=["x"]).mse_psnr(orig, ref["recon_u8"])
   got = model.decompress(z, q, (H, W), return_float=True, return_yhat=True, original=orig)
-  rep = check_against_oracle(got, ref, hyper=model.hyperprior)
+  rep = check_against_oracle(got, ref, hyper=model.hyperprior, precision=precision)
   assert np.all(np.abs(got["psnr"] - ref_psnr) < PSNR_TOL), (got["psnr"], ref_psnr)
-  print(name, kind, rep)
+  print(name, kind, precision, rep)
 
 
 def test_yhat_is_bit_exact_single_add(gpu_ctx):
@@ -114,18 +116,44 @@ def test_argument_errors_are_loud(gpu_ctx):
   assert empty["image"].shape == (0, 64, 64, 3)
 
 
-def test_full_size_config2_properties(gpu_ctx):
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_full_size_config2_properties(gpu_ctx, precision):
   """BASELINE config 2 (two_layer_syn, 24 x 512x768): oracle on 2 of the 24 images + size-independent
   properties (shard independence, exact integer SSD / PSNR against a host recomputation)."""
   B, H, W = 24, 512, 768
-  model, wts, z, q = make_case("two_layer_syn", B, H, W, "stress", "fp32", gpu_ctx)
+  model, wts, z, q = make_case("two_layer_syn", B, H, W, "stress", precision, gpu_ctx)
   got = model.decompress(z, q, (H, W), return_float=True, return_yhat=True)
   for b in (0, 23):
     ref = oracle_decode(model, wts, z[b:b + 1], q[b:b + 1], H, W)
     sub = {k: v[b:b + 1] for k, v in got.items()}
-    print(b, check_against_oracle(sub, ref))
+    print(b, check_against_oracle(sub, ref, precision=precision))
+  shard = model.decompress(z[5:9], q[5:9], (H, W))
+  assert np.array_equal(shard["image"], got["image"][5:9]) and np.array_equal(shard["idx"], got["idx"][5:9])
   orig = synthetic.make_original(got["image"])
   m = model.decompress(z, q, (H, W), original=orig)
   ssd = ((m["image"].astype(np.int64) - orig.astype(np.int64)) ** 2).reshape(B, -1).sum(1)
   assert np.array_equal(m["ssd"].astype(np.int64), ssd)
   assert np.array_equal(m["image"], got["image"])
+
+
+@pytest.mark.parametrize("name,B,H,W", [("two_layer_syn", 2, 128, 192), ("jpegl", 1, 64, 128)])
+def test_tc_path_matches_fp32_path(gpu_ctx, name, B, H, W):
+  """The two GPU implementations agree with each other far inside the tolerance."""
+  m32, wts, z, q = make_case(name, B, H, W, "stress", "fp32", gpu_ctx)
+  mtc, _, _, _ = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
+  a = m32.decompress(z, q, (H, W), return_float=True, return_yhat=True)
+  b = mtc.decompress(z, q, (H, W), return_float=True, return_yhat=True)
+  assert np.abs(a["float"] - b["float"]).max() < 1e-4
+  assert np.abs(a["y_hat"] - b["y_hat"]).max() < 1e-3
+  assert (a["idx"] != b["idx"]).mean() < 1e-3
+  l0 = gpu_ctx.launch_count
+  mtc.decompress(z, q, (H, W))
+  assert gpu_ctx.launch_count > l0, "the tensor-core decode must launch libsntc kernels"
+
+
+def test_tc_hyper_transform_call(gpu_ctx):
+  from oracle import ntc_oracle as O
+  model, wts, z, q = make_case("two_layer_syn", 1, 64, 128, "stress", "tc", gpu_ctx)
+  hs = model.hyper_synthesis(z)
+  ref = O.hyper_synthesis(wts, z)
+  assert np.abs(hs - ref).max() < 2e-4
