@@ -217,34 +217,39 @@ def main():
   prof = model.layer_profile()
   clocks = sampler.stop()
 
-  # ---- e2e: pinned host buffers through the public API, copies inside the timed region ----
-  pin = [(ctx.pinned_like(z), ctx.pinned_like(q)) for z, q in sets[:2]]
-  out_host = dict(image=ctx.pinned_empty((B, H, W, 3), np.uint8), idx=ctx.pinned_empty(ys, np.uint8))
-  for i in range(2):
-    model.decompress(pin[i % 2][0], pin[i % 2][1], (H, W), out=out_host)
-  barrier()
-  f0, f1 = ctx.event(), ctx.event()
-  f0.record()
-  for i in range(args.steps):
-    model.decompress(pin[i % 2][0], pin[i % 2][1], (H, W), out=out_host)
-  f1.record()
-  ctx.sync()
-  ms_e2e = f0.elapsed_ms(f1)
-  h2d = int(sets[0][0].nbytes + sets[0][1].nbytes)
-  d2h = int(out_host["image"].nbytes + out_host["idx"].nbytes)
+  # ---- e2e: pinned HOST buffers through the public streaming API (DecodePipeline): every step uploads its
+  # symbols (H2D) and downloads image + index map (D2H) inside the timed region; copies overlap the decode of
+  # the neighbouring steps on separate streams ----
+  from shallow_ntc_b200 import DecodePipeline
+
+  def run_e2e(q_dtype):
+    pin = [(ctx.pinned_like(z), ctx.pinned_like(q.astype(q_dtype))) for z, q in sets[:2]]
+    outs = [dict(image=ctx.pinned_empty((B, H, W, 3), np.uint8), idx=ctx.pinned_empty(ys, np.uint8)) for _ in range(2)]
+    pipe = DecodePipeline(model, B, (H, W), q_dtype=q_dtype, depth=2)
+    for i in range(3):
+      pipe.submit(pin[i % 2][0], pin[i % 2][1], outs[i % 2]["image"], outs[i % 2]["idx"])
+    pipe.drain()
+    barrier()
+    f0, f1 = ctx.event(), ctx.event()
+    f0.record(pipe.s_in.handle)
+    for i in range(args.steps):
+      pipe.submit(pin[i % 2][0], pin[i % 2][1], outs[i % 2]["image"], outs[i % 2]["idx"])
+    f1.record(pipe.s_out.handle)
+    pipe.drain()
+    return f0.elapsed_ms(f1), int(pin[0][0].nbytes + pin[0][1].nbytes), int(outs[0]["image"].nbytes + outs[0]["idx"].nbytes), outs
+
+  ms_e2e, h2d, d2h, out_hosts = run_e2e(np.float32)
+  ms_e2e_i8, h2d_i8, _, _ = run_e2e(np.int8)
+  out_host = out_hosts[(args.steps - 1) % 2]
 
   # final quality sum over ranks (the only collective; NCCL all-reduce of 3 doubles)
   orig = synthetic.make_original(out_host["image"][:2], first_index=rank * B)
   met = model.decompress(sets[(args.steps - 1) % 2][0][:2], sets[(args.steps - 1) % 2][1][:2], (H, W), original=orig)
   qsum = np.array([met["psnr"].sum(), met["mse"].sum(), float(len(met["psnr"]))])
   if dist is not None:
-    import torch
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
-    tq = torch.tensor(qsum, dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(tq, op=dist.ReduceOp.SUM)
-    qsum = tq.cpu().numpy()
+    from shallow_ntc_b200 import parallel
+    ms, ms_e2e, ms_e2e_i8 = (float(v) for v in parallel.max_over_ranks(dist, [ms, ms_e2e, ms_e2e_i8], device=f"cuda:{local}"))
+    qsum = parallel.reduce_metric_sums(dist, qsum, device=f"cuda:{local}")     # NCCL: the only collective
 
   if rank == 0:
     px_step = world * B * H * W
@@ -268,7 +273,9 @@ def main():
                             layers_ms={k: round(v["ms"] / max(v["n"], 1), 4) for k, v in prof.items()},
                             mean_psnr_db=float(qsum[0] / qsum[2])),
                 clocks=clocks, gpu_launches=int(launches),
-                e2e=dict(value=e2e, unit="Mpx/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps),
+                e2e=dict(value=e2e, unit="Mpx/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
+                         api="DecodePipeline.submit (float32 symbols, pinned host buffers, depth 2)",
+                         int8_symbols=dict(value=px_step * args.steps / (ms_e2e_i8 * 1e-3) / 1e6, h2d_bytes_per_step=h2d_i8)),
                 roofline=roof)
     if world == 1 and not args.no_cpu_baseline:
       n_img = 2

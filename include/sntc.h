@@ -197,6 +197,12 @@ int sntc_memcpy_h2d(sntc_ctx* ctx, void* dst, const void* src, size_t bytes, voi
 int sntc_memcpy_d2h(sntc_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream);
 int sntc_memset(sntc_ctx* ctx, void* dst, int value, size_t bytes, void* stream);
 
+/* ---- extra streams for copy/compute overlap (the streaming decode pipeline) ---- */
+int sntc_stream_create(sntc_ctx* ctx, void** out);
+int sntc_stream_destroy(sntc_ctx* ctx, void* stream);
+int sntc_stream_wait_event(sntc_ctx* ctx, void* stream, void* event); /* stream == NULL: the context stream */
+int sntc_stream_sync(sntc_ctx* ctx, void* stream);
+
 /* ---- CUDA-event timers on the launching stream (bench.py) ---- */
 int sntc_event_create(sntc_ctx* ctx, void** out);
 int sntc_event_destroy(sntc_ctx* ctx, void* ev);

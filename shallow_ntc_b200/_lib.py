@@ -82,6 +82,10 @@ _PROTOS = {
   "sntc_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
   "sntc_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
   "sntc_memset": (C.c_int, [_P, _P, C.c_int, C.c_size_t, _P]),
+  "sntc_stream_create": (C.c_int, [_P, C.POINTER(_P)]),
+  "sntc_stream_destroy": (C.c_int, [_P, _P]),
+  "sntc_stream_wait_event": (C.c_int, [_P, _P, _P]),
+  "sntc_stream_sync": (C.c_int, [_P, _P]),
   "sntc_event_create": (C.c_int, [_P, C.POINTER(_P)]),
   "sntc_event_destroy": (C.c_int, [_P, _P]),
   "sntc_event_record": (C.c_int, [_P, _P, _P]),

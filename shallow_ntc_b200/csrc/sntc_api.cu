@@ -177,6 +177,32 @@ extern "C" int sntc_memset(sntc_ctx* ctx, void* dst, int value, size_t bytes, vo
   CU_TRY(cudaMemsetAsync(dst, value, bytes, pick_stream(ctx, stream)));
   return SNTC_OK;
 }
+extern "C" int sntc_stream_create(sntc_ctx* ctx, void** out) {
+  if (!ctx || !out) return fail(SNTC_E_INVALID, "sntc_stream_create: bad argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st;
+  CU_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *out = st;
+  return SNTC_OK;
+}
+extern "C" int sntc_stream_destroy(sntc_ctx* ctx, void* stream) {
+  if (!ctx || !stream) return fail(SNTC_E_INVALID, "sntc_stream_destroy: bad argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamDestroy((cudaStream_t)stream));
+  return SNTC_OK;
+}
+extern "C" int sntc_stream_wait_event(sntc_ctx* ctx, void* stream, void* event) {
+  if (!ctx || !event) return fail(SNTC_E_INVALID, "sntc_stream_wait_event: bad argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamWaitEvent(pick_stream(ctx, stream), (cudaEvent_t)event, 0));
+  return SNTC_OK;
+}
+extern "C" int sntc_stream_sync(sntc_ctx* ctx, void* stream) {
+  if (!ctx) return fail(SNTC_E_INVALID, "sntc_stream_sync: ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamSynchronize(pick_stream(ctx, stream)));
+  return SNTC_OK;
+}
 extern "C" int sntc_event_create(sntc_ctx* ctx, void** out) {
   if (!ctx || !out) return fail(SNTC_E_INVALID, "sntc_event_create: bad argument");
   CU_TRY(cudaSetDevice(ctx->device));
@@ -538,7 +564,34 @@ static int run_conv_f32(sntc_ctx* ctx, const ConvLayer& c, const float* in, int 
   return SNTC_OK;
 }
 
+template <int K, int PD, int C1, int TR>
+static int launch_tail(sntc_ctx* ctx, const ConvLayer& c, const float* in, int B, int h, int w, const FinalOut* fin, cudaStream_t s) {
+  constexpr int T = (K + 1) / 2, RY = 8;
+  constexpr int NY = ((PD + RY - 1) >> 1) - (PD >> 1) + T, NX = ((PD + 1) >> 1) - (PD >> 1) + T;
+  constexpr int TILE_Y = (RY / 2) * (TR - 1) + NY, TILE_X = 31 + NX;
+  TailParams Q{};
+  Q.x = in; Q.B = B; Q.hin = h; Q.win = w; Q.w = c.d_w_rgb; Q.bias = c.d_bias;
+  Q.hout = 2 * h; Q.wout = 2 * w;
+  if (fin) { Q.out = fin->full; Q.out_u8 = fin->u8; Q.out_crop = fin->crop; Q.H = fin->H; Q.W = fin->W; }
+  size_t smem = ((size_t)TILE_Y * TILE_X * C1 + (size_t)K * K * C1 * 4) * 4;
+  static bool attr_done = false;
+  if (!attr_done && smem > 48 * 1024) {
+    CU_TRY(cudaFuncSetAttribute(tail_s2_kernel<K, PD, C1, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((Q.wout + 63) / 64, (Q.hout + RY * TR - 1) / (RY * TR), B);
+  tail_s2_kernel<K, PD, C1, TR><<<grid, 32 * TR, smem, s>>>(Q);
+  ctx->launches++;
+  CU_TRY(cudaGetLastError());
+  return SNTC_OK;
+}
+
 static int run_rgb_f32(sntc_ctx* ctx, const ConvLayer& c, const float* in, int B, int h, int w, const FinalOut* fin, cudaStream_t s) {
+  if (c.s == 2 && c.k == 5 && c.p == 1 && c.cout == 3 && c.cin == c.cin_pad) {   // the two-layer tail (Keras k5 s2)
+    if (c.cin == 12) return launch_tail<5, 1, 12, 4>(ctx, c, in, B, h, w, fin, s);
+    if (c.cin == 24) return launch_tail<5, 1, 24, 2>(ctx, c, in, B, h, w, fin, s);
+    if (c.cin == 48) return launch_tail<5, 1, 48, 2>(ctx, c, in, B, h, w, fin, s);
+  }
   RgbCellParams P{};
   P.x = in; P.B = B; P.hin = h; P.win = w; P.cin = c.cin_pad; P.w = c.d_w_rgb; P.bias = c.d_bias;
   P.cout = c.cout; P.k = c.k; P.s = c.s; P.p = c.p;
@@ -657,9 +710,10 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
           CU_TRY(cudaGetLastError());
           cur.hi = hi; cur.lo = lo;
         }
-        const TcConv& tcv = (is_hyper ? m->tc.hyper : m->tc.syn)[op.conv];
+        TcConv& tcv = (is_hyper ? m->tc.hyper : m->tc.syn)[op.conv];
         TcConvOut o;
         Cur nxt;
+        bool skip_next = false;
         const bool next_tc = !last && op_on_tc(m, t, is_hyper, i + 1);
         if (last && hf) {
           o.hyper_final = true; o.q = hf->q; o.q_kind = hf->q_kind; o.Cy = hf->Cy; o.max_index = hf->max_index; o.trunc = hf->trunc;
@@ -670,6 +724,22 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
           hf->done = true; hf->yh_hi = o.hi; hf->yh_lo = o.lo;
         } else if (last) {
           if (fin) { o.f32 = fin->full; o.u8 = fin->u8; o.crop = fin->crop; o.H = fin->H; o.W = fin->W; }
+        } else if (tcv.fused_two_layer) {
+          // the pointwise stage that follows (IGDN / activation, + residual) is this GEMM's epilogue
+          const Op& nx = t.ops[i + 1];
+          o.two_layer = true;
+          o.has_res = nx.type == OP_ACT_RES;
+          o.C1 = o.has_res ? c.cout / 2 : c.cout;
+          if (nx.gdn >= 0) {
+            const GdnLayer& g = t.gdns[nx.gdn];
+            o.gamma = g.d_gamma; o.gamma_stride = g.Npad; o.beta = g.d_beta; o.tl_inverse = g.inverse;
+            o.tl_act = g.inverse ? SNTC_ACT_IGDN1 : SNTC_ACT_GDN1;
+          } else {
+            o.tl_act = nx.act;
+          }
+          float* dst = next_buf();
+          o.f32 = dst; nxt.f32 = dst;
+          skip_next = true;
         } else if (next_tc) {
           __half *hi, *lo;
           next_planes(&hi, &lo);
@@ -679,11 +749,12 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
           o.f32 = dst; nxt.f32 = dst;
         }
         std::string err;
-        ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
+        ProfScope ps(m, s, skip_next ? lbl + "+activation" : lbl, conv_macs(c, B, ch, cw));
         if (tc_run_conv(ctx->tc, c, tcv, cur.hi, cur.lo, B, ch, cw, o, s, &ctx->launches, &err) != TC_OK)
           return fail(SNTC_E_CUDA, "tensor-core path: " + err);
         ch *= c.s; cw *= c.s; cc = c.cout;
         cur = nxt;
+        if (skip_next) { cc = o.C1; ++i; }
         continue;
       }
       // ---- fp32 CUDA-core kernels ----

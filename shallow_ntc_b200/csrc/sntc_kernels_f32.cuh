@@ -299,6 +299,125 @@ __global__ void __launch_bounds__(128) convt_rgb_cell_kernel(const RgbCellParams
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tail of the two-layer synthesis: stride-2 transposed conv C1 -> 3 with the fused crop + uint8 epilogue
+// (common/transforms.py:311-313, 350-353 + image_utils.py:22-23, 69-71).  HBM-class: reads t once, writes the
+// image once.  One thread = 4 (y) x 2 (x) output pixels; the input tile and the weights sit in shared
+// memory; every tap index is a compile-time constant (a = (P&1) + d + 2(T-1) - 2i).
+struct TailParams {
+  const float* x; int B, hin, win;          // t [B,hin,win,C1]
+  const float* w;                            // [K*K][C1][4]
+  const float* bias;
+  float* out; int hout, wout;                // optional f32 [B,hout,wout,3]
+  uint8_t* out_u8; float* out_crop; int H, W;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <int K, int P, int C1, int TR>
+__global__ void __launch_bounds__(32 * TR) tail_s2_kernel(const TailParams Q) {
+  constexpr int T = (K + 1) / 2;
+  constexpr int RY = 8, TCX = 32;                                  // one thread = 8 (y) x 2 (x) output pixels; 32 x TR threads
+  constexpr int NT = TCX * TR;
+  constexpr int NY = ((P + RY - 1) >> 1) - (P >> 1) + T, NX = ((P + 1) >> 1) - (P >> 1) + T;
+  constexpr int TILE_Y = (RY / 2) * (TR - 1) + NY, TILE_X = (TCX - 1) + NX;
+  extern __shared__ __align__(16) float sm_tail[];
+  float* sx = sm_tail;                                             // [TILE_Y][TILE_X][C1]
+  float* sw = sm_tail + TILE_Y * TILE_X * C1;                      // [K*K][C1][4]
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * (RY * TR), ox0 = blockIdx.x * (2 * TCX);
+  const int ny0 = oy0 / 2 + (P >> 1) - (T - 1), nx0 = ox0 / 2 + (P >> 1) - (T - 1);
+  const float* img = Q.x + (size_t)b * Q.hin * Q.win * C1;
+  // global -> shared with cp.async (16 B per request, zero-filled outside the image): all requests of a
+  // thread are in flight together instead of one dependent load/store pair per loop trip
+  for (int i = threadIdx.x; i < TILE_Y * TILE_X * (C1 / 4); i += NT) {
+    int c4 = i % (C1 / 4), px = i / (C1 / 4);
+    int tx = px % TILE_X, ty = px / TILE_X;
+    int ny = ny0 + ty, nx = nx0 + tx;
+    const bool ok = ny >= 0 && ny < Q.hin && nx >= 0 && nx < Q.win;
+    const float* src = ok ? img + ((size_t)ny * Q.win + nx) * C1 + c4 * 4 : img;
+    cp_async16(sx + (size_t)px * C1 + c4 * 4, src, ok ? 16 : 0);
+  }
+  for (int i = threadIdx.x; i < K * K * C1; i += NT) cp_async16(sw + (size_t)i * 4, Q.w + (size_t)i * 4, 16);
+  cp_async_wait_all();
+  __syncthreads();
+  const int ti = threadIdx.x % TCX, tr = threadIdx.x / TCX;
+  float acc[RY][2][3];
+#pragma unroll
+  for (int dy = 0; dy < RY; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) { acc[dy][dx][0] = 0.f; acc[dy][dx][1] = 0.f; acc[dy][dx][2] = 0.f; }
+  const float* tbase = sx + ((size_t)((RY / 2) * tr) * TILE_X + ti) * C1;
+  // taps outermost: each weight vector feeds the RY/2 output rows of its phase; all indices are compile-time
+#pragma unroll
+  for (int ay = 0; ay < K; ++ay) {
+#pragma unroll
+    for (int ax = 0; ax < K; ++ax) {
+      const int dx = ((ax - P) % 2 + 2) % 2;                       // the output column of this thread with phase ax
+      const int ix = (dx + P - ax) / 2 - (P >> 1) + (T - 1);
+      const int dy0 = ((ay - P) % 2 + 2) % 2;
+#pragma unroll 1
+      for (int c = 0; c < C1; c += 4) {
+        const float* wp = sw + ((size_t)(ay * K + ax) * C1 + c) * 4;
+        const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+        const float4 w2 = *reinterpret_cast<const float4*>(wp + 8), w3 = *reinterpret_cast<const float4*>(wp + 12);
+#pragma unroll
+        for (int e = 0; e < RY / 2; ++e) {
+          const int dy = dy0 + 2 * e;
+          const int iy = (dy + P - ay) / 2 - (P >> 1) + (T - 1);
+          const float4 xv = *reinterpret_cast<const float4*>(tbase + ((size_t)iy * TILE_X + ix) * C1 + c);
+          float* a = acc[dy][dx];
+          a[0] = fmaf(xv.x, w0.x, a[0]); a[1] = fmaf(xv.x, w0.y, a[1]); a[2] = fmaf(xv.x, w0.z, a[2]);
+          a[0] = fmaf(xv.y, w1.x, a[0]); a[1] = fmaf(xv.y, w1.y, a[1]); a[2] = fmaf(xv.y, w1.z, a[2]);
+          a[0] = fmaf(xv.z, w2.x, a[0]); a[1] = fmaf(xv.z, w2.y, a[1]); a[2] = fmaf(xv.z, w2.z, a[2]);
+          a[0] = fmaf(xv.w, w3.x, a[0]); a[1] = fmaf(xv.w, w3.y, a[1]); a[2] = fmaf(xv.w, w3.z, a[2]);
+        }
+      }
+    }
+  }
+  const float b0 = __ldg(Q.bias), b1 = __ldg(Q.bias + 1), b2 = __ldg(Q.bias + 2);
+#pragma unroll
+  for (int dy = 0; dy < RY; ++dy) {
+    const int oy = oy0 + RY * tr + dy;
+    if (oy >= Q.hout) continue;
+    const int ox = ox0 + 2 * ti;
+    if (ox >= Q.wout) continue;
+    float v[2][3];
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) { v[dx][0] = acc[dy][dx][0] + b0; v[dx][1] = acc[dy][dx][1] + b1; v[dx][2] = acc[dy][dx][2] + b2; }
+    if (Q.out) {
+      float* o = Q.out + (((size_t)b * Q.hout + oy) * Q.wout + ox) * 3;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) if (ox + dx < Q.wout) { o[dx * 3] = v[dx][0]; o[dx * 3 + 1] = v[dx][1]; o[dx * 3 + 2] = v[dx][2]; }
+    }
+    if (oy < Q.H) {
+      if (Q.out_u8) {
+        uint8_t* o = Q.out_u8 + (((size_t)b * Q.H + oy) * Q.W + ox) * 3;
+        if (ox + 1 < Q.W && ((Q.W * 3) % 2 == 0)) {     // 6 contiguous bytes, 2-byte aligned: three 16-bit stores
+          const uint8_t p0 = float_to_pixel(v[0][0]), p1 = float_to_pixel(v[0][1]), p2 = float_to_pixel(v[0][2]);
+          const uint8_t p3 = float_to_pixel(v[1][0]), p4 = float_to_pixel(v[1][1]), p5 = float_to_pixel(v[1][2]);
+          uint16_t* o16 = reinterpret_cast<uint16_t*>(o);
+          o16[0] = (uint16_t)(p0 | (p1 << 8)); o16[1] = (uint16_t)(p2 | (p3 << 8)); o16[2] = (uint16_t)(p4 | (p5 << 8));
+        } else {
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) if (ox + dx < Q.W) { o[dx * 3] = float_to_pixel(v[dx][0]); o[dx * 3 + 1] = float_to_pixel(v[dx][1]); o[dx * 3 + 2] = float_to_pixel(v[dx][2]); }
+        }
+      }
+      if (Q.out_crop) {
+        float* o = Q.out_crop + (((size_t)b * Q.H + oy) * Q.W + ox) * 3;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) if (ox + dx < Q.W) { o[dx * 3] = v[dx][0]; o[dx * 3 + 1] = v[dx][1]; o[dx * 3 + 2] = v[dx][2]; }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // mshyper/models.py:274-279: split, exp, clamp, round -> idx ; y_hat = q + mu.
 // hs: [P, 2*C] (mu || raw_sigma).  q may be f32 / i16 / i8.  One thread per 4 channels.
 struct DequantParams {

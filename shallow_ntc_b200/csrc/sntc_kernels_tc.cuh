@@ -26,19 +26,30 @@
 namespace sntc {
 
 enum { TC_OK = 0, TC_NOT_HANDLED = 1, TC_ERROR = 2 };
-enum { TC_EPI_PLAIN = 0, TC_EPI_HYPER_FINAL = 1 };
+enum { TC_EPI_PLAIN = 0, TC_EPI_HYPER_FINAL = 1, TC_EPI_TWO_LAYER = 2 };
 
-constexpr int TC_BM = 128;      // cells per tile (UMMA M)
-constexpr int TC_BK = 64;       // fp16 channels per k-block (128 bytes = one swizzle row)
+constexpr int TC_BM = 128;        // cells per tile (UMMA M)
+constexpr int TC_BK = 64;         // fp16 channels per k-block (128 bytes = one swizzle row)
 constexpr int TC_THREADS = 256;
+constexpr int TC_ACC_COLS = 256;  // TMEM columns per accumulator buffer (two buffers = all 512 columns)
+constexpr int TC_MAX_BANDS = 16;
+
+// One band of a layer, resident in device memory (tensor maps must be 64-byte aligned).
+struct alignas(64) TcBandDev {
+  CUtensorMap mapBhi, mapBlo;     // packed K-major band matrix, hi / lo fp16 planes
+  int phy0, nphx, phx0, Ty, Tx, mloy, mlox;
+  int N, BN, ntiles;
+  int item_begin;                 // first work item (m-tile, n-tile) of this band in the layer's item list
+  int pad_[5];
+};
 
 struct TcParams {
-  int B, hin, win;
-  int s, p, phy0, nphx, phx0, Ty, Tx, mloy, mlox;
+  const TcBandDev* bands; int nbands; int total_items;
+  int B, hin, win, s, p;
   int TH, TW, tiles_y, tiles_x;
   int kblocks;        // 64-channel blocks per tap
   int last_kmma;      // MMAs (K=16 each) in the last block of a tap (1..4)
-  int N, cout, BN, stages, tmem_cols;
+  int cout, bn_max, stages;
   float inv_scale;
   const float* bias;
   int act;
@@ -51,6 +62,8 @@ struct TcParams {
   // TC_EPI_HYPER_FINAL: columns [0,Cy) = mu, [Cy,2Cy) = raw sigma
   const void* q; int q_kind; int Cy; float max_index; int trunc;
   float* y_hat; uint8_t* idx;              // + out_hi/out_lo = planes of y_hat [B,hout,wout,Cy]
+  // TC_EPI_TWO_LAYER: columns of one output pixel = base[0,C1) (|| res[C1,2C1)); out_f32 = t [B,hout,wout,C1]
+  int C1, has_res, tl_act, tl_inverse; const float* gamma; int gamma_stride; const float* beta;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -123,6 +136,22 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
 }
 
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
 //   bits [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64)
 //   | [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
@@ -159,36 +188,181 @@ __device__ __forceinline__ void store8_planes(__half* hi, __half* lo, size_t off
 }
 
 // ------------------------------------------------------------------------------------------------
+// Epilogue helpers (one thread = one cell row of the accumulator tile)
+
+struct TcItem {
+  int band, b, iy0, ix0, n0, nrows, mma_n;
+};
+
+__device__ __forceinline__ TcItem tc_decode_item(const TcParams& P, int item) {
+  TcItem it;
+  int bi = 0;
+  for (int i = 1; i < P.nbands; ++i)
+    if (item >= P.bands[i].item_begin) bi = i;
+  const TcBandDev& bd = P.bands[bi];
+  int local = item - bd.item_begin;
+  int nt = local % bd.ntiles, mt = local / bd.ntiles;
+  int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y;
+  it.band = bi;
+  it.b = mt / (P.tiles_x * P.tiles_y);
+  it.iy0 = ty * P.TH; it.ix0 = tx * P.TW;
+  it.n0 = nt * bd.BN;
+  it.nrows = min(bd.BN, bd.N - it.n0);
+  it.mma_n = (it.nrows + 15) & ~15;
+  return it;
+}
+
+// plain / hyper-final epilogue for 8 consecutive columns n..n+7 of one cell (cout % 8 == 0)
+__device__ __forceinline__ void tc_epi_vec8(const TcParams& P, const TcBandDev& bd, int b, int my, int mx, int n, float* v) {
+  const int co = n % P.cout, ph = n / P.cout;
+  const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
+  if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) return;
+  const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
+  float4 b0 = __ldg(reinterpret_cast<const float4*>(P.bias + co));
+  float4 b1 = __ldg(reinterpret_cast<const float4*>(P.bias + co + 4));
+  float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], P.inv_scale, bb[i]);
+  if (P.epi == TC_EPI_HYPER_FINAL) {
+    if (co < P.Cy) {   // mu half: y_hat = q + mu                     mshyper/models.py:278
+      const size_t e = pix * P.Cy + co;
+      float4 q0 = load_q4(P.q, P.q_kind, e), q1 = load_q4(P.q, P.q_kind, e + 4);
+      float y[8] = {__fadd_rn(q0.x, v[0]), __fadd_rn(q0.y, v[1]), __fadd_rn(q0.z, v[2]), __fadd_rn(q0.w, v[3]),
+                    __fadd_rn(q1.x, v[4]), __fadd_rn(q1.y, v[5]), __fadd_rn(q1.z, v[6]), __fadd_rn(q1.w, v[7])};
+      if (P.y_hat) {
+        *reinterpret_cast<float4*>(P.y_hat + e) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(P.y_hat + e + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      if (P.out_hi) store8_planes(P.out_hi, P.out_lo, e, y);
+    } else if (P.idx) {   // sigma half: idx = round(clamp(exp(sigma), 0, S-1))   :274-276
+      __align__(8) uint8_t o8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o8[i] = scale_index(v[i], P.max_index, P.trunc);
+      *reinterpret_cast<uint2*>(P.idx + pix * P.Cy + (co - P.Cy)) = *reinterpret_cast<const uint2*>(o8);
+    }
+    if (P.out_f32) {
+      float* o = P.out_f32 + pix * P.cout + co;
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], P.act);
+  if (P.out_hi) store8_planes(P.out_hi, P.out_lo, pix * P.cout + co, v);
+  if (P.out_f32) {
+    float* o = P.out_f32 + pix * P.cout + co;
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// generic scalar epilogue (final layers with cout = 3, ...)
+__device__ __forceinline__ void tc_epi_scalar8(const TcParams& P, const TcBandDev& bd, int b, int my, int mx, int n, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int nn = n + i;
+    if (nn >= bd.N) break;
+    const int co = nn % P.cout, ph = nn / P.cout;
+    const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
+    if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) continue;
+    float x = apply_act(fmaf(v[i], P.inv_scale, __ldg(P.bias + co)), P.act);
+    const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
+    if (P.out_f32) P.out_f32[pix * P.cout + co] = x;
+    if ((P.out_u8 || P.out_crop) && oy < P.H && ox < P.W) {
+      const size_t qi = (((size_t)b * P.H + oy) * P.W + ox) * P.cout + co;
+      if (P.out_u8) P.out_u8[qi] = float_to_pixel(x);
+      if (P.out_crop) P.out_crop[qi] = x;
+    }
+  }
+}
+
+// Two-layer synthesis, layer 1: one output pixel = C1 base columns (|| C1 residual columns).
+// t = act(base + bias) (+ res + bias'), act = IGDN1 / GDN1 / relu / leaky / none   (common/transforms.py:331-360)
+template <int C1, bool RES>
+__device__ __forceinline__ void tc_epi_two_layer_pixel(const TcParams& P, const float* sgamma, const float* sbeta, const float* sbias,
+                                                        const uint32_t* raw, float* dst) {
+  constexpr int PW = RES ? 2 * C1 : C1;
+  float x[C1];
+#pragma unroll
+  for (int j = 0; j < C1; ++j) x[j] = fmaf(__uint_as_float(raw[j]), P.inv_scale, sbias[j]);
+  float t[C1];
+  if (P.tl_act == SNTC_ACT_IGDN1 || P.tl_act == SNTC_ACT_GDN1) {
+#pragma unroll
+    for (int j = 0; j < C1; ++j) t[j] = sbeta[j];
+#pragma unroll
+    for (int i = 0; i < C1; ++i) {
+      const float a = fabsf(x[i]);
+#pragma unroll
+      for (int j = 0; j < C1; ++j) t[j] = fmaf(a, sgamma[i * C1 + j], t[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < C1; ++j) t[j] = P.tl_inverse ? x[j] * t[j] : x[j] / t[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < C1; ++j) t[j] = apply_act(x[j], P.tl_act);
+  }
+  if (RES) {
+#pragma unroll
+    for (int j = 0; j < C1; ++j) t[j] += fmaf(__uint_as_float(raw[C1 + j]), P.inv_scale, sbias[C1 + j]);
+  }
+  (void)PW;
+#pragma unroll
+  for (int j = 0; j < C1; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
+}
+
+template <int C1, bool RES>
+__device__ __forceinline__ void tc_epi_two_layer(const TcParams& P, const TcBandDev& bd, const TcItem& it, uint32_t trow, int b, int my, int mx,
+                                                 bool cell_ok, const float* sgamma, const float* sbeta, const float* sbias) {
+  constexpr int PW = RES ? 2 * C1 : C1;
+  const int npx = it.nrows / PW;
+  for (int pp = 0; pp < npx; ++pp) {
+    uint32_t raw[PW];
+#pragma unroll
+    for (int c = 0; c < PW; c += 4) tcx::tmem_ld4_nowait(trow + (uint32_t)(pp * PW + c), raw + c);
+    tcx::tmem_ld_wait();
+    if (!cell_ok) continue;
+    const int ph = (it.n0 + pp * PW) / PW;
+    const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
+    if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) continue;
+    float* dst = P.out_f32 + (((size_t)b * P.hout + oy) * P.wout + ox) * C1;
+    tc_epi_two_layer_pixel<C1, RES>(P, sgamma, sbeta, sbias, raw, dst);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent layer kernel: every CTA (one per SM) loops over the layer's work items
+// (band, m-tile, n-tile); the smem ring and the two TMEM accumulators run across items, so the
+// epilogue of item i overlaps the MMAs of item i+1.
 __global__ void __launch_bounds__(TC_THREADS, 1)
-band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
-                    const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, const TcParams P) {
+band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int BN = P.BN;
-  const uint32_t a_bytes = TC_BM * 128;            // one A plane tile
-  const uint32_t b_bytes = (uint32_t)BN * 128;     // one W plane tile
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const uint32_t a_bytes = TC_BM * 128;                   // one A plane tile
+  const uint32_t b_slot = (uint32_t)P.bn_max * 128;       // smem reserved per W plane tile
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_slot;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + P.stages;
-  uint64_t* tmem_full_bar = empty_bar + P.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + P.stages;         // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* sconst = reinterpret_cast<float*>(tmem_slot + 4);   // two-layer epilogue constants: gamma | beta | bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int tx = tile % P.tiles_x, ty = (tile / P.tiles_x) % P.tiles_y, b = tile / (P.tiles_x * P.tiles_y);
-  const int n0 = blockIdx.y * BN;
-  const int iy0 = ty * P.TH, ix0 = tx * P.TW;      // first cell (index within the band's h x w cell grid)
-  const int nk = P.Ty * P.Tx * P.kblocks;
 
-  if (warp == 0 && lane == 0) {
-    tcx::prefetch_tmap(&mapAhi); tcx::prefetch_tmap(&mapAlo); tcx::prefetch_tmap(&mapBhi); tcx::prefetch_tmap(&mapBlo);
-  }
+  if (warp == 0 && lane == 0) { tcx::prefetch_tmap(&mapAhi); tcx::prefetch_tmap(&mapAlo); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < P.stages; ++i) { tcx::mbar_init(&full_bar[i], 1); tcx::mbar_init(&empty_bar[i], 1); }
-    tcx::mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) { tcx::mbar_init(&tmem_full_bar[i], 1); tcx::mbar_init(&tmem_empty_bar[i], 4); }
     tcx::fence_barrier_init();
   }
-  if (warp == 2) tcx::tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  if (warp == 2) tcx::tmem_alloc(tmem_slot, 2 * TC_ACC_COLS);
+  if (warp >= 4 && P.epi == TC_EPI_TWO_LAYER) {
+    const int t = threadIdx.x - 128, C1 = P.C1, nb = P.cout;
+    if (P.gamma) for (int i = t; i < C1 * C1; i += 128) sconst[i] = P.gamma[(size_t)(i / C1) * P.gamma_stride + (i % C1)];
+    if (P.beta) for (int i = t; i < C1; i += 128) sconst[C1 * C1 + i] = P.beta[i];
+    for (int i = t; i < nb; i += 128) sconst[C1 * C1 + C1 + i] = P.bias[i];
+  }
   tcx::tc_fence_before();
   __syncthreads();
   tcx::tc_fence_after();
@@ -197,137 +371,118 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int it = 0; it < nk; ++it) {
-        const int st = it % P.stages;
-        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-        tcx::mbar_wait(&empty_bar[st], ph ^ 1u);
-        const int tap = it / P.kblocks, kb = it - tap * P.kblocks;
-        const int jy = tap / P.Tx, jx = tap - jy * P.Tx;
-        uint8_t* sa = smem + (size_t)st * stage_bytes;
-        tcx::mbar_expect_tx(&full_bar[st], stage_bytes);
-        const int cx = P.mlox + ix0 - jx, cy = P.mloy + iy0 - jy, cc = kb * TC_BK;
-        tcx::tma_load_4d(sa, &mapAhi, &full_bar[st], cc, cx, cy, b);
-        tcx::tma_load_4d(sa + a_bytes, &mapAlo, &full_bar[st], cc, cx, cy, b);
-        const int kcol = (tap * P.kblocks + kb) * TC_BK;
-        tcx::tma_load_2d(sa + 2 * a_bytes, &mapBhi, &full_bar[st], kcol, n0);
-        tcx::tma_load_2d(sa + 2 * a_bytes + b_bytes, &mapBlo, &full_bar[st], kcol, n0);
+      uint32_t g = 0;   // global k-step counter: the smem ring runs across work items
+      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+        const TcItem it = tc_decode_item(P, item);
+        const TcBandDev& bd = P.bands[it.band];
+        const int nk = bd.Ty * bd.Tx * P.kblocks;
+        const uint32_t tx_bytes = 2 * a_bytes + 2 * (uint32_t)bd.BN * 128;
+        for (int k = 0; k < nk; ++k, ++g) {
+          const int st = g % P.stages;
+          const uint32_t ph = (g / P.stages) & 1u;
+          tcx::mbar_wait(&empty_bar[st], ph ^ 1u);
+          const int tap = k / P.kblocks, kb = k - tap * P.kblocks;
+          const int jy = tap / bd.Tx, jx = tap - jy * bd.Tx;
+          uint8_t* sa = smem + (size_t)st * stage_bytes;
+          tcx::mbar_expect_tx(&full_bar[st], tx_bytes);
+          const int cx = bd.mlox + it.ix0 - jx, cy = bd.mloy + it.iy0 - jy, cc = kb * TC_BK;
+          tcx::tma_load_4d(sa, &mapAhi, &full_bar[st], cc, cx, cy, it.b);
+          tcx::tma_load_4d(sa + a_bytes, &mapAlo, &full_bar[st], cc, cx, cy, it.b);
+          const int kcol = k * TC_BK;
+          tcx::tma_load_2d(sa + 2 * a_bytes, &bd.mapBhi, &full_bar[st], kcol, it.n0);
+          tcx::tma_load_2d(sa + 2 * a_bytes + b_slot, &bd.mapBlo, &full_bar[st], kcol, it.n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = tcx::make_idesc(TC_BM, BN);
-      uint32_t acc = 0;
-      for (int it = 0; it < nk; ++it) {
-        const int st = it % P.stages;
-        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-        tcx::mbar_wait(&full_bar[st], ph);
+      uint32_t g = 0, j = 0;
+      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x, ++j) {
+        const TcItem it = tc_decode_item(P, item);
+        const TcBandDev& bd = P.bands[it.band];
+        const int nk = bd.Ty * bd.Tx * P.kblocks;
+        const uint32_t buf = j & 1u;
+        tcx::mbar_wait(&tmem_empty_bar[buf], ((j >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
         tcx::tc_fence_after();
-        const uint32_t sa = tcx::smem_u32(smem + (size_t)st * stage_bytes);
-        const uint64_t a_hi = tcx::make_smem_desc(sa), a_lo = tcx::make_smem_desc(sa + a_bytes);
-        const uint64_t b_hi = tcx::make_smem_desc(sa + 2 * a_bytes), b_lo = tcx::make_smem_desc(sa + 2 * a_bytes + b_bytes);
-        const int kb = it % P.kblocks;
-        const int nm = (kb == P.kblocks - 1) ? P.last_kmma : 4;
-        // lo*hi and hi*lo first (small terms), hi*hi last
-        for (int k = 0; k < nm; ++k) { tcx::umma_f16(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, acc); acc = 1; }
-        for (int k = 0; k < nm; ++k) tcx::umma_f16(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
-        for (int k = 0; k < nm; ++k) tcx::umma_f16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
-        tcx::umma_commit(&empty_bar[st]);       // frees this smem stage when the MMAs above retire
+        const uint32_t tacc = tmem_base + buf * TC_ACC_COLS;
+        const uint32_t idesc = tcx::make_idesc(TC_BM, it.mma_n);
+        uint32_t acc = 0;
+        for (int k = 0; k < nk; ++k, ++g) {
+          const int st = g % P.stages;
+          const uint32_t ph = (g / P.stages) & 1u;
+          tcx::mbar_wait(&full_bar[st], ph);
+          tcx::tc_fence_after();
+          const uint32_t sa = tcx::smem_u32(smem + (size_t)st * stage_bytes);
+          const uint64_t a_hi = tcx::make_smem_desc(sa), a_lo = tcx::make_smem_desc(sa + a_bytes);
+          const uint64_t b_hi = tcx::make_smem_desc(sa + 2 * a_bytes), b_lo = tcx::make_smem_desc(sa + 2 * a_bytes + b_slot);
+          const int kb = k % P.kblocks;
+          const int nm = (kb == P.kblocks - 1) ? P.last_kmma : 4;
+          // lo*hi and hi*lo first (small terms), hi*hi last
+          for (int q = 0; q < nm; ++q) { tcx::umma_f16(tacc, a_lo + 2 * q, b_hi + 2 * q, idesc, acc); acc = 1; }
+          for (int q = 0; q < nm; ++q) tcx::umma_f16(tacc, a_hi + 2 * q, b_lo + 2 * q, idesc, 1);
+          for (int q = 0; q < nm; ++q) tcx::umma_f16(tacc, a_hi + 2 * q, b_hi + 2 * q, idesc, 1);
+          tcx::umma_commit(&empty_bar[st]);       // frees this smem stage when the MMAs above retire
+        }
+        tcx::umma_commit(&tmem_full_bar[buf]);    // accumulator complete
       }
-      tcx::umma_commit(tmem_full_bar);          // accumulator complete
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> global =====
     const int ew = warp - 4;                    // TMEM lanes [32*ew, 32*ew+32)
     const int r = ew * 32 + lane;               // row of the tile = cell
-    const int iy = iy0 + r / P.TW, ix = ix0 + r % P.TW;
-    const bool cell_ok = iy < P.hin && ix < P.win;
-    const int my = P.mloy + iy, mx = P.mlox + ix;
-    if (nk > 0) {
-      tcx::mbar_wait(tmem_full_bar, 0);
+    const float* sgamma = sconst; const float* sbeta = sconst + P.C1 * P.C1; const float* sbias = sbeta + P.C1;
+    uint32_t j = 0;
+    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x, ++j) {
+      const TcItem it = tc_decode_item(P, item);
+      const TcBandDev& bd = P.bands[it.band];
+      const int nk = bd.Ty * bd.Tx * P.kblocks;
+      const uint32_t buf = j & 1u;
+      const int iy = it.iy0 + r / P.TW, ix = it.ix0 + r % P.TW;
+      const bool cell_ok = iy < P.hin && ix < P.win;
+      const int my = bd.mloy + iy, mx = bd.mlox + ix;
+      tcx::mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1u);
       tcx::tc_fence_after();
-    }
-    const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16);
-    const bool vec = (P.cout % 8) == 0;
-    for (int c = 0; c < BN; c += 8) {
-      float v[8];
-      if (nk > 0) tcx::tmem_ld8(trow + (uint32_t)c, v);      // warp-wide: executed by all lanes
-      else { for (int i = 0; i < 8; ++i) v[i] = 0.f; }
-      const int n = n0 + c;
-      if (!cell_ok || n >= P.N) continue;
-      if (vec) {
-        const int co = n % P.cout, ph = n / P.cout;
-        const int oy = P.s * my + P.phy0 + ph / P.nphx - P.p, ox = P.s * mx + P.phx0 + ph % P.nphx - P.p;
-        if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) continue;
-        const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
-        float4 b0 = __ldg(reinterpret_cast<const float4*>(P.bias + co));
-        float4 b1 = __ldg(reinterpret_cast<const float4*>(P.bias + co + 4));
-        float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], P.inv_scale, bb[i]);
-        if (P.epi == TC_EPI_HYPER_FINAL) {
-          if (co < P.Cy) {   // mu half: y_hat = q + mu                     mshyper/models.py:278
-            const size_t e = pix * P.Cy + co;
-            float4 q0 = load_q4(P.q, P.q_kind, e), q1 = load_q4(P.q, P.q_kind, e + 4);
-            float y[8] = {__fadd_rn(q0.x, v[0]), __fadd_rn(q0.y, v[1]), __fadd_rn(q0.z, v[2]), __fadd_rn(q0.w, v[3]),
-                          __fadd_rn(q1.x, v[4]), __fadd_rn(q1.y, v[5]), __fadd_rn(q1.z, v[6]), __fadd_rn(q1.w, v[7])};
-            if (P.y_hat) {
-              *reinterpret_cast<float4*>(P.y_hat + e) = make_float4(y[0], y[1], y[2], y[3]);
-              *reinterpret_cast<float4*>(P.y_hat + e + 4) = make_float4(y[4], y[5], y[6], y[7]);
-            }
-            if (P.out_hi) store8_planes(P.out_hi, P.out_lo, e, y);
-            if (P.out_f32) {
-              float* o = P.out_f32 + pix * P.cout + co;
-              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-          } else {           // sigma half: idx = round(clamp(exp(sigma), 0, S-1))   :274-276
-            if (P.idx) {
-              __align__(8) uint8_t o8[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o8[i] = scale_index(v[i], P.max_index, P.trunc);
-              *reinterpret_cast<uint2*>(P.idx + pix * P.Cy + (co - P.Cy)) = *reinterpret_cast<const uint2*>(o8);
-            }
-            if (P.out_f32) {
-              float* o = P.out_f32 + pix * P.cout + co;
-              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], P.act);
-          if (P.out_hi) store8_planes(P.out_hi, P.out_lo, pix * P.cout + co, v);
-          if (P.out_f32) {
-            float* o = P.out_f32 + pix * P.cout + co;
-            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          }
-        }
+      const uint32_t trow = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(ew * 32) << 16);
+      if (P.epi == TC_EPI_TWO_LAYER && nk > 0) {
+        if (P.C1 == 12) { if (P.has_res) tc_epi_two_layer<12, true>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias);
+                          else tc_epi_two_layer<12, false>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias); }
+        else            { if (P.has_res) tc_epi_two_layer<24, true>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias);
+                          else tc_epi_two_layer<24, false>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias); }
       } else {
-        // generic scalar path (final layers with cout = 3, ...)
+        const bool vec = (P.cout % 8) == 0;
+        for (int c = 0; c < it.mma_n; c += 16) {
+          uint32_t raw[16];
+          if (nk > 0) {                           // warp-wide TMEM loads: executed by all lanes
+            tcx::tmem_ld8_nowait(trow + (uint32_t)c, raw);
+            tcx::tmem_ld8_nowait(trow + (uint32_t)c + 8, raw + 8);
+            tcx::tmem_ld_wait();
+          } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int nn = n + i;
-          if (nn >= P.N) break;
-          const int co = nn % P.cout, ph = nn / P.cout;
-          const int oy = P.s * my + P.phy0 + ph / P.nphx - P.p, ox = P.s * mx + P.phx0 + ph % P.nphx - P.p;
-          if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) continue;
-          float x = apply_act(fmaf(v[i], P.inv_scale, __ldg(P.bias + co)), P.act);
-          const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
-          if (P.out_f32) P.out_f32[pix * P.cout + co] = x;
-          if ((P.out_u8 || P.out_crop) && oy < P.H && ox < P.W) {
-            const size_t qi = (((size_t)b * P.H + oy) * P.W + ox) * P.cout + co;
-            if (P.out_u8) P.out_u8[qi] = float_to_pixel(x);
-            if (P.out_crop) P.out_crop[qi] = x;
+            for (int i = 0; i < 16; ++i) raw[i] = 0u;
+          }
+          if (!cell_ok) continue;
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int n = it.n0 + c + h8 * 8;
+            if (n >= bd.N) break;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[h8 * 8 + i]);
+            if (vec) tc_epi_vec8(P, bd, it.b, my, mx, n, v);
+            else tc_epi_scalar8(P, bd, it.b, my, mx, n, v);
           }
         }
       }
+      // this warp is done reading accumulator `buf`
+      tcx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tcx::mbar_arrive(&tmem_empty_bar[buf]);
     }
   }
   tcx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) tcx::tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  if (warp == 2) tcx::tmem_dealloc(tmem_base, 2 * TC_ACC_COLS);
 }
 
 // f32 NHWC -> fp16 hi/lo planes (input of the first tensor-core layer)
@@ -347,6 +502,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct TcDriver {
   PFN_encodeTiled encode = nullptr;
+  int num_sms = 148;
   std::string err;
   void init() {
     void* fn = nullptr;
@@ -358,22 +514,24 @@ struct TcDriver {
       return;
     }
     encode = (PFN_encodeTiled)fn;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) num_sms = n;
   }
-};
-
-struct TcBand {
-  int N = 0, BN = 0, ntiles = 0, stages = 0, tmem_cols = 0;
-  size_t row0 = 0;          // first row of this band in the packed matrices
-  CUtensorMap mapBhi, mapBlo;
 };
 
 struct TcConv {
   bool ok = false;
   int cin = 0, kblocks = 0, last_kmma = 4, ktot_pad = 0;   // per-tap K padded to kblocks*64
+  int bn_max = 16, stages = 2;
+  bool fused_two_layer = false;                            // layer-1 of a two-layer synthesis with the IGDN(+res) epilogue
   float scale = 1.f;
-  __half* d_hi = nullptr; __half* d_lo = nullptr;          // [rows][Kmax] K-major
+  __half* d_hi = nullptr; __half* d_lo = nullptr;          // [rows][kmax] K-major
   size_t kmax = 0;                                         // row pitch (elements)
-  std::vector<TcBand> bands;
+  std::vector<TcBandDev> bands;                            // host copy, sorted by K descending
+  std::vector<int> items_per_mtile;                        // n-tiles per band
+  TcBandDev* d_bands = nullptr;
+  int nbands = 0;
+  int uploaded_mtiles = -1;                                // geometry the device band table was built for
 };
 
 struct TcDevBuf {
@@ -398,17 +556,17 @@ struct TcModelState {
   void release() { for (auto& b : plane) b.release(); yh[0].release(); yh[1].release(); }
 };
 
-inline int tc_choose_bn(int N, int* stages) {
-  // widest tile that keeps >= 3 pipeline stages in 227 KB and wastes the least padded columns
+// Widest n-tile (multiple of `unit`, itself a multiple of 16) that keeps >= 3 pipeline stages in 227 KB
+// and wastes the least padded columns; the last tile of a band only issues MMAs for its own columns.
+inline int tc_choose_bn(int N, int unit) {
   int best = 0; long best_cost = -1;
-  for (int bn = 160; bn >= 16; bn -= 16) {
+  for (int bn = (160 / unit) * unit; bn >= unit; bn -= unit) {
     int tiles = (N + bn - 1) / bn;
-    long cost = (long)tiles * bn * 1000 + tiles * 40 * 64;   // padded MMA work + per-tile A re-read/epilogue overhead
+    int last = N - (tiles - 1) * bn;
+    long cols = (long)(tiles - 1) * bn + ((last + 15) & ~15);
+    long cost = cols * 1000 + (long)tiles * 40 * 64;   // MMA work + per-tile A re-read / epilogue overhead
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
-  int stage_bytes = 2 * TC_BM * 128 + 2 * best * 128;
-  int st = (227 * 1024 - 2048) / stage_bytes;
-  *stages = st > 6 ? 6 : st;
   return best;
 }
 
@@ -437,15 +595,17 @@ inline bool tc_make_map_4d(TcDriver& drv, CUtensorMap* map, void* base, int C, i
 
 // A conv layer runs on the tensor cores when its input channel count is TMA-addressable.
 inline bool tc_conv_supported(const ConvLayer& c) {
-  return !c.append_ones && c.cin % 8 == 0 && c.cin >= 64;
+  return !c.append_ones && c.cin % 8 == 0 && c.cin >= 64 && (int)c.bands.size() <= TC_MAX_BANDS;
 }
 
-inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& hw, TcConv& t, std::vector<void*>& owned, std::string* err) {
+// `pixel_cols` > 0: n-tiles must hold whole output pixels of that many columns (fused two-layer epilogue).
+inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& hw, TcConv& t, int pixel_cols, std::vector<void*>& owned, std::string* err) {
   t.cin = c.cin;
   t.kblocks = (c.cin + TC_BK - 1) / TC_BK;
   int rem = c.cin - (t.kblocks - 1) * TC_BK;
   t.last_kmma = (rem + 15) / 16;
   t.ktot_pad = t.kblocks * TC_BK;
+  t.fused_two_layer = pixel_cols > 0;
   // power-of-two scale so that max |w| * S lies in [2^11, 2^12)
   float wmax = 0.f;
   for (auto& s : c.sources) for (float v : hw.at(s.kernel).second) wmax = std::max(wmax, std::fabs(v));
@@ -457,15 +617,17 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
   if (kmax == 0) kmax = TC_BK;
   t.kmax = kmax;
   std::vector<__half> hi(rows * kmax, __float2half(0.f)), lo(rows * kmax, __float2half(0.f));
-  t.bands.resize(c.bands.size());
+  int unit = 16;
+  if (pixel_cols > 0) { unit = pixel_cols; while (unit % 16) unit += pixel_cols; }   // lcm(pixel_cols, 16)
+  // heavy bands first: with items dealt round-robin to the persistent CTAs this balances the tail
+  std::vector<size_t> order(c.bands.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return c.bands[a].Ty * c.bands[a].Tx > c.bands[b].Ty * c.bands[b].Tx; });
+  std::vector<size_t> row0_of(c.bands.size());
   size_t row0 = 0;
   for (size_t bi = 0; bi < c.bands.size(); ++bi) {
     const Band& b = c.bands[bi];
-    TcBand& tb = t.bands[bi];
-    tb.N = b.N; tb.row0 = row0;
-    tb.BN = tc_choose_bn(b.N, &tb.stages);
-    tb.ntiles = (b.N + tb.BN - 1) / tb.BN;
-    tb.tmem_cols = tb.BN <= 32 ? 32 : (tb.BN <= 64 ? 64 : (tb.BN <= 128 ? 128 : 256));
+    row0_of[bi] = row0;
     for (int fy = 0; fy < b.nphy; ++fy) for (int fx = 0; fx < b.nphx; ++fx) for (int co = 0; co < c.cout; ++co) {
       size_t row = row0 + (size_t)(fy * b.nphx + fx) * c.cout + co;
       for (int jy = 0; jy < b.Ty; ++jy) for (int jx = 0; jx < b.Tx; ++jx) {
@@ -488,15 +650,35 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
   if (cudaMemcpy(t.d_hi, hi.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(t.d_lo, lo.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
     *err = "cudaMemcpy (tc weights) failed"; return false;
   }
-  for (size_t bi = 0; bi < c.bands.size(); ++bi) {
+  t.bands.clear(); t.items_per_mtile.clear();
+  t.bn_max = 16;
+  for (size_t oi = 0; oi < order.size(); ++oi) {
+    size_t bi = order[oi];
     const Band& b = c.bands[bi];
-    TcBand& tb = t.bands[bi];
     if (b.N == 0) continue;
+    TcBandDev d;
+    memset(&d, 0, sizeof(d));
+    d.phy0 = b.phy0; d.nphx = b.nphx; d.phx0 = b.phx0; d.Ty = b.Ty; d.Tx = b.Tx;
+    // band index -> (yi, xi) in row-major order of (by, bx)
+    d.mloy = c.by[bi / c.bx.size()].mlo; d.mlox = c.bx[bi % c.bx.size()].mlo;
+    d.N = b.N;
+    d.BN = tc_choose_bn(b.N, unit);
+    if (d.BN >= b.N) d.BN = (b.N + 15) & ~15;            // single tile: no alignment constraint
+    d.ntiles = (b.N + d.BN - 1) / d.BN;
+    t.bn_max = std::max(t.bn_max, d.BN);
     uint64_t kcols = (uint64_t)std::max(1, b.Ty * b.Tx) * t.ktot_pad;
-    if (!tc_make_map_2d(drv, &tb.mapBhi, t.d_hi + tb.row0 * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)tb.BN, err)) return false;
-    if (!tc_make_map_2d(drv, &tb.mapBlo, t.d_lo + tb.row0 * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)tb.BN, err)) return false;
+    if (!tc_make_map_2d(drv, &d.mapBhi, t.d_hi + row0_of[bi] * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)d.BN, err)) return false;
+    if (!tc_make_map_2d(drv, &d.mapBlo, t.d_lo + row0_of[bi] * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)d.BN, err)) return false;
+    t.bands.push_back(d);
   }
-  t.ok = true;
+  t.nbands = (int)t.bands.size();
+  if (t.bn_max > TC_ACC_COLS) { *err = "n-tile wider than a TMEM accumulator"; return false; }
+  int stage_bytes = 2 * TC_BM * 128 + 2 * t.bn_max * 128;
+  t.stages = std::min(8, (227 * 1024 - 4096) / stage_bytes);
+  if (t.stages < 2) { *err = "not enough shared memory for a 2-stage pipeline"; return false; }
+  if (cudaMalloc((void**)&t.d_bands, sizeof(TcBandDev) * std::max(1, t.nbands)) != cudaSuccess) { *err = "cudaMalloc (band table) failed"; return false; }
+  owned.push_back(t.d_bands);
+  t.ok = t.nbands > 0;
   return true;
 }
 
@@ -506,8 +688,20 @@ inline bool tc_finalize(TcDriver& drv, TcModelState& st, Transform* hyper, Trans
   auto pack = [&](Transform* t, std::vector<TcConv>& out) {
     if (!t) return true;
     out.resize(t->convs.size());
-    for (size_t i = 0; i < t->convs.size(); ++i)
-      if (tc_conv_supported(t->convs[i]) && !tc_pack_conv(drv, t->convs[i], hw, out[i], owned, err)) return false;
+    for (size_t i = 0; i < t->convs.size(); ++i) {
+      const ConvLayer& c = t->convs[i];
+      if (!tc_conv_supported(c)) continue;
+      // two-layer synthesis layer 1 followed by the pointwise IGDN(+res) stage: fuse it when C1 is 12 or 24
+      int pixel_cols = 0;
+      for (size_t oi = 0; oi + 1 < t->ops.size(); ++oi) {
+        if ((t->ops[oi].type == OP_CONVT) && t->ops[oi].conv == (int)i) {
+          const Op& nx = t->ops[oi + 1];
+          if (nx.type == OP_ACT_RES && (c.cout == 24 || c.cout == 48)) pixel_cols = c.cout;
+          if (nx.type == OP_GDN && t->gdns[nx.gdn].kind == GDN_1 && (c.cout == 12 || c.cout == 24) && (t->kind == SNTC_T_TWO_LAYER)) pixel_cols = c.cout;
+        }
+      }
+      if (!tc_pack_conv(drv, c, hw, out[i], pixel_cols, owned, err)) return false;
+    }
     return true;
   };
   if (!pack(hyper, st.hyper) || !pack(syn, st.syn)) return false;
@@ -525,6 +719,9 @@ struct TcConvOut {
   // hyper-final fusion
   bool hyper_final = false; const void* q = nullptr; int q_kind = 0; int Cy = 0; float max_index = 63.f; bool trunc = false;
   float* y_hat = nullptr; uint8_t* idx = nullptr;
+  // two-layer fusion: f32 receives t = act(base) (+ res), [B,hout,wout,C1]
+  bool two_layer = false; int C1 = 0; bool has_res = false; int tl_act = SNTC_ACT_NONE; bool tl_inverse = true;
+  const float* gamma = nullptr; int gamma_stride = 0; const float* beta = nullptr;
 };
 
 inline void tc_choose_patch(int h, int w, int* TH, int* TW) {
@@ -536,38 +733,46 @@ inline void tc_choose_patch(int h, int w, int* TH, int* TW) {
   }
 }
 
-// Launches all bands of one conv layer.  Input: fp16 planes [B,h,w,cin].
-inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, const TcConv& t, const __half* in_hi, const __half* in_lo, int B, int h, int w,
+// One persistent launch for all bands of one conv layer.  Input: fp16 planes [B,h,w,cin].
+inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __half* in_hi, const __half* in_lo, int B, int h, int w,
                        const TcConvOut& o, cudaStream_t s, uint64_t* launches, std::string* err) {
   int TH, TW;
   tc_choose_patch(h, w, &TH, &TW);
   CUtensorMap mapAhi, mapAlo;
   if (!tc_make_map_4d(drv, &mapAhi, (void*)in_hi, c.cin, w, h, B, TW, TH, err)) return TC_ERROR;
   if (!tc_make_map_4d(drv, &mapAlo, (void*)in_lo, c.cin, w, h, B, TW, TH, err)) return TC_ERROR;
-  for (size_t yi = 0, bi = 0; yi < c.by.size(); ++yi)
-    for (size_t xi = 0; xi < c.bx.size(); ++xi, ++bi) {
-      const Band& b = c.bands[bi];
-      const TcBand& tb = t.bands[bi];
-      if (b.N == 0) continue;
-      TcParams P{};
-      P.B = B; P.hin = h; P.win = w; P.s = c.s; P.p = c.p;
-      P.phy0 = b.phy0; P.nphx = b.nphx; P.phx0 = b.phx0; P.Ty = b.Ty; P.Tx = b.Tx;
-      P.mloy = c.by[yi].mlo; P.mlox = c.bx[xi].mlo;
-      P.TH = TH; P.TW = TW; P.tiles_y = (h + TH - 1) / TH; P.tiles_x = (w + TW - 1) / TW;
-      P.kblocks = t.kblocks; P.last_kmma = t.last_kmma;
-      P.N = b.N; P.cout = c.cout; P.BN = tb.BN; P.stages = tb.stages; P.tmem_cols = tb.tmem_cols;
-      P.inv_scale = 1.f / t.scale; P.bias = c.d_bias; P.act = c.act;
-      P.hout = h * c.s; P.wout = w * c.s;
-      P.epi = o.hyper_final ? TC_EPI_HYPER_FINAL : TC_EPI_PLAIN;
-      P.out_hi = o.hi; P.out_lo = o.lo; P.out_f32 = o.f32; P.out_u8 = o.u8; P.out_crop = o.crop; P.H = o.H; P.W = o.W;
-      P.q = o.q; P.q_kind = o.q_kind; P.Cy = o.Cy; P.max_index = o.max_index; P.trunc = o.trunc ? 1 : 0; P.y_hat = o.y_hat; P.idx = o.idx;
-      size_t smem = (size_t)tb.stages * (2 * TC_BM * 128 + 2 * tb.BN * 128) + 1024 + 256;
-      dim3 grid((unsigned)(P.tiles_x * P.tiles_y * B), (unsigned)tb.ntiles);
-      band_gemm_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mapAhi, mapAlo, tb.mapBhi, tb.mapBlo, P);
-      if (launches) (*launches)++;
-      cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) { *err = std::string("band_gemm_tc_kernel launch: ") + cudaGetErrorString(e); return TC_ERROR; }
-    }
+  TcParams P{};
+  P.B = B; P.hin = h; P.win = w; P.s = c.s; P.p = c.p;
+  P.TH = TH; P.TW = TW; P.tiles_y = (h + TH - 1) / TH; P.tiles_x = (w + TW - 1) / TW;
+  const int mtiles = P.tiles_x * P.tiles_y * B;
+  int item = 0;
+  for (auto& bd : t.bands) { bd.item_begin = item; item += mtiles * bd.ntiles; }
+  // the band table depends on the batch geometry only through item_begin: refresh it when that changes
+  cudaError_t e = cudaSuccess;
+  if (t.uploaded_mtiles != mtiles) {
+    e = cudaMemcpyAsync(t.d_bands, t.bands.data(), sizeof(TcBandDev) * t.nbands, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { *err = std::string("band table upload: ") + cudaGetErrorString(e); return TC_ERROR; }
+    t.uploaded_mtiles = mtiles;
+  }
+  P.bands = t.d_bands; P.nbands = t.nbands; P.total_items = item;
+  P.kblocks = t.kblocks; P.last_kmma = t.last_kmma;
+  P.cout = c.cout; P.bn_max = t.bn_max; P.stages = t.stages;
+  P.inv_scale = 1.f / t.scale; P.bias = c.d_bias; P.act = c.act;
+  P.hout = h * c.s; P.wout = w * c.s;
+  P.epi = o.hyper_final ? TC_EPI_HYPER_FINAL : (o.two_layer ? TC_EPI_TWO_LAYER : TC_EPI_PLAIN);
+  P.out_hi = o.hi; P.out_lo = o.lo; P.out_f32 = o.f32; P.out_u8 = o.u8; P.out_crop = o.crop; P.H = o.H; P.W = o.W;
+  P.q = o.q; P.q_kind = o.q_kind; P.Cy = o.Cy; P.max_index = o.max_index; P.trunc = o.trunc ? 1 : 0; P.y_hat = o.y_hat; P.idx = o.idx;
+  P.C1 = o.C1; P.has_res = o.has_res ? 1 : 0; P.tl_act = o.tl_act; P.tl_inverse = o.tl_inverse ? 1 : 0;
+  P.gamma = o.gamma; P.gamma_stride = o.gamma_stride; P.beta = o.beta;
+  size_t smem = (size_t)t.stages * (2 * TC_BM * 128 + 2 * t.bn_max * 128) + 1024 + 64 * 8 + (size_t)(o.C1 * o.C1 + o.C1 + c.cout + 8) * 4 * (o.two_layer ? 1 : 0);
+  if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns
+  if (smem > 227 * 1024) { *err = "shared memory budget exceeded"; return TC_ERROR; }
+  int grid = std::min(drv.num_sms, P.total_items);
+  if (grid <= 0) return TC_OK;
+  band_gemm_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mapAhi, mapAlo, P);
+  if (launches) (*launches)++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("band_gemm_tc_kernel launch: ") + cudaGetErrorString(e); return TC_ERROR; }
   return TC_OK;
 }
 

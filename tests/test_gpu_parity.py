@@ -157,3 +157,22 @@ def test_tc_hyper_transform_call(gpu_ctx):
   hs = model.hyper_synthesis(z)
   ref = O.hyper_synthesis(wts, z)
   assert np.abs(hs - ref).max() < 2e-4
+
+
+@pytest.mark.parametrize("q_dtype", [np.float32, np.int8])
+def test_streaming_pipeline_matches_direct_decode(gpu_ctx, q_dtype):
+  """DecodePipeline (H2D / decode / D2H on three streams, double-buffered) returns exactly what the
+  synchronous call returns, for every batch, in order."""
+  from shallow_ntc_b200 import DecodePipeline
+  B, H, W = 2, 64, 128
+  model, wts, z, q = make_case("two_layer_syn", B * 5, H, W, "stress", "tc", gpu_ctx)
+  pipe = DecodePipeline(model, B, (H, W), q_dtype=q_dtype, depth=2)
+  zs, ys = model.latent_shapes(B, H, W)
+  outs = [dict(image=gpu_ctx.pinned_empty((B, H, W, 3), np.uint8), idx=gpu_ctx.pinned_empty(ys, np.uint8)) for _ in range(5)]
+  pins = [(gpu_ctx.pinned_like(z[i * B:(i + 1) * B]), gpu_ctx.pinned_like(q[i * B:(i + 1) * B].astype(q_dtype))) for i in range(5)]
+  tickets = [pipe.submit(pz, pq, o["image"], o["idx"]) for (pz, pq), o in zip(pins, outs)]
+  pipe.wait(tickets[-1])
+  pipe.drain()
+  for i in range(5):
+    ref = model.decompress(z[i * B:(i + 1) * B], q[i * B:(i + 1) * B], (H, W))
+    assert np.array_equal(outs[i]["image"], ref["image"]) and np.array_equal(outs[i]["idx"], ref["idx"])

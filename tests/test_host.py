@@ -1,0 +1,93 @@
+"""not-gpu: host-side mirror of the reference's plugin interface (registry, constructor kwargs, config
+dicts, geometry) and the DLPack / array-interface tensor hand-off."""
+import ctypes
+import numpy as np
+import pytest
+
+from shallow_ntc_b200 import class_builder, build_config, CONFIGS, Model, FactorizedModel, as_tensor, _lib
+from shallow_ntc_b200 import transforms as T
+
+
+def test_registry_has_the_decoder_classes_of_the_reference():
+  """common/transforms.py:383-393 minus the encoder-side classes."""
+  for name in ("BLS2017Synthesis", "CNNSynthesis", "HyperSynthesis", "MBT2018Synthesis", "HyperSynthesisSmall",
+               "JPEGLikeSynthesis", "TwoLayerSynthesis", "TwoLayerResSynthesis", "JPEGLikeHyperSynthesis"):
+    assert name in class_builder
+  t = class_builder.build("TwoLayerResSynthesis", channels=(12, 3), strides=(8, 2), kernel_sizes=(13, 5),
+                          activation_type="igdn", res_type="conv")
+  assert t.upsample == 16 and t.out_channels == 3
+  with pytest.raises(KeyError):
+    class_builder.build("ElicAnalysis")
+  with pytest.raises(NotImplementedError):
+    class_builder.build("TwoLayerResSynthesis", res_type="d2s")
+  with pytest.raises(NotImplementedError):
+    T.activation_code("prelu")
+
+
+def test_constructor_defaults_match_the_reference_signatures():
+  assert T.JPEGLikeSynthesis().kernel_size == 16 and T.JPEGLikeSynthesis().strides == 16
+  assert T.TwoLayerSynthesis().channels == (24, 3) and T.TwoLayerResSynthesis().channels == (12, 3)
+  assert T.JPEGLikeHyperSynthesis(320).kernel_size == 6
+  assert T.MBT2018Synthesis(192).n_layers == 4 and T.MBT2018Synthesis(192).output_channels == 3
+  assert T.CNNSynthesis(192).activation_type == "leaky_relu"
+  assert T.HyperSynthesis(320).activation_type == "relu"
+
+
+def test_variable_layouts():
+  v = T.HyperSynthesis(320).variable_shapes(320)
+  assert v["hyper_synthesis.layer_1.kernel"] == (5, 5, 480, 320)     # Keras [kh,kw,Cout,Cin]
+  assert v["hyper_synthesis.layer_2.kernel"] == (3, 3, 640, 480)
+  v = T.BLS2017Synthesis(256).variable_shapes(256)
+  assert v["synthesis.layer_2.kernel"] == (9, 9, 256, 3)             # tfc [kh,kw,Cin,Cout]
+  assert v["synthesis.igdn_0.gamma"] == (256, 256)
+  v = T.JPEGLikeSynthesis(kernel_size=18, strides=16, use_offset=True).variable_shapes(320)
+  assert v["synthesis.conv.kernel"] == (18, 18, 3, 321)
+
+
+def test_model_geometry_follows_the_reference():
+  m = build_config("two_layer_syn")
+  assert m.downsample_factor == 64 and m.latent_channels == 320 and m.hyper_channels == 320
+  assert m.latent_shapes(24, 512, 768) == ((24, 8, 12, 320), (24, 32, 48, 320))
+  assert m.latent_shapes(1, 500, 700) == ((1, 8, 11, 320), (1, 32, 44, 320))       # pad to a multiple of 64
+  f = build_config("bls2017")
+  assert isinstance(f, FactorizedModel) and f.downsample_factor == 16 and f.latent_channels == 256
+  assert set(CONFIGS) == {"jpegl", "two_layer_syn", "two_layer_syn2", "mbt2018", "bls2017"}
+  assert build_config("two_layer_syn2:48")._synthesis.channels == (48, 3)
+  custom = Model(dict(analysis=dict(cls="ElicAnalysis", channels=(192, 192, 192, 320)),
+                      synthesis=dict(cls="JPEGLikeSynthesis", kernel_size=18, strides=16),
+                      hyper_synthesis=dict(cls="JPEGLikeHyperSynthesis", bottleneck_size=320, kernel_size=6)))
+  assert custom.downsample_factor == 64
+
+
+def test_descriptors_carry_the_kwargs():
+  d = build_config("two_layer_syn")._synthesis.desc(320)
+  assert d.kind == _lib.T_TWO_LAYER_RES and list(d.channels) == [12, 3] and list(d.kernel_sizes) == [13, 5]
+  assert list(d.strides) == [8, 2] and d.activation == _lib.ACT_IGDN1 and d.in_channels == 320
+  d = T.JPEGLikeSynthesis(kernel_size=18, strides=16).desc(320)
+  assert d.kind == _lib.T_JPEG_LIKE_SYNTHESIS and d.kernel_sizes[0] == 18 and d.strides[0] == 16 and d.use_bias == 1
+
+
+def test_tensor_handoff_numpy_and_dlpack():
+  a = np.arange(24, dtype=np.float32).reshape(1, 2, 3, 4)
+  t = as_tensor(a)
+  assert t.t.device_type == _lib.DL_CPU and t.shape == (1, 2, 3, 4) and t.t.dtype_code == _lib.DL_FLOAT and t.t.dtype_bits == 32
+  assert t.t.data == a.ctypes.data
+  with pytest.raises(ValueError):
+    as_tensor(a.transpose(0, 2, 1, 3))
+  with pytest.raises(TypeError):
+    as_tensor(a.astype(np.float64))
+  # a DLPack producer (torch stands in for TensorFlow's tf.experimental.dlpack.to_dlpack): zero-copy, borrowed
+  import torch
+  x = torch.arange(24, dtype=torch.int16).reshape(1, 2, 3, 4)
+  t = as_tensor(x)
+  assert t.t.device_type == _lib.DL_CPU and t.shape == (1, 2, 3, 4) and t.t.dtype_code == _lib.DL_INT and t.t.dtype_bits == 16
+  assert t.t.data + t.t.byte_offset == x.data_ptr()
+  cap = torch.utils.dlpack.to_dlpack(torch.zeros(2, 2, 2, 2, dtype=torch.uint8))
+  assert as_tensor(cap).t.dtype_code == _lib.DL_UINT
+
+
+def test_cuda_array_interface_objects_are_device_tensors():
+  class Fake:
+    __cuda_array_interface__ = dict(shape=(1, 2, 2, 4), typestr="<f4", data=(0x7f0000000000, False), version=3, strides=None)
+  t = as_tensor(Fake(), device_id=3)
+  assert t.t.device_type == _lib.DL_CUDA and t.t.device_id == 3 and t.t.data == 0x7f0000000000

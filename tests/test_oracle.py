@@ -1,0 +1,157 @@
+"""not-gpu: pins the oracle (oracle/ntc_oracle.py) against (a) the reference's own structural
+known-answers (results/*.csv, notebooks/get_flops.ipynb) and (b) the torch-definition fixtures in
+tests/golden/ (see make_golden.py for why TensorFlow itself cannot be the source)."""
+import os
+import numpy as np
+import pytest
+
+from oracle import ntc_oracle as O
+from shallow_ntc_b200 import build_config, synthetic
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "torch_definitions.npz"))
+
+
+@pytest.mark.parametrize("k,s", [(13, 8), (5, 2), (18, 16), (3, 1), (6, 4), (16, 16), (4, 2), (7, 3)])
+@pytest.mark.parametrize("gemm_form", [False, True])
+def test_keras_conv2d_transpose_matches_gradient_definition(k, s, gemm_form):
+  x, w, b, y = (GOLD[f"keras_k{k}s{s}_{n}"] for n in "xwby")
+  got = O.keras_conv2d_transpose(x, w, b, s, np.float64, gemm_form)
+  assert got.shape == y.shape == (2, 3 * s, 4 * s, 4)
+  assert np.abs(got - y).max() < 1e-12
+
+
+@pytest.mark.parametrize("k,s", [(5, 2), (9, 4), (3, 1)])
+def test_tfc_signal_conv_up_matches_upsample_then_convolve(k, s):
+  x, w, b, y = (GOLD[f"tfc_k{k}s{s}_{n}"] for n in "xwby")
+  got = O.tfc_signal_conv2d_up(x, w, b, s)
+  assert got.shape == y.shape and np.abs(got - y).max() < 1e-12
+
+
+def _wts(prefix):
+  return {k[len(prefix):]: GOLD[k] for k in GOLD.files if k.startswith(prefix)}
+
+
+def test_two_layer_res_synthesis_golden():
+  got = O.two_layer_res_synthesis(_wts("tlr_w:"), GOLD["tlr_yhat"])
+  assert np.abs(got - GOLD["tlr_out"]).max() < 1e-11
+
+
+def test_hyper_synthesis_golden():
+  got = O.hyper_synthesis(_wts("hs_w:"), GOLD["hs_z"])
+  assert got.shape == (1, 8, 12, 8) and np.abs(got - GOLD["hs_out"]).max() < 1e-11
+
+
+def test_bls_and_mbt_style_golden():
+  w = _wts("bls_w:")
+  assert np.abs(O.bls2017_synthesis(w, GOLD["bls_yhat"]) - GOLD["bls_out"]).max() < 1e-10
+  # prefix of MBT2018Synthesis: two SignalConv + classic IGDN stages
+  x = GOLD["bls_yhat"]
+  for i in range(2):
+    x = O.tfc_signal_conv2d_up(x, w[f"synthesis.layer_{i}.kernel"], w[f"synthesis.layer_{i}.bias"], 2)
+    x = O.gdn_classic(x, w[f"synthesis.igdn_{i}.beta"], w[f"synthesis.igdn_{i}.gamma"], True)
+  assert np.abs(x - GOLD["mbt2_out"]).max() < 1e-10
+
+
+# ---- the reference's own known answers -------------------------------------------------------
+def test_parameter_counts_match_results_all_params_csv():
+  """results/all_params.csv:3-5 and notebooks/get_flops.ipynb cells 21, 26, 30."""
+  assert build_config("jpegl")._synthesis.count_params(320) == 311043
+  assert build_config("two_layer_syn")._synthesis.count_params(320) == 1299003
+  assert build_config("two_layer_syn2:24")._synthesis.count_params(320) == 1300347
+  assert build_config("two_layer_syn")._hyper_synthesis.count_params(320) == 9166240
+  from shallow_ntc_b200.transforms import CNNSynthesis, JPEGLikeSynthesis
+  assert CNNSynthesis(192, activation_type="leaky_relu").count_params(320) == 3394179
+  assert CNNSynthesis(192, activation_type="igdn").count_params(320) == 3431235
+  assert JPEGLikeSynthesis(kernel_size=16, strides=16).count_params(320) == 245763
+  # the oracle counts what it is given the same way
+  m = build_config("two_layer_syn")
+  w = synthetic.make_weights(m.variable_shapes())
+  assert O.count_params(w, "synthesis") == 1299003 and O.count_params(w, "hyper_synthesis") == 9166240
+
+
+def test_flops_per_pixel_match_results_csv():
+  """results/flops_per_pixel.csv / all_fpp.csv: TF profiler FLOPs at 512x768 = 2*MAC (+ bias adds)."""
+  px = 512 * 768
+  hs = O.convt_macs(8, 12, 5, 2, 320, 320) + O.convt_macs(16, 24, 5, 2, 320, 480) + O.convt_macs(32, 48, 3, 1, 480, 640)
+  assert abs(2 * hs / px - 30354.6875) / 30354.6875 < 2e-3          # g_h column
+  jpegl = O.convt_macs(32, 48, 18, 16, 320, 3)
+  assert abs(2 * jpegl / px - 2433.0) / 2433.0 < 2e-3               # JPEG-like g
+  assert abs(2 * jpegl - 956694528) / 956694528 < 2e-3              # notebook cell 23
+  gdn = lambda c: 256 * 384 * c * c                                  # the 1x1 conv inside GDN1 (transforms.py:47)
+  tlr = 2 * O.convt_macs(32, 48, 13, 8, 320, 12) + O.convt_macs(256, 384, 5, 2, 12, 3) + gdn(12)
+  assert abs(2 * tlr / px - 10677.0) / 10677.0 < 3e-3               # 2-layer g
+  tl24 = O.convt_macs(32, 48, 13, 8, 320, 24) + O.convt_macs(256, 384, 5, 2, 24, 3) + gdn(24)
+  assert abs(2 * tl24 - 4462610184) / 4462610184 < 3e-3             # notebook cell 29
+
+
+def test_shapes_and_zero_input_property():
+  """notebook cells 12-14, 26: y [1,32,48,320], z [1,8,12,320] for 512x768; vis_syn_filters cells 28-29:
+  synthesis(zeros[1,1,1,320]) -> [1,16,16,3] == bias."""
+  m = build_config("jpegl")
+  assert m.latent_shapes(1, 512, 768) == ((1, 8, 12, 320), (1, 32, 48, 320))
+  assert build_config("two_layer_syn2").latent_shapes(1, 1200, 1200) == ((1, 19, 19, 320), (1, 76, 76, 320))
+  assert build_config("bls2017").latent_shapes(1, 2160, 3840) == (None, (1, 135, 240, 256))
+  w = synthetic.make_weights(m.variable_shapes(), "stress")
+  out = O.jpeg_like_synthesis(w, np.zeros((1, 1, 1, 320)), strides=16)
+  assert out.shape == (1, 16, 16, 3) and np.allclose(out, w["synthesis.conv.bias"])
+
+
+def test_linearity_and_single_pixel_support():
+  """vis_syn_filters.ipynb cells 36-44."""
+  m = build_config("jpegl")
+  w = synthetic.make_weights(m.variable_shapes(), "init")
+  e = np.zeros((1, 2, 2, 320)); e[0, 0, 0, 5] = 1
+  g0 = O.jpeg_like_synthesis(w, np.zeros_like(e)); g1 = O.jpeg_like_synthesis(w, e); g3 = O.jpeg_like_synthesis(w, 3 * e)
+  assert np.abs((g3 - g0) - 3 * (g1 - g0)).max() < 1e-12
+  nz = np.argwhere(np.abs(g1 - g0)[0].sum(-1) > 0)
+  assert nz.max() <= 16     # 18x18 patch starting at -1: rows/cols 0..16 survive the SAME crop
+
+
+# ---- tiers, glue, epilogue ---------------------------------------------------------------------
+def test_t1_float32_gemm_form_agrees_with_t0():
+  m = build_config("two_layer_syn")
+  cfg = m._transform_config["synthesis"]
+  kw = {k: v for k, v in cfg.items() if k != "cls"}
+  w = synthetic.make_weights(m.variable_shapes(), "stress", synthesis_cls=cfg["cls"])
+  zs, ys = m.latent_shapes(1, 64, 128)
+  z, q = synthetic.make_latents(zs, ys)
+  t0 = O.mshyper_decode(w, cfg["cls"], z, q, 64, 128, kw)
+  t1 = O.mshyper_decode(w, cfg["cls"], z, q, 64, 128, kw, dtype=np.float32, gemm_form=True)
+  assert np.abs(t1["recon"] - t0["recon"]).max() < 1e-5 * max(1.0, np.abs(t0["recon"]).max())
+  far = t0["idx_dist"] > 5e-5 * np.maximum(1, t0["i_c"])
+  assert np.array_equal(t1["idx"][far], t0["idx"][far])
+  assert t0["idx"].min() == 0 and t0["idx"].max() == 63, "stress weights must exercise both clamps"
+  assert len(np.unique(t0["idx"])) == 64, "and every scale-table row"
+
+
+def test_scale_index_rules():
+  raw = np.log(np.array([1e-9, 0.49, 0.51, 1.49, 2.51, 62.4, 62.6, 63.5, 1e6]))
+  i_c, idx, dist = O.scale_indexes(raw)
+  assert idx.tolist() == [0, 0, 1, 1, 3, 62, 63, 63, 63]         # clamp to [0, 63], round to nearest
+  assert np.allclose(dist[:3], [0.5 - 1e-9, 0.01, 0.01], atol=1e-6) and abs(dist[-1] - 0.5) < 1e-12
+  assert np.rint(np.array([0.5, 1.5, 2.5, 62.5])).tolist() == [0, 2, 2, 62]   # A3: ties to even
+  _, idx_t, _ = O.scale_indexes(raw, "trunc")
+  assert idx_t.tolist() == [0, 0, 0, 1, 2, 62, 62, 63, 63]
+  assert abs(O.scale_fn(0) - 0.11) < 1e-12 and abs(O.scale_fn(63) - 256.0) < 1e-9
+
+
+def test_pixel_epilogue_and_metrics():
+  x = np.array([[-0.6, -0.5, -0.5 + 0.4 / 255, -0.5 + 1.6 / 255, 0.0, 0.5, 0.7]], dtype=np.float32).reshape(1, 1, 7, 1)
+  u8 = O.floats_to_pixels(x).ravel().tolist()
+  assert u8 == [0, 0, 0, 2, 128, 255, 255]                          # saturate; the one exact tie 127.5 -> 128 (even)
+  a = np.zeros((2, 4, 4, 3), np.uint8); b = a.copy(); b[0] += 10
+  mse, psnr = O.mse_psnr(a, b)
+  assert np.allclose(mse, [100.0, 0.0]) and abs(psnr[0] - 10 * np.log10(255 ** 2 / 100)) < 1e-9 and np.isinf(psnr[1])
+  assert np.array_equal(O.dequantize(np.float32([3, -2]), np.float32([0.25, 0.5])), np.float32([3.25, -1.5]))
+  assert np.array_equal(O.quantize_latent(np.array([0.5, 1.5, 2.5, -0.5])), [0, 2, 2, -0])
+
+
+def test_synthetic_inputs_are_shard_invariant():
+  m = build_config("two_layer_syn")
+  zs, ys = m.latent_shapes(4, 64, 64)
+  z, q = synthetic.make_latents(zs, ys)
+  z2, q2 = synthetic.make_latents((2,) + zs[1:], (2,) + ys[1:], first_index=2)
+  assert np.array_equal(z[2:], z2) and np.array_equal(q[2:], q2)
+  assert np.array_equal(q, np.rint(q)) and np.abs(q).max() <= 127
+  assert [synthetic.shard_range(24, r, 8) for r in range(8)] == [(3 * r, 3 * r + 3) for r in range(8)]
+  assert [synthetic.shard_range(5, r, 2) for r in range(2)] == [(0, 3), (3, 5)]
