@@ -112,20 +112,23 @@ def cpu_reference_run(config, n_images, steps, warmup):
 
   def one():
     return O.mshyper_decode(wts, cfg["cls"], z, q, H, W, kw, dtype=np.float32, gemm_form=True)
-  for _ in range(warmup):
-    one()
-  t0 = time.perf_counter()
-  for _ in range(steps):
-    one()
-  dt = time.perf_counter() - t0
+  # all host threads for BLAS, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
+  from threadpoolctl import threadpool_limits
+  with threadpool_limits(limits=os.cpu_count()):
+    for _ in range(warmup):
+      one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+      one()
+    dt = time.perf_counter() - t0
   return n_images * H * W * steps / dt / 1e6, dt / steps
 
 
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=20)
-  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--steps", type=int, default=200)
+  ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
   ap.add_argument("--config", default="two_layer_syn")
   ap.add_argument("--batch", type=int, default=24)
@@ -144,7 +147,8 @@ def main():
     v, sec = cpu_reference_run(args.config, n_img, max(1, args.steps), max(1, min(args.warmup, 2)))
     line = dict(impl="reference", metric="decoded Mpx/s", value=v, unit="Mpx/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=f"mshyper {args.config} decode, 768x512, random-init weights", images_per_step=n_img),
+                config=dict(workload=f"mshyper {args.config} decode (BASELINE configs[1]): 24 x 768x512 per GPU, random-init 'stress' weights",
+                            images_per_step=n_img, note="CPU arm times a 2-image sample of the 24-image step"),
                 cpu_baseline=dict(value=v, unit="Mpx/s", cores=cores, kind="port",
                                   sample=f"{n_img} of the {args.batch} images per step, oracle tier T1 (numpy float32 GEMM-form, BLAS threads = all cores); "
                                          "TF-2.10 itself is not installable offline"),

@@ -360,6 +360,12 @@ extern "C" int sntc_model_finalize(sntc_model* m) {
         } else {
           std::vector<float> w = pack_rgb_weights(c, m->hw);
           TRY(upload(m, w.data(), w.size() * 4, (void**)&c.d_w_rgb));
+          if (c.k == 5 && c.s == 2 && c.cin == 12 && c.cout == 3 && c.p == 1) {
+            c.h_w_tail.assign((size_t)25 * 12 * 3 + 3, 0.f);
+            for (int tap = 0; tap < 25; ++tap) for (int ci = 0; ci < 12; ++ci) for (int co = 0; co < 3; ++co)
+              c.h_w_tail[((size_t)tap * 12 + ci) * 3 + co] = w[((size_t)tap * c.cin_pad + ci) * 4 + co];
+            for (int co = 0; co < 3; ++co) c.h_w_tail[(size_t)25 * 12 * 3 + co] = b[co];
+          }
         }
       }
       if (op.gdn >= 0) {
@@ -588,6 +594,18 @@ static int launch_tail(sntc_ctx* ctx, const ConvLayer& c, const float* in, int B
 
 static int run_rgb_f32(sntc_ctx* ctx, const ConvLayer& c, const float* in, int B, int h, int w, const FinalOut* fin, cudaStream_t s) {
   if (c.s == 2 && c.k == 5 && c.p == 1 && c.cout == 3 && c.cin == c.cin_pad) {   // the two-layer tail (Keras k5 s2)
+    if (c.cin == 12 && !c.h_w_tail.empty()) {
+      TailParams Q{};
+      Q.x = in; Q.B = B; Q.hin = h; Q.win = w; Q.w = c.d_w_rgb; Q.bias = c.d_bias; Q.hout = 2 * h; Q.wout = 2 * w;
+      if (fin) { Q.out = fin->full; Q.out_u8 = fin->u8; Q.out_crop = fin->crop; Q.H = fin->H; Q.W = fin->W; }
+      TailWeights<5, 12> Wt;
+      memcpy(&Wt, c.h_w_tail.data(), sizeof(Wt));
+      dim3 grid((Q.wout + 63) / 64, (Q.hout + 31) / 32, B);
+      tail_s2_const_kernel<5, 1, 12, 4><<<grid, 128, 0, s>>>(Q, Wt);
+      ctx->launches++;
+      CU_TRY(cudaGetLastError());
+      return SNTC_OK;
+    }
     if (c.cin == 12) return launch_tail<5, 1, 12, 4>(ctx, c, in, B, h, w, fin, s);
     if (c.cin == 24) return launch_tail<5, 1, 24, 2>(ctx, c, in, B, h, w, fin, s);
     if (c.cin == 48) return launch_tail<5, 1, 48, 2>(ctx, c, in, B, h, w, fin, s);

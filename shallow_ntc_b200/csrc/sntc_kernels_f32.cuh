@@ -417,6 +417,102 @@ __global__ void __launch_bounds__(32 * TR) tail_s2_kernel(const TailParams Q) {
   }
 }
 
+// Same computation with the weights passed BY VALUE as a kernel parameter: after full unrolling every weight
+// is a constant-bank operand of its FFMA (no shared-memory weight traffic, the kernel becomes FMA-issue bound).
+// Fits the 4 KB parameter space for K=5, C1=12 (3600 B): the headline two_layer_syn configuration.
+template <int K, int C1>
+struct TailWeights { float w[K * K * C1 * 3]; float bias[3]; };   // [ay*K+ax][ci][co]
+
+template <int K, int P, int C1, int TR>
+__global__ void __launch_bounds__(32 * TR, 4) tail_s2_const_kernel(const TailParams Q, const __grid_constant__ TailWeights<K, C1> Wt) {
+  constexpr int T = (K + 1) / 2;
+  constexpr int RY = 8, TCX = 32;
+  constexpr int NT = TCX * TR;
+  constexpr int NY = ((P + RY - 1) >> 1) - (P >> 1) + T, NX = ((P + 1) >> 1) - (P >> 1) + T;
+  constexpr int TILE_Y = (RY / 2) * (TR - 1) + NY, TILE_X = (TCX - 1) + NX;
+  __shared__ __align__(16) float sx[TILE_Y * TILE_X * C1];
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * (RY * TR), ox0 = blockIdx.x * (2 * TCX);
+  const int ny0 = oy0 / 2 + (P >> 1) - (T - 1), nx0 = ox0 / 2 + (P >> 1) - (T - 1);
+  const float* img = Q.x + (size_t)b * Q.hin * Q.win * C1;
+  for (int i = threadIdx.x; i < TILE_Y * TILE_X * (C1 / 4); i += NT) {
+    int c4 = i % (C1 / 4), px = i / (C1 / 4);
+    int tx = px % TILE_X, ty = px / TILE_X;
+    int ny = ny0 + ty, nx = nx0 + tx;
+    const bool ok = ny >= 0 && ny < Q.hin && nx >= 0 && nx < Q.win;
+    const float* src = ok ? img + ((size_t)ny * Q.win + nx) * C1 + c4 * 4 : img;
+    cp_async16(sx + (size_t)px * C1 + c4 * 4, src, ok ? 16 : 0);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int ti = threadIdx.x % TCX, tr = threadIdx.x / TCX;
+  float acc[RY][2][3];
+#pragma unroll
+  for (int dy = 0; dy < RY; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) { acc[dy][dx][0] = 0.f; acc[dy][dx][1] = 0.f; acc[dy][dx][2] = 0.f; }
+  const float* tbase = sx + ((size_t)((RY / 2) * tr) * TILE_X + ti) * C1;
+#pragma unroll
+  for (int ay = 0; ay < K; ++ay) {
+#pragma unroll
+    for (int ax = 0; ax < K; ++ax) {
+      const int dx = ((ax - P) % 2 + 2) % 2;
+      const int ix = (dx + P - ax) / 2 - (P >> 1) + (T - 1);
+      const int dy0 = ((ay - P) % 2 + 2) % 2;
+#pragma unroll
+      for (int c = 0; c < C1; c += 4) {
+#pragma unroll
+        for (int e = 0; e < RY / 2; ++e) {
+          const int dy = dy0 + 2 * e;
+          const int iy = (dy + P - ay) / 2 - (P >> 1) + (T - 1);
+          const float4 xv = *reinterpret_cast<const float4*>(tbase + ((size_t)iy * TILE_X + ix) * C1 + c);
+          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+          float* a = acc[dy][dx];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float* w = Wt.w + ((ay * K + ax) * C1 + c + u) * 3;
+            a[0] = fmaf(xs[u], w[0], a[0]); a[1] = fmaf(xs[u], w[1], a[1]); a[2] = fmaf(xs[u], w[2], a[2]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int dy = 0; dy < RY; ++dy) {
+    const int oy = oy0 + RY * tr + dy;
+    if (oy >= Q.hout) continue;
+    const int ox = ox0 + 2 * ti;
+    if (ox >= Q.wout) continue;
+    float v[2][3];
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) { v[dx][0] = acc[dy][dx][0] + Wt.bias[0]; v[dx][1] = acc[dy][dx][1] + Wt.bias[1]; v[dx][2] = acc[dy][dx][2] + Wt.bias[2]; }
+    if (Q.out) {
+      float* o = Q.out + (((size_t)b * Q.hout + oy) * Q.wout + ox) * 3;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) if (ox + dx < Q.wout) { o[dx * 3] = v[dx][0]; o[dx * 3 + 1] = v[dx][1]; o[dx * 3 + 2] = v[dx][2]; }
+    }
+    if (oy < Q.H) {
+      if (Q.out_u8) {
+        uint8_t* o = Q.out_u8 + (((size_t)b * Q.H + oy) * Q.W + ox) * 3;
+        if (ox + 1 < Q.W && ((Q.W * 3) % 2 == 0)) {
+          const uint8_t p0 = float_to_pixel(v[0][0]), p1 = float_to_pixel(v[0][1]), p2 = float_to_pixel(v[0][2]);
+          const uint8_t p3 = float_to_pixel(v[1][0]), p4 = float_to_pixel(v[1][1]), p5 = float_to_pixel(v[1][2]);
+          uint16_t* o16 = reinterpret_cast<uint16_t*>(o);
+          o16[0] = (uint16_t)(p0 | (p1 << 8)); o16[1] = (uint16_t)(p2 | (p3 << 8)); o16[2] = (uint16_t)(p4 | (p5 << 8));
+        } else {
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) if (ox + dx < Q.W) { o[dx * 3] = float_to_pixel(v[dx][0]); o[dx * 3 + 1] = float_to_pixel(v[dx][1]); o[dx * 3 + 2] = float_to_pixel(v[dx][2]); }
+        }
+      }
+      if (Q.out_crop) {
+        float* o = Q.out_crop + (((size_t)b * Q.H + oy) * Q.W + ox) * 3;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) if (ox + dx < Q.W) { o[dx * 3] = v[dx][0]; o[dx * 3 + 1] = v[dx][1]; o[dx * 3 + 2] = v[dx][2]; }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // mshyper/models.py:274-279: split, exp, clamp, round -> idx ; y_hat = q + mu.
 // hs: [P, 2*C] (mu || raw_sigma).  q may be f32 / i16 / i8.  One thread per 4 channels.

@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "sntc_plan.hpp"
@@ -50,6 +51,7 @@ struct TcParams {
   int kblocks;        // 64-channel blocks per tap
   int last_kmma;      // MMAs (K=16 each) in the last block of a tap (1..4)
   int cout, bn_max, stages;
+  int mtiles;         // m-tiles per band (tiles_y*tiles_x*B); a CTA pair takes m-tiles (2i, 2i+1)
   float inv_scale;
   const float* bias;
   int act;
@@ -152,6 +154,49 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- thread-block cluster / CTA-pair (cta_group::2) forms ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in THIS CTA's smem, the transaction bytes are counted on the barrier
+// at cluster address `bar_cluster` (the leader CTA's full barrier)
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+    "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+    ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+    "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+    ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both: 128 rows each] * B[smem of both: N/2 rows each]; issued by the leader CTA
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this smem offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
 //   bits [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64)
 //   | [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
@@ -192,16 +237,22 @@ __device__ __forceinline__ void store8_planes(__half* hi, __half* lo, size_t off
 
 struct TcItem {
   int band, b, iy0, ix0, n0, nrows, mma_n;
+  bool dup;     // second CTA of a pair past the last m-tile: participates in the MMA, stores nothing
 };
 
-__device__ __forceinline__ TcItem tc_decode_item(const TcParams& P, int item) {
+// CG = CTAs per work item (1, or 2 for a cta_group::2 pair).  Items of a band: (m-tile group, n-tile), n-tile fastest.
+template <int CG>
+__device__ __forceinline__ TcItem tc_decode_item(const TcParams& P, int item, int rank) {
   TcItem it;
   int bi = 0;
   for (int i = 1; i < P.nbands; ++i)
     if (item >= P.bands[i].item_begin) bi = i;
   const TcBandDev& bd = P.bands[bi];
   int local = item - bd.item_begin;
-  int nt = local % bd.ntiles, mt = local / bd.ntiles;
+  int nt = local % bd.ntiles, mg = local / bd.ntiles;
+  int mt = mg * CG + rank;
+  it.dup = mt >= P.mtiles;
+  if (it.dup) mt = P.mtiles - 1;
   int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y;
   it.band = bi;
   it.b = mt / (P.tiles_x * P.tiles_y);
@@ -331,15 +382,21 @@ __device__ __forceinline__ void tc_epi_two_layer(const TcParams& P, const TcBand
 }
 
 // ------------------------------------------------------------------------------------------------
-// Persistent layer kernel: every CTA (one per SM) loops over the layer's work items
-// (band, m-tile, n-tile); the smem ring and the two TMEM accumulators run across items, so the
-// epilogue of item i overlaps the MMAs of item i+1.
+// Persistent layer kernel: every CTA (CG = 1) or CTA pair (CG = 2, one cluster = two SMs of a TPC) loops over
+// the layer's work items (band, m-tile group, n-tile); the smem ring and the two TMEM accumulators run across
+// items, so the epilogue of item i overlaps the MMAs of item i+1.
+//
+// CG = 2 (cta_group::2): the pair computes D[2 x 128 cells, N].  Each CTA TMA-loads its own 128-cell A tile and
+// HALF of the W tile rows into its own smem; the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), which reads
+// A and the W halves from both SMs -> per-SM shared-memory operand traffic drops by the W half.  Transaction bytes
+// of both CTAs are counted on the leader's full barrier; the MMA commit is multicast to both CTAs' barriers.
+template <int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t a_bytes = TC_BM * 128;                   // one A plane tile
-  const uint32_t b_slot = (uint32_t)P.bn_max * 128;       // smem reserved per W plane tile
+  const uint32_t a_bytes = TC_BM * 128;                        // one A plane tile
+  const uint32_t b_slot = (uint32_t)(P.bn_max / CG) * 128;     // smem reserved per W plane tile (this CTA's rows)
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_slot;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + P.stages;
@@ -349,14 +406,17 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
   float* sconst = reinterpret_cast<float*>(tmem_slot + 4);   // two-layer epilogue constants: gamma | beta | bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CG == 2 ? (int)tcx::cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int unit0 = (int)blockIdx.x / CG, nunits = (int)gridDim.x / CG;   // persistent work units (CTAs or pairs)
 
   if (warp == 0 && lane == 0) { tcx::prefetch_tmap(&mapAhi); tcx::prefetch_tmap(&mapAlo); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < P.stages; ++i) { tcx::mbar_init(&full_bar[i], 1); tcx::mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { tcx::mbar_init(&tmem_full_bar[i], 1); tcx::mbar_init(&tmem_empty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { tcx::mbar_init(&tmem_full_bar[i], 1); tcx::mbar_init(&tmem_empty_bar[i], 4 * CG); }
     tcx::fence_barrier_init();
   }
-  if (warp == 2) tcx::tmem_alloc(tmem_slot, 2 * TC_ACC_COLS);
+  if (warp == 2) { if (CG == 2) tcx::tmem_alloc_2sm(tmem_slot, 2 * TC_ACC_COLS); else tcx::tmem_alloc(tmem_slot, 2 * TC_ACC_COLS); }
   if (warp >= 4 && P.epi == TC_EPI_TWO_LAYER) {
     const int t = threadIdx.x - 128, C1 = P.C1, nb = P.cout;
     if (P.gamma) for (int i = t; i < C1 * C1; i += 128) sconst[i] = P.gamma[(size_t)(i / C1) * P.gamma_stride + (i % C1)];
@@ -364,19 +424,21 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     for (int i = t; i < nb; i += 128) sconst[C1 * C1 + C1 + i] = P.bias[i];
   }
   tcx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) tcx::cluster_sync_all(); else __syncthreads();
   tcx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
+      // ===== TMA producer (every CTA loads its own A tile and its own rows of W) =====
       uint32_t g = 0;   // global k-step counter: the smem ring runs across work items
-      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
-        const TcItem it = tc_decode_item(P, item);
+      for (int item = unit0; item < P.total_items; item += nunits) {
+        const TcItem it = tc_decode_item<CG>(P, item, rank);
         const TcBandDev& bd = P.bands[it.band];
         const int nk = bd.Ty * bd.Tx * P.kblocks;
-        const uint32_t tx_bytes = 2 * a_bytes + 2 * (uint32_t)bd.BN * 128;
+        const int wrows = bd.BN / CG;                                  // W box rows per CTA
+        const int wrow0 = it.n0 + rank * (it.mma_n / CG);              // this CTA supplies columns [rank*mma_n/CG, ...)
+        const uint32_t tx_bytes = (uint32_t)CG * (2 * a_bytes + 2 * (uint32_t)wrows * 128);
         for (int k = 0; k < nk; ++k, ++g) {
           const int st = g % P.stages;
           const uint32_t ph = (g / P.stages) & 1u;
@@ -384,29 +446,38 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
           const int tap = k / P.kblocks, kb = k - tap * P.kblocks;
           const int jy = tap / bd.Tx, jx = tap - jy * bd.Tx;
           uint8_t* sa = smem + (size_t)st * stage_bytes;
-          tcx::mbar_expect_tx(&full_bar[st], tx_bytes);
           const int cx = bd.mlox + it.ix0 - jx, cy = bd.mloy + it.iy0 - jy, cc = kb * TC_BK;
-          tcx::tma_load_4d(sa, &mapAhi, &full_bar[st], cc, cx, cy, it.b);
-          tcx::tma_load_4d(sa + a_bytes, &mapAlo, &full_bar[st], cc, cx, cy, it.b);
           const int kcol = k * TC_BK;
-          tcx::tma_load_2d(sa + 2 * a_bytes, &bd.mapBhi, &full_bar[st], kcol, it.n0);
-          tcx::tma_load_2d(sa + 2 * a_bytes + b_slot, &bd.mapBlo, &full_bar[st], kcol, it.n0);
+          if (CG == 2) {
+            if (leader) tcx::mbar_expect_tx(&full_bar[st], tx_bytes);
+            const uint32_t fb = tcx::mapa_u32(tcx::smem_u32(&full_bar[st]), 0);   // the leader's full barrier
+            tcx::tma_load_4d_2sm(sa, &mapAhi, fb, cc, cx, cy, it.b);
+            tcx::tma_load_4d_2sm(sa + a_bytes, &mapAlo, fb, cc, cx, cy, it.b);
+            tcx::tma_load_2d_2sm(sa + 2 * a_bytes, &bd.mapBhi, fb, kcol, wrow0);
+            tcx::tma_load_2d_2sm(sa + 2 * a_bytes + b_slot, &bd.mapBlo, fb, kcol, wrow0);
+          } else {
+            tcx::mbar_expect_tx(&full_bar[st], tx_bytes);
+            tcx::tma_load_4d(sa, &mapAhi, &full_bar[st], cc, cx, cy, it.b);
+            tcx::tma_load_4d(sa + a_bytes, &mapAlo, &full_bar[st], cc, cx, cy, it.b);
+            tcx::tma_load_2d(sa + 2 * a_bytes, &bd.mapBhi, &full_bar[st], kcol, wrow0);
+            tcx::tma_load_2d(sa + 2 * a_bytes + b_slot, &bd.mapBlo, &full_bar[st], kcol, wrow0);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (leader CTA only) =====
       uint32_t g = 0, j = 0;
-      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x, ++j) {
-        const TcItem it = tc_decode_item(P, item);
+      for (int item = unit0; item < P.total_items; item += nunits, ++j) {
+        const TcItem it = tc_decode_item<CG>(P, item, 0);
         const TcBandDev& bd = P.bands[it.band];
         const int nk = bd.Ty * bd.Tx * P.kblocks;
         const uint32_t buf = j & 1u;
-        tcx::mbar_wait(&tmem_empty_bar[buf], ((j >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+        tcx::mbar_wait(&tmem_empty_bar[buf], ((j >> 1) & 1u) ^ 1u);   // the epilogue(s) drained this accumulator
         tcx::tc_fence_after();
         const uint32_t tacc = tmem_base + buf * TC_ACC_COLS;
-        const uint32_t idesc = tcx::make_idesc(TC_BM, it.mma_n);
+        const uint32_t idesc = tcx::make_idesc(TC_BM * CG, it.mma_n);
         uint32_t acc = 0;
         for (int k = 0; k < nk; ++k, ++g) {
           const int st = g % P.stages;
@@ -419,27 +490,34 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
           const int kb = k % P.kblocks;
           const int nm = (kb == P.kblocks - 1) ? P.last_kmma : 4;
           // lo*hi and hi*lo first (small terms), hi*hi last
-          for (int q = 0; q < nm; ++q) { tcx::umma_f16(tacc, a_lo + 2 * q, b_hi + 2 * q, idesc, acc); acc = 1; }
-          for (int q = 0; q < nm; ++q) tcx::umma_f16(tacc, a_hi + 2 * q, b_lo + 2 * q, idesc, 1);
-          for (int q = 0; q < nm; ++q) tcx::umma_f16(tacc, a_hi + 2 * q, b_hi + 2 * q, idesc, 1);
-          tcx::umma_commit(&empty_bar[st]);       // frees this smem stage when the MMAs above retire
+          if (CG == 2) {
+            for (int q = 0; q < nm; ++q) { tcx::umma_f16_2sm(tacc, a_lo + 2 * q, b_hi + 2 * q, idesc, acc); acc = 1; }
+            for (int q = 0; q < nm; ++q) tcx::umma_f16_2sm(tacc, a_hi + 2 * q, b_lo + 2 * q, idesc, 1);
+            for (int q = 0; q < nm; ++q) tcx::umma_f16_2sm(tacc, a_hi + 2 * q, b_hi + 2 * q, idesc, 1);
+            tcx::umma_commit_2sm(&empty_bar[st], 3);   // frees this smem stage in both CTAs
+          } else {
+            for (int q = 0; q < nm; ++q) { tcx::umma_f16(tacc, a_lo + 2 * q, b_hi + 2 * q, idesc, acc); acc = 1; }
+            for (int q = 0; q < nm; ++q) tcx::umma_f16(tacc, a_hi + 2 * q, b_lo + 2 * q, idesc, 1);
+            for (int q = 0; q < nm; ++q) tcx::umma_f16(tacc, a_hi + 2 * q, b_hi + 2 * q, idesc, 1);
+            tcx::umma_commit(&empty_bar[st]);
+          }
         }
-        tcx::umma_commit(&tmem_full_bar[buf]);    // accumulator complete
+        if (CG == 2) tcx::umma_commit_2sm(&tmem_full_bar[buf], 3); else tcx::umma_commit(&tmem_full_bar[buf]);   // accumulator complete
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> global (every CTA drains its own 128 accumulator rows) =====
     const int ew = warp - 4;                    // TMEM lanes [32*ew, 32*ew+32)
     const int r = ew * 32 + lane;               // row of the tile = cell
     const float* sgamma = sconst; const float* sbeta = sconst + P.C1 * P.C1; const float* sbias = sbeta + P.C1;
     uint32_t j = 0;
-    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x, ++j) {
-      const TcItem it = tc_decode_item(P, item);
+    for (int item = unit0; item < P.total_items; item += nunits, ++j) {
+      const TcItem it = tc_decode_item<CG>(P, item, rank);
       const TcBandDev& bd = P.bands[it.band];
       const int nk = bd.Ty * bd.Tx * P.kblocks;
       const uint32_t buf = j & 1u;
       const int iy = it.iy0 + r / P.TW, ix = it.ix0 + r % P.TW;
-      const bool cell_ok = iy < P.hin && ix < P.win;
+      const bool cell_ok = iy < P.hin && ix < P.win && !it.dup;
       const int my = bd.mloy + iy, mx = bd.mlox + ix;
       tcx::mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1u);
       tcx::tc_fence_after();
@@ -474,15 +552,18 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
           }
         }
       }
-      // this warp is done reading accumulator `buf`
+      // this warp is done reading accumulator `buf`: tell the (leader's) MMA issuer
       tcx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tcx::mbar_arrive(&tmem_empty_bar[buf]);
+      if (lane == 0) {
+        if (CG == 2) tcx::mbar_arrive_cluster(tcx::mapa_u32(tcx::smem_u32(&tmem_empty_bar[buf]), 0));
+        else tcx::mbar_arrive(&tmem_empty_bar[buf]);
+      }
     }
   }
   tcx::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tcx::tmem_dealloc(tmem_base, 2 * TC_ACC_COLS);
+  if (CG == 2) tcx::cluster_sync_all(); else __syncthreads();   // the peer may still read this CTA's smem / signal its barriers
+  if (warp == 2) { if (CG == 2) tcx::tmem_dealloc_2sm(tmem_base, 2 * TC_ACC_COLS); else tcx::tmem_dealloc(tmem_base, 2 * TC_ACC_COLS); }
 }
 
 // f32 NHWC -> fp16 hi/lo planes (input of the first tensor-core layer)
@@ -523,6 +604,7 @@ struct TcConv {
   bool ok = false;
   int cin = 0, kblocks = 0, last_kmma = 4, ktot_pad = 0;   // per-tap K padded to kblocks*64
   int bn_max = 16, stages = 2;
+  int cg = 1;                                              // CTAs per work item: 2 = cta_group::2 pairs
   bool fused_two_layer = false;                            // layer-1 of a two-layer synthesis with the IGDN(+res) epilogue
   float scale = 1.f;
   __half* d_hi = nullptr; __half* d_lo = nullptr;          // [rows][kmax] K-major
@@ -558,16 +640,25 @@ struct TcModelState {
 
 // Widest n-tile (multiple of `unit`, itself a multiple of 16) that keeps >= 3 pipeline stages in 227 KB
 // and wastes the least padded columns; the last tile of a band only issues MMAs for its own columns.
+inline int tc_env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+inline int tc_bn_max() {
+  static int v = -1;
+  if (v < 0) { v = tc_env_int("SNTC_TC_BN_MAX", 256); if (v < 16 || v > TC_ACC_COLS) v = 256; }
+  return v;
+}
+inline int tc_cta_group() {
+  static int v = -1;
+  if (v < 0) { v = tc_env_int("SNTC_TC_CTA_GROUP", 2); if (v != 1 && v != 2) v = 2; }
+  return v;
+}
+// Fewest n-tiles of at most bn_max columns, then the narrowest (balanced) tile that achieves it; tiles are
+// multiples of `unit`.  The last tile of a band only issues MMAs for its own columns.
 inline int tc_choose_bn(int N, int unit) {
-  int best = 0; long best_cost = -1;
-  for (int bn = (160 / unit) * unit; bn >= unit; bn -= unit) {
-    int tiles = (N + bn - 1) / bn;
-    int last = N - (tiles - 1) * bn;
-    long cols = (long)(tiles - 1) * bn + ((last + 15) & ~15);
-    long cost = cols * 1000 + (long)tiles * 40 * 64;   // MMA work + per-tile A re-read / epilogue overhead
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
-  }
-  return best;
+  int cap = (tc_bn_max() / unit) * unit;
+  if (cap < unit) cap = unit;
+  int tiles = (N + cap - 1) / cap;
+  int bn = ((N + tiles - 1) / tiles + unit - 1) / unit * unit;
+  return std::min(bn, cap);
 }
 
 inline bool tc_make_map_2d(TcDriver& drv, CUtensorMap* map, void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
@@ -617,8 +708,10 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
   if (kmax == 0) kmax = TC_BK;
   t.kmax = kmax;
   std::vector<__half> hi(rows * kmax, __float2half(0.f)), lo(rows * kmax, __float2half(0.f));
-  int unit = 16;
-  if (pixel_cols > 0) { unit = pixel_cols; while (unit % 16) unit += pixel_cols; }   // lcm(pixel_cols, 16)
+  t.cg = tc_cta_group();
+  const int base_unit = 16 * t.cg;                                                   // each CTA of a pair holds BN/2 rows of W
+  int unit = base_unit;
+  if (pixel_cols > 0) { unit = pixel_cols; while (unit % base_unit) unit += pixel_cols; }   // lcm(pixel_cols, 16*cg)
   // heavy bands first: with items dealt round-robin to the persistent CTAs this balances the tail
   std::vector<size_t> order(c.bands.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = i;
@@ -662,18 +755,18 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
     // band index -> (yi, xi) in row-major order of (by, bx)
     d.mloy = c.by[bi / c.bx.size()].mlo; d.mlox = c.bx[bi % c.bx.size()].mlo;
     d.N = b.N;
-    d.BN = tc_choose_bn(b.N, unit);
-    if (d.BN >= b.N) d.BN = (b.N + 15) & ~15;            // single tile: no alignment constraint
+    if (b.N <= tc_bn_max()) d.BN = (b.N + base_unit - 1) / base_unit * base_unit;   // single tile: no pixel-alignment constraint
+    else d.BN = tc_choose_bn(b.N, unit);
     d.ntiles = (b.N + d.BN - 1) / d.BN;
     t.bn_max = std::max(t.bn_max, d.BN);
     uint64_t kcols = (uint64_t)std::max(1, b.Ty * b.Tx) * t.ktot_pad;
-    if (!tc_make_map_2d(drv, &d.mapBhi, t.d_hi + row0_of[bi] * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)d.BN, err)) return false;
-    if (!tc_make_map_2d(drv, &d.mapBlo, t.d_lo + row0_of[bi] * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)d.BN, err)) return false;
+    if (!tc_make_map_2d(drv, &d.mapBhi, t.d_hi + row0_of[bi] * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)(d.BN / t.cg), err)) return false;
+    if (!tc_make_map_2d(drv, &d.mapBlo, t.d_lo + row0_of[bi] * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)(d.BN / t.cg), err)) return false;
     t.bands.push_back(d);
   }
   t.nbands = (int)t.bands.size();
   if (t.bn_max > TC_ACC_COLS) { *err = "n-tile wider than a TMEM accumulator"; return false; }
-  int stage_bytes = 2 * TC_BM * 128 + 2 * t.bn_max * 128;
+  int stage_bytes = 2 * TC_BM * 128 + 2 * (t.bn_max / t.cg) * 128;
   t.stages = std::min(8, (227 * 1024 - 4096) / stage_bytes);
   if (t.stages < 2) { *err = "not enough shared memory for a 2-stage pipeline"; return false; }
   if (cudaMalloc((void**)&t.d_bands, sizeof(TcBandDev) * std::max(1, t.nbands)) != cudaSuccess) { *err = "cudaMalloc (band table) failed"; return false; }
@@ -706,7 +799,8 @@ inline bool tc_finalize(TcDriver& drv, TcModelState& st, Transform* hyper, Trans
   };
   if (!pack(hyper, st.hyper) || !pack(syn, st.syn)) return false;
   if (!st.smem_attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(band_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(band_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(band_gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return false; }
     st.smem_attr_set = true;
   }
@@ -745,8 +839,10 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   P.B = B; P.hin = h; P.win = w; P.s = c.s; P.p = c.p;
   P.TH = TH; P.TW = TW; P.tiles_y = (h + TH - 1) / TH; P.tiles_x = (w + TW - 1) / TW;
   const int mtiles = P.tiles_x * P.tiles_y * B;
+  const int groups = (mtiles + t.cg - 1) / t.cg;
+  P.mtiles = mtiles;
   int item = 0;
-  for (auto& bd : t.bands) { bd.item_begin = item; item += mtiles * bd.ntiles; }
+  for (auto& bd : t.bands) { bd.item_begin = item; item += groups * bd.ntiles; }
   // the band table depends on the batch geometry only through item_begin: refresh it when that changes
   cudaError_t e = cudaSuccess;
   if (t.uploaded_mtiles != mtiles) {
@@ -764,12 +860,23 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   P.q = o.q; P.q_kind = o.q_kind; P.Cy = o.Cy; P.max_index = o.max_index; P.trunc = o.trunc ? 1 : 0; P.y_hat = o.y_hat; P.idx = o.idx;
   P.C1 = o.C1; P.has_res = o.has_res ? 1 : 0; P.tl_act = o.tl_act; P.tl_inverse = o.tl_inverse ? 1 : 0;
   P.gamma = o.gamma; P.gamma_stride = o.gamma_stride; P.beta = o.beta;
-  size_t smem = (size_t)t.stages * (2 * TC_BM * 128 + 2 * t.bn_max * 128) + 1024 + 64 * 8 + (size_t)(o.C1 * o.C1 + o.C1 + c.cout + 8) * 4 * (o.two_layer ? 1 : 0);
+  size_t smem = (size_t)t.stages * (2 * TC_BM * 128 + 2 * (t.bn_max / t.cg) * 128) + 1024 + 64 * 8 + (size_t)(o.C1 * o.C1 + o.C1 + c.cout + 8) * 4 * (o.two_layer ? 1 : 0);
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns
   if (smem > 227 * 1024) { *err = "shared memory budget exceeded"; return TC_ERROR; }
-  int grid = std::min(drv.num_sms, P.total_items);
-  if (grid <= 0) return TC_OK;
-  band_gemm_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mapAhi, mapAlo, P);
+  int units = std::min(drv.num_sms / t.cg, P.total_items);
+  if (units <= 0) return TC_OK;
+  if (t.cg == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * units)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, band_gemm_tc_kernel<2>, mapAhi, mapAlo, P);
+    if (e != cudaSuccess) { *err = std::string("band_gemm_tc_kernel<2> launch: ") + cudaGetErrorString(e); return TC_ERROR; }
+  } else {
+    band_gemm_tc_kernel<1><<<units, TC_THREADS, smem, s>>>(mapAhi, mapAlo, P);
+  }
   if (launches) (*launches)++;
   e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("band_gemm_tc_kernel launch: ") + cudaGetErrorString(e); return TC_ERROR; }

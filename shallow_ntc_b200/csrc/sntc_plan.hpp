@@ -78,6 +78,7 @@ struct ConvLayer {
   float* d_bias = nullptr;   // [cout] (zeros when !has_bias)
   // rgb-cell packing for final layers with tiny Cout: [k*k][cin_pad][4]
   float* d_w_rgb = nullptr;
+  std::vector<float> h_w_tail;   // [k*k][cin][3] + bias[3]: by-value kernel parameter of the constant-bank tail kernel
   // tensor-core packing (fp16 hi/lo), see sntc_kernels_tc.cuh
   void* d_w_hi = nullptr; void* d_w_lo = nullptr; float w_scale = 1.f; int cin_tc = 0; int n_tc_rows = 0;
   std::vector<size_t> tc_band_row0;
