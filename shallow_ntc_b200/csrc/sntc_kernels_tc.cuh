@@ -125,6 +125,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
     "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 // all previously issued MMAs of this thread arrive on `bar` when they complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -149,6 +150,13 @@ __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one lane of the (converged) warp; the surrounding code stays warp-uniform, so the compiler keeps the
+// operands of the TMA / MMA instructions in uniform registers instead of broadcasting them per instruction
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -190,6 +198,10 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
   asm volatile(
     "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_f16_t(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2) umma_f16_2sm(tmem_d, adesc, bdesc, idesc, accumulate); else umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 // commit of the pair's MMAs: arrives on the barrier at this smem offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
@@ -405,7 +417,9 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* sconst = reinterpret_cast<float*>(tmem_slot + 4);   // two-layer epilogue constants: gamma | beta | bias
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops
+  // (and the operands of the TMA / MMA instructions) on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int rank = CG == 2 ? (int)tcx::cluster_ctarank() : 0;
   const bool leader = rank == 0;
   const int unit0 = (int)blockIdx.x / CG, nunits = (int)gridDim.x / CG;   // persistent work units (CTAs or pairs)
@@ -427,82 +441,96 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
   if (CG == 2) tcx::cluster_sync_all(); else __syncthreads();
   tcx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = tcx::smem_u32(smem);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer (every CTA loads its own A tile and its own rows of W) =====
-      uint32_t g = 0;   // global k-step counter: the smem ring runs across work items
-      for (int item = unit0; item < P.total_items; item += nunits) {
-        const TcItem it = tc_decode_item<CG>(P, item, rank);
-        const TcBandDev& bd = P.bands[it.band];
-        const int nk = bd.Ty * bd.Tx * P.kblocks;
-        const int wrows = bd.BN / CG;                                  // W box rows per CTA
-        const int wrow0 = it.n0 + rank * (it.mma_n / CG);              // this CTA supplies columns [rank*mma_n/CG, ...)
-        const uint32_t tx_bytes = (uint32_t)CG * (2 * a_bytes + 2 * (uint32_t)wrows * 128);
-        for (int k = 0; k < nk; ++k, ++g) {
-          const int st = g % P.stages;
-          const uint32_t ph = (g / P.stages) & 1u;
-          tcx::mbar_wait(&empty_bar[st], ph ^ 1u);
-          const int tap = k / P.kblocks, kb = k - tap * P.kblocks;
-          const int jy = tap / bd.Tx, jx = tap - jy * bd.Tx;
-          uint8_t* sa = smem + (size_t)st * stage_bytes;
-          const int cx = bd.mlox + it.ix0 - jx, cy = bd.mloy + it.iy0 - jy, cc = kb * TC_BK;
-          const int kcol = k * TC_BK;
-          if (CG == 2) {
-            if (leader) tcx::mbar_expect_tx(&full_bar[st], tx_bytes);
-            const uint32_t fb = tcx::mapa_u32(tcx::smem_u32(&full_bar[st]), 0);   // the leader's full barrier
-            tcx::tma_load_4d_2sm(sa, &mapAhi, fb, cc, cx, cy, it.b);
-            tcx::tma_load_4d_2sm(sa + a_bytes, &mapAlo, fb, cc, cx, cy, it.b);
-            tcx::tma_load_2d_2sm(sa + 2 * a_bytes, &bd.mapBhi, fb, kcol, wrow0);
-            tcx::tma_load_2d_2sm(sa + 2 * a_bytes + b_slot, &bd.mapBlo, fb, kcol, wrow0);
-          } else {
-            tcx::mbar_expect_tx(&full_bar[st], tx_bytes);
-            tcx::tma_load_4d(sa, &mapAhi, &full_bar[st], cc, cx, cy, it.b);
-            tcx::tma_load_4d(sa + a_bytes, &mapAlo, &full_bar[st], cc, cx, cy, it.b);
-            tcx::tma_load_2d(sa + 2 * a_bytes, &bd.mapBhi, &full_bar[st], kcol, wrow0);
-            tcx::tma_load_2d(sa + 2 * a_bytes + b_slot, &bd.mapBlo, &full_bar[st], kcol, wrow0);
+    // ===== TMA producer: the whole warp runs the (uniform) loop, one elected lane issues the copies.
+    // Every CTA loads its own A tile and its own rows of W. =====
+    uint32_t st = 0, ph = 0;   // smem ring position: runs across work items
+    for (int item = unit0; item < P.total_items; item += nunits) {
+      const TcItem it = tc_decode_item<CG>(P, item, rank);
+      const TcBandDev& bd = P.bands[it.band];
+      const int Ty = bd.Ty, Tx = bd.Tx;
+      const int wrows = bd.BN / CG;                                  // W box rows per CTA
+      const int wrow0 = it.n0 + rank * (it.mma_n / CG);              // this CTA supplies columns [rank*mma_n/CG, ...)
+      const uint32_t tx_bytes = (uint32_t)CG * (2 * a_bytes + 2 * (uint32_t)wrows * 128);
+      const int cx0 = bd.mlox + it.ix0, cy0 = bd.mloy + it.iy0;
+      int kcol = 0;
+      for (int jy = 0; jy < Ty; ++jy)
+        for (int jx = 0; jx < Tx; ++jx)
+          for (int kb = 0; kb < P.kblocks; ++kb, kcol += TC_BK) {
+            tcx::mbar_wait(&empty_bar[st], ph ^ 1u);
+            if (tcx::elect_one()) {
+              uint8_t* sa = smem + (size_t)st * stage_bytes;
+              const int cx = cx0 - jx, cy = cy0 - jy, cc = kb * TC_BK;
+              if (CG == 2) {
+                if (leader) tcx::mbar_expect_tx(&full_bar[st], tx_bytes);
+                const uint32_t fb = tcx::mapa_u32(tcx::smem_u32(&full_bar[st]), 0);   // the leader's full barrier
+                tcx::tma_load_4d_2sm(sa, &mapAhi, fb, cc, cx, cy, it.b);
+                tcx::tma_load_4d_2sm(sa + a_bytes, &mapAlo, fb, cc, cx, cy, it.b);
+                tcx::tma_load_2d_2sm(sa + 2 * a_bytes, &bd.mapBhi, fb, kcol, wrow0);
+                tcx::tma_load_2d_2sm(sa + 2 * a_bytes + b_slot, &bd.mapBlo, fb, kcol, wrow0);
+              } else {
+                tcx::mbar_expect_tx(&full_bar[st], tx_bytes);
+                tcx::tma_load_4d(sa, &mapAhi, &full_bar[st], cc, cx, cy, it.b);
+                tcx::tma_load_4d(sa + a_bytes, &mapAlo, &full_bar[st], cc, cx, cy, it.b);
+                tcx::tma_load_2d(sa + 2 * a_bytes, &bd.mapBhi, &full_bar[st], kcol, wrow0);
+                tcx::tma_load_2d(sa + 2 * a_bytes + b_slot, &bd.mapBlo, &full_bar[st], kcol, wrow0);
+              }
+            }
+            __syncwarp();
+            if (++st == (uint32_t)P.stages) { st = 0; ph ^= 1u; }
           }
-        }
-      }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ===== MMA issuer (leader CTA only) =====
-      uint32_t g = 0, j = 0;
+    if (leader) {
+      // ===== MMA issuer (leader CTA only): warp-uniform loop, one elected lane issues the MMAs + commits =====
+      // descriptor = fixed high word | (smem address >> 4) in the low word; +2 per K=16 step inside the swizzle row
+      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      uint32_t st = 0, ph = 0, j = 0;
       for (int item = unit0; item < P.total_items; item += nunits, ++j) {
         const TcItem it = tc_decode_item<CG>(P, item, 0);
         const TcBandDev& bd = P.bands[it.band];
-        const int nk = bd.Ty * bd.Tx * P.kblocks;
+        const int ntaps = bd.Ty * bd.Tx;
         const uint32_t buf = j & 1u;
         tcx::mbar_wait(&tmem_empty_bar[buf], ((j >> 1) & 1u) ^ 1u);   // the epilogue(s) drained this accumulator
         tcx::tc_fence_after();
         const uint32_t tacc = tmem_base + buf * TC_ACC_COLS;
         const uint32_t idesc = tcx::make_idesc(TC_BM * CG, it.mma_n);
         uint32_t acc = 0;
-        for (int k = 0; k < nk; ++k, ++g) {
-          const int st = g % P.stages;
-          const uint32_t ph = (g / P.stages) & 1u;
-          tcx::mbar_wait(&full_bar[st], ph);
-          tcx::tc_fence_after();
-          const uint32_t sa = tcx::smem_u32(smem + (size_t)st * stage_bytes);
-          const uint64_t a_hi = tcx::make_smem_desc(sa), a_lo = tcx::make_smem_desc(sa + a_bytes);
-          const uint64_t b_hi = tcx::make_smem_desc(sa + 2 * a_bytes), b_lo = tcx::make_smem_desc(sa + 2 * a_bytes + b_slot);
-          const int kb = k % P.kblocks;
-          const int nm = (kb == P.kblocks - 1) ? P.last_kmma : 4;
-          // lo*hi and hi*lo first (small terms), hi*hi last
-          if (CG == 2) {
-            for (int q = 0; q < nm; ++q) { tcx::umma_f16_2sm(tacc, a_lo + 2 * q, b_hi + 2 * q, idesc, acc); acc = 1; }
-            for (int q = 0; q < nm; ++q) tcx::umma_f16_2sm(tacc, a_hi + 2 * q, b_lo + 2 * q, idesc, 1);
-            for (int q = 0; q < nm; ++q) tcx::umma_f16_2sm(tacc, a_hi + 2 * q, b_hi + 2 * q, idesc, 1);
-            tcx::umma_commit_2sm(&empty_bar[st], 3);   // frees this smem stage in both CTAs
-          } else {
-            for (int q = 0; q < nm; ++q) { tcx::umma_f16(tacc, a_lo + 2 * q, b_hi + 2 * q, idesc, acc); acc = 1; }
-            for (int q = 0; q < nm; ++q) tcx::umma_f16(tacc, a_hi + 2 * q, b_lo + 2 * q, idesc, 1);
-            for (int q = 0; q < nm; ++q) tcx::umma_f16(tacc, a_hi + 2 * q, b_hi + 2 * q, idesc, 1);
-            tcx::umma_commit(&empty_bar[st]);
+        for (int tap = 0; tap < ntaps; ++tap)
+          for (int kb = 0; kb < P.kblocks; ++kb) {
+            tcx::mbar_wait(&full_bar[st], ph);
+            tcx::tc_fence_after();
+            const uint32_t sa = smem_base + st * stage_bytes;
+            const uint32_t a_hi = (((sa) & 0x3FFFFu) >> 4) | (1u << 16), a_lo = (((sa + a_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_hi = (((sa + 2 * a_bytes) & 0x3FFFFu) >> 4) | (1u << 16), b_lo = (((sa + 2 * a_bytes + b_slot) & 0x3FFFFu) >> 4) | (1u << 16);
+            const int nm = (kb == P.kblocks - 1) ? P.last_kmma : 4;
+            if (tcx::elect_one()) {
+              // lo*hi and hi*lo first (small terms), hi*hi last
+              if (nm == 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_lo + 2 * q, desc_hi), tcx::desc64(b_hi + 2 * q, desc_hi), idesc, q == 0 ? acc : 1u); }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_hi + 2 * q, desc_hi), tcx::desc64(b_lo + 2 * q, desc_hi), idesc, 1u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_hi + 2 * q, desc_hi), tcx::desc64(b_hi + 2 * q, desc_hi), idesc, 1u);
+              } else {
+                for (int q = 0; q < nm; ++q) { tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_lo + 2 * q, desc_hi), tcx::desc64(b_hi + 2 * q, desc_hi), idesc, q == 0 ? acc : 1u); }
+                for (int q = 0; q < nm; ++q) tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_hi + 2 * q, desc_hi), tcx::desc64(b_lo + 2 * q, desc_hi), idesc, 1u);
+                for (int q = 0; q < nm; ++q) tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_hi + 2 * q, desc_hi), tcx::desc64(b_hi + 2 * q, desc_hi), idesc, 1u);
+              }
+              if (CG == 2) tcx::umma_commit_2sm(&empty_bar[st], 3);   // frees this smem stage in both CTAs
+              else tcx::umma_commit(&empty_bar[st]);
+            }
+            __syncwarp();
+            acc = 1;
+            if (++st == (uint32_t)P.stages) { st = 0; ph ^= 1u; }
           }
+        if (tcx::elect_one()) {   // accumulator complete
+          if (CG == 2) tcx::umma_commit_2sm(&tmem_full_bar[buf], 3); else tcx::umma_commit(&tmem_full_bar[buf]);
         }
-        if (CG == 2) tcx::umma_commit_2sm(&tmem_full_bar[buf], 3); else tcx::umma_commit(&tmem_full_bar[buf]);   // accumulator complete
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
