@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -31,9 +32,11 @@ enum { TC_EPI_PLAIN = 0, TC_EPI_HYPER_FINAL = 1, TC_EPI_TWO_LAYER = 2 };
 
 constexpr int TC_BM = 128;        // cells per tile (UMMA M)
 constexpr int TC_BK = 64;         // fp16 channels per k-block (128 bytes = one swizzle row)
-constexpr int TC_THREADS = 256;
+constexpr int TC_EPI_WARPS = 8;    // epilogue warps 4..11: two per TMEM lane quarter (they split the columns)
+constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;
 constexpr int TC_ACC_COLS = 256;  // TMEM columns per accumulator buffer (two buffers = all 512 columns)
 constexpr int TC_MAX_BANDS = 16;
+constexpr int TC_TRACE_ITEMS = 64;
 
 // One band of a layer, resident in device memory (tensor maps must be 64-byte aligned).
 struct alignas(64) TcBandDev {
@@ -66,6 +69,8 @@ struct TcParams {
   float* y_hat; uint8_t* idx;              // + out_hi/out_lo = planes of y_hat [B,hout,wout,Cy]
   // TC_EPI_TWO_LAYER: columns of one output pixel = base[0,C1) (|| res[C1,2C1)); out_f32 = t [B,hout,wout,C1]
   int C1, has_res, tl_act, tl_inverse; const float* gamma; int gamma_stride; const float* beta;
+  int vec16;          // fast epilogue: cout % 16 == 0, Cy % 16 == 0 and every epilogue tensor 32-byte aligned
+  long long* trace;   // debug timeline (SNTC_TC_TRACE=1): [unit][TC_TRACE_ITEMS][8] clock64 stamps, leader CTA only
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -146,6 +151,22 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                 "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                 "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr) : "memory");
+}
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane and request
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void ldg256_nc(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -275,14 +296,12 @@ __device__ __forceinline__ TcItem tc_decode_item(const TcParams& P, int item, in
   return it;
 }
 
-// plain / hyper-final epilogue for 8 consecutive columns n..n+7 of one cell (cout % 8 == 0)
-__device__ __forceinline__ void tc_epi_vec8(const TcParams& P, const TcBandDev& bd, int b, int my, int mx, int n, float* v) {
-  const int co = n % P.cout, ph = n / P.cout;
-  const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
+// plain / hyper-final epilogue for 8 consecutive columns co..co+7 of output pixel (b, oy, ox)  (cout % 8 == 0)
+__device__ __forceinline__ void tc_epi_vec8(const TcParams& P, const float* sbias, int b, int oy, int ox, int co, float* v) {
   if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) return;
   const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
-  float4 b0 = __ldg(reinterpret_cast<const float4*>(P.bias + co));
-  float4 b1 = __ldg(reinterpret_cast<const float4*>(P.bias + co + 4));
+  float4 b0 = *reinterpret_cast<const float4*>(sbias + co);       // bias staged in shared memory
+  float4 b1 = *reinterpret_cast<const float4*>(sbias + co + 4);
   float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], P.inv_scale, bb[i]);
@@ -320,8 +339,85 @@ __device__ __forceinline__ void tc_epi_vec8(const TcParams& P, const TcBandDev& 
   }
 }
 
+// 16 consecutive columns co..co+15 (cout % 16 == 0, Cy % 16 == 0, all tensors 32-byte aligned): every global access
+// is a full 32-byte sector (256-bit loads / stores).
+__device__ __forceinline__ void store16_planes(__half* hi, __half* lo, size_t off, const float* v) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __half h0, l0, h1, l1;
+    split_f16(v[2 * i], h0, l0); split_f16(v[2 * i + 1], h1, l1);
+    h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  }
+  tcx::stg256(hi + off, h);
+  tcx::stg256(lo + off, l);
+}
+__device__ __forceinline__ void store16_f32(float* o, const float* v) {
+  tcx::stg256(o, reinterpret_cast<const uint32_t*>(v));
+  tcx::stg256(o + 8, reinterpret_cast<const uint32_t*>(v) + 8);
+}
+__device__ __forceinline__ void load_q16(const void* q, int kind, size_t e, float* out) {
+  if (kind == 0) {
+    tcx::ldg256_nc(reinterpret_cast<const float*>(q) + e, reinterpret_cast<uint32_t*>(out));
+    tcx::ldg256_nc(reinterpret_cast<const float*>(q) + e + 8, reinterpret_cast<uint32_t*>(out) + 8);
+  } else if (kind == 1) {
+    uint32_t r[8];
+    tcx::ldg256_nc(reinterpret_cast<const int16_t*>(q) + e, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { out[2 * i] = (float)(int16_t)(r[i] & 0xFFFFu); out[2 * i + 1] = (float)(int16_t)(r[i] >> 16); }
+  } else {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const int8_t*>(q) + e));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      out[4 * i] = (float)(int8_t)(w[i] & 0xFFu); out[4 * i + 1] = (float)(int8_t)((w[i] >> 8) & 0xFFu);
+      out[4 * i + 2] = (float)(int8_t)((w[i] >> 16) & 0xFFu); out[4 * i + 3] = (float)(int8_t)(w[i] >> 24);
+    }
+  }
+}
+__device__ __forceinline__ void tc_epi_vec16(const TcParams& P, const float* sbias, int b, int oy, int ox, int co, const uint32_t* raw) {
+  if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) return;
+  const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
+  float v[16];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 bb = *reinterpret_cast<const float4*>(sbias + co + 4 * g);   // bias staged in shared memory
+    v[4 * g] = fmaf(__uint_as_float(raw[4 * g]), P.inv_scale, bb.x); v[4 * g + 1] = fmaf(__uint_as_float(raw[4 * g + 1]), P.inv_scale, bb.y);
+    v[4 * g + 2] = fmaf(__uint_as_float(raw[4 * g + 2]), P.inv_scale, bb.z); v[4 * g + 3] = fmaf(__uint_as_float(raw[4 * g + 3]), P.inv_scale, bb.w);
+  }
+  if (P.epi == TC_EPI_HYPER_FINAL) {
+    if (P.out_f32) store16_f32(P.out_f32 + pix * P.cout + co, v);
+    if (co < P.Cy) {   // mu half: y_hat = q + mu                     mshyper/models.py:278
+      const size_t e = pix * P.Cy + co;
+      float y[16];
+      load_q16(P.q, P.q_kind, e, y);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) y[i] = __fadd_rn(y[i], v[i]);
+      if (P.y_hat) store16_f32(P.y_hat + e, y);
+      if (P.out_hi) store16_planes(P.out_hi, P.out_lo, e, y);
+    } else if (P.idx) {   // sigma half: idx = round(clamp(exp(sigma), 0, S-1))   :274-276
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        o[i] = (uint32_t)scale_index(v[4 * i], P.max_index, P.trunc) | ((uint32_t)scale_index(v[4 * i + 1], P.max_index, P.trunc) << 8) |
+               ((uint32_t)scale_index(v[4 * i + 2], P.max_index, P.trunc) << 16) | ((uint32_t)scale_index(v[4 * i + 3], P.max_index, P.trunc) << 24);
+      *reinterpret_cast<uint4*>(P.idx + pix * P.Cy + (co - P.Cy)) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], P.act);
+  if (P.out_hi) store16_planes(P.out_hi, P.out_lo, pix * P.cout + co, v);
+  if (P.out_f32) store16_f32(P.out_f32 + pix * P.cout + co, v);
+}
+
+// The band fields the epilogue needs, copied to registers once per work item: the band table lives in global
+// memory and the epilogue's own stores would otherwise force a reload (possible aliasing) per column group.
+struct TcBandRegs { int N, nphx, phy0, phx0; };
+
 // generic scalar epilogue (final layers with cout = 3, ...)
-__device__ __forceinline__ void tc_epi_scalar8(const TcParams& P, const TcBandDev& bd, int b, int my, int mx, int n, const float* v) {
+__device__ __forceinline__ void tc_epi_scalar8(const TcParams& P, const TcBandRegs& bd, const float* sbias, int b, int my, int mx, int n, const float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int nn = n + i;
@@ -329,7 +425,7 @@ __device__ __forceinline__ void tc_epi_scalar8(const TcParams& P, const TcBandDe
     const int co = nn % P.cout, ph = nn / P.cout;
     const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
     if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) continue;
-    float x = apply_act(fmaf(v[i], P.inv_scale, __ldg(P.bias + co)), P.act);
+    float x = apply_act(fmaf(v[i], P.inv_scale, sbias[co]), P.act);
     const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
     if (P.out_f32) P.out_f32[pix * P.cout + co] = x;
     if ((P.out_u8 || P.out_crop) && oy < P.H && ox < P.W) {
@@ -375,11 +471,11 @@ __device__ __forceinline__ void tc_epi_two_layer_pixel(const TcParams& P, const 
 }
 
 template <int C1, bool RES>
-__device__ __forceinline__ void tc_epi_two_layer(const TcParams& P, const TcBandDev& bd, const TcItem& it, uint32_t trow, int b, int my, int mx,
-                                                 bool cell_ok, const float* sgamma, const float* sbeta, const float* sbias) {
+__device__ __forceinline__ void tc_epi_two_layer(const TcParams& P, const TcBandRegs& bd, const TcItem& it, uint32_t trow, int b, int my, int mx,
+                                                 bool cell_ok, const float* sgamma, const float* sbeta, const float* sbias, int pp0, int pstep) {
   constexpr int PW = RES ? 2 * C1 : C1;
   const int npx = it.nrows / PW;
-  for (int pp = 0; pp < npx; ++pp) {
+  for (int pp = pp0; pp < npx; pp += pstep) {
     uint32_t raw[PW];
 #pragma unroll
     for (int c = 0; c < PW; c += 4) tcx::tmem_ld4_nowait(trow + (uint32_t)(pp * PW + c), raw + c);
@@ -427,15 +523,15 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
   if (warp == 0 && lane == 0) { tcx::prefetch_tmap(&mapAhi); tcx::prefetch_tmap(&mapAlo); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < P.stages; ++i) { tcx::mbar_init(&full_bar[i], 1); tcx::mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { tcx::mbar_init(&tmem_full_bar[i], 1); tcx::mbar_init(&tmem_empty_bar[i], 4 * CG); }
+    for (int i = 0; i < 2; ++i) { tcx::mbar_init(&tmem_full_bar[i], 1); tcx::mbar_init(&tmem_empty_bar[i], TC_EPI_WARPS * CG); }
     tcx::fence_barrier_init();
   }
   if (warp == 2) { if (CG == 2) tcx::tmem_alloc_2sm(tmem_slot, 2 * TC_ACC_COLS); else tcx::tmem_alloc(tmem_slot, 2 * TC_ACC_COLS); }
-  if (warp >= 4 && P.epi == TC_EPI_TWO_LAYER) {
-    const int t = threadIdx.x - 128, C1 = P.C1, nb = P.cout;
-    if (P.gamma) for (int i = t; i < C1 * C1; i += 128) sconst[i] = P.gamma[(size_t)(i / C1) * P.gamma_stride + (i % C1)];
-    if (P.beta) for (int i = t; i < C1; i += 128) sconst[C1 * C1 + i] = P.beta[i];
-    for (int i = t; i < nb; i += 128) sconst[C1 * C1 + C1 + i] = P.bias[i];
+  if (warp >= 4) {   // epilogue constants -> shared memory: gamma [C1*C1] | beta [C1] | bias [cout]  (C1 = 0 unless two-layer)
+    const int t = threadIdx.x - 128, C1 = P.epi == TC_EPI_TWO_LAYER ? P.C1 : 0, nb = P.cout, nt = 32 * TC_EPI_WARPS;
+    if (C1 && P.gamma) for (int i = t; i < C1 * C1; i += nt) sconst[i] = P.gamma[(size_t)(i / C1) * P.gamma_stride + (i % C1)];
+    if (C1 && P.beta) for (int i = t; i < C1; i += nt) sconst[C1 * C1 + i] = P.beta[i];
+    for (int i = t; i < nb; i += nt) sconst[C1 * C1 + C1 + i] = P.bias[i];
   }
   tcx::tc_fence_before();
   if (CG == 2) tcx::cluster_sync_all(); else __syncthreads();
@@ -456,6 +552,9 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
       const uint32_t tx_bytes = (uint32_t)CG * (2 * a_bytes + 2 * (uint32_t)wrows * 128);
       const int cx0 = bd.mlox + it.ix0, cy0 = bd.mloy + it.iy0;
       int kcol = 0;
+      const int jt = (item - unit0) / nunits;
+      long long* tr = (P.trace && leader && jt < TC_TRACE_ITEMS) ? P.trace + ((size_t)unit0 * TC_TRACE_ITEMS + jt) * 8 : nullptr;
+      if (tr && lane == 0) { tr[0] = clock64(); tr[7] = item; }
       for (int jy = 0; jy < Ty; ++jy)
         for (int jx = 0; jx < Tx; ++jx)
           for (int kb = 0; kb < P.kblocks; ++kb, kcol += TC_BK) {
@@ -481,6 +580,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
             __syncwarp();
             if (++st == (uint32_t)P.stages) { st = 0; ph ^= 1u; }
           }
+      if (tr && lane == 0) tr[1] = clock64();
     }
   } else if (warp == 1) {
     if (leader) {
@@ -493,8 +593,10 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
         const TcBandDev& bd = P.bands[it.band];
         const int ntaps = bd.Ty * bd.Tx;
         const uint32_t buf = j & 1u;
+        long long* tr = (P.trace && j < TC_TRACE_ITEMS) ? P.trace + ((size_t)unit0 * TC_TRACE_ITEMS + j) * 8 : nullptr;
         tcx::mbar_wait(&tmem_empty_bar[buf], ((j >> 1) & 1u) ^ 1u);   // the epilogue(s) drained this accumulator
         tcx::tc_fence_after();
+        if (tr && lane == 0) tr[2] = clock64();
         const uint32_t tacc = tmem_base + buf * TC_ACC_COLS;
         const uint32_t idesc = tcx::make_idesc(TC_BM * CG, it.mma_n);
         uint32_t acc = 0;
@@ -502,6 +604,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
           for (int kb = 0; kb < P.kblocks; ++kb) {
             tcx::mbar_wait(&full_bar[st], ph);
             tcx::tc_fence_after();
+            if (tr && lane == 0 && tap == 0 && kb == 0) tr[3] = clock64();
             const uint32_t sa = smem_base + st * stage_bytes;
             const uint32_t a_hi = (((sa) & 0x3FFFFu) >> 4) | (1u << 16), a_lo = (((sa + a_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t b_hi = (((sa + 2 * a_bytes) & 0x3FFFFu) >> 4) | (1u << 16), b_lo = (((sa + 2 * a_bytes + b_slot) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -531,33 +634,71 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
           if (CG == 2) tcx::umma_commit_2sm(&tmem_full_bar[buf], 3); else tcx::umma_commit(&tmem_full_bar[buf]);
         }
         __syncwarp();
+        if (tr && lane == 0) tr[4] = clock64();
       }
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> global (every CTA drains its own 128 accumulator rows) =====
-    const int ew = warp - 4;                    // TMEM lanes [32*ew, 32*ew+32)
+    const int ew = warp & 3;                    // TMEM lanes [32*ew, 32*ew+32): a warp may only touch the quarter (warp % 4)
+    const int eh = (warp - 4) >> 2;             // which of the quarter's warps: they take alternate column chunks / pixels
+    constexpr int EH = TC_EPI_WARPS / 4;
     const int r = ew * 32 + lane;               // row of the tile = cell
-    const float* sgamma = sconst; const float* sbeta = sconst + P.C1 * P.C1; const float* sbias = sbeta + P.C1;
+    const int C1s = P.epi == TC_EPI_TWO_LAYER ? P.C1 : 0;
+    const float* sgamma = sconst; const float* sbeta = sconst + C1s * C1s; const float* sbias = sbeta + C1s;
     uint32_t j = 0;
     for (int item = unit0; item < P.total_items; item += nunits, ++j) {
       const TcItem it = tc_decode_item<CG>(P, item, rank);
-      const TcBandDev& bd = P.bands[it.band];
-      const int nk = bd.Ty * bd.Tx * P.kblocks;
+      const TcBandDev& bdg = P.bands[it.band];
+      const TcBandRegs bd{bdg.N, bdg.nphx, bdg.phy0, bdg.phx0};
+      const int nk = bdg.Ty * bdg.Tx * P.kblocks;
       const uint32_t buf = j & 1u;
       const int iy = it.iy0 + r / P.TW, ix = it.ix0 + r % P.TW;
       const bool cell_ok = iy < P.hin && ix < P.win && !it.dup;
-      const int my = bd.mloy + iy, mx = bd.mlox + ix;
+      const int my = bdg.mloy + iy, mx = bdg.mlox + ix;
+      long long* tr = (P.trace && leader && warp == 4 && lane == 0 && j < TC_TRACE_ITEMS) ? P.trace + ((size_t)unit0 * TC_TRACE_ITEMS + j) * 8 : nullptr;
       tcx::mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1u);
       tcx::tc_fence_after();
+      if (tr) tr[5] = clock64();
       const uint32_t trow = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(ew * 32) << 16);
       if (P.epi == TC_EPI_TWO_LAYER && nk > 0) {
-        if (P.C1 == 12) { if (P.has_res) tc_epi_two_layer<12, true>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias);
-                          else tc_epi_two_layer<12, false>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias); }
-        else            { if (P.has_res) tc_epi_two_layer<24, true>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias);
-                          else tc_epi_two_layer<24, false>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias); }
+        if (P.C1 == 12) { if (P.has_res) tc_epi_two_layer<12, true>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias, eh, EH);
+                          else tc_epi_two_layer<12, false>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias, eh, EH); }
+        else            { if (P.has_res) tc_epi_two_layer<24, true>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias, eh, EH);
+                          else tc_epi_two_layer<24, false>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias, eh, EH); }
       } else {
+        if (P.vec16 && nk > 0) {
+          // 32-column chunks (one tcgen05.ld.x32 each), the quarter's warps take alternate chunks; the load of the
+          // next chunk is in flight while this one is processed
+          int co = it.n0 % P.cout, ph = it.n0 / P.cout, c_at = 0;
+          int last_ph = -1, oy = 0, ox = 0;
+          uint32_t raw[32], nxt[32];
+          int c = 32 * eh;
+          if (c < it.mma_n) tcx::tmem_ld32_nowait(trow + (uint32_t)c, nxt);
+          for (; c < it.mma_n; c += 32 * EH) {
+            tcx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) raw[i] = nxt[i];
+            if (c + 32 * EH < it.mma_n) tcx::tmem_ld32_nowait(trow + (uint32_t)(c + 32 * EH), nxt);
+            if (!cell_ok) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int cc = c + 16 * h;
+              if (it.n0 + cc >= bd.N) break;
+              co += cc - c_at; c_at = cc;
+              while (co >= P.cout) { co -= P.cout; ++ph; }
+              if (ph != last_ph) {
+                last_ph = ph;
+                oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p; ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
+              }
+              tc_epi_vec16(P, sbias, it.b, oy, ox, co, raw + 16 * h);
+            }
+          }
+        } else {
         const bool vec = (P.cout % 8) == 0;
-        for (int c = 0; c < it.mma_n; c += 16) {
+        // (co, phase) of column n = it.n0 + c advance incrementally: no per-group division by cout
+        int co = it.n0 % P.cout, ph = it.n0 / P.cout, c_at = 0;
+        int last_ph = -1, oy = 0, ox = 0;
+        for (int c = 16 * eh; c < it.mma_n; c += 16 * EH) {
           uint32_t raw[16];
           if (nk > 0) {                           // warp-wide TMEM loads: executed by all lanes
             tcx::tmem_ld8_nowait(trow + (uint32_t)c, raw);
@@ -575,9 +716,19 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[h8 * 8 + i]);
-            if (vec) tc_epi_vec8(P, bd, it.b, my, mx, n, v);
-            else tc_epi_scalar8(P, bd, it.b, my, mx, n, v);
+            if (vec) {
+              co += (c + h8 * 8) - c_at; c_at = c + h8 * 8;
+              while (co >= P.cout) { co -= P.cout; ++ph; }
+              if (ph != last_ph) {
+                last_ph = ph;
+                oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p; ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
+              }
+              tc_epi_vec8(P, sbias, it.b, oy, ox, co, v);
+            } else {
+              tc_epi_scalar8(P, bd, sbias, it.b, my, mx, n, v);
+            }
           }
+        }
         }
       }
       // this warp is done reading accumulator `buf`: tell the (leader's) MMA issuer
@@ -587,6 +738,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
         if (CG == 2) tcx::mbar_arrive_cluster(tcx::mapa_u32(tcx::smem_u32(&tmem_empty_bar[buf]), 0));
         else tcx::mbar_arrive(&tmem_empty_bar[buf]);
       }
+      if (tr) tr[6] = clock64();
     }
   }
   tcx::tc_fence_before();
@@ -795,7 +947,8 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
   t.nbands = (int)t.bands.size();
   if (t.bn_max > TC_ACC_COLS) { *err = "n-tile wider than a TMEM accumulator"; return false; }
   int stage_bytes = 2 * TC_BM * 128 + 2 * (t.bn_max / t.cg) * 128;
-  t.stages = std::min(8, (227 * 1024 - 4096) / stage_bytes);
+  const int reserve = 2048 + (c.cout + 700) * 4;   // alignment slack + barriers + epilogue constants (gamma | beta | bias)
+  t.stages = std::min(8, (227 * 1024 - reserve) / stage_bytes);
   if (t.stages < 2) { *err = "not enough shared memory for a 2-stage pipeline"; return false; }
   if (cudaMalloc((void**)&t.d_bands, sizeof(TcBandDev) * std::max(1, t.nbands)) != cudaSuccess) { *err = "cudaMalloc (band table) failed"; return false; }
   owned.push_back(t.d_bands);
@@ -888,11 +1041,28 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   P.q = o.q; P.q_kind = o.q_kind; P.Cy = o.Cy; P.max_index = o.max_index; P.trunc = o.trunc ? 1 : 0; P.y_hat = o.y_hat; P.idx = o.idx;
   P.C1 = o.C1; P.has_res = o.has_res ? 1 : 0; P.tl_act = o.tl_act; P.tl_inverse = o.tl_inverse ? 1 : 0;
   P.gamma = o.gamma; P.gamma_stride = o.gamma_stride; P.beta = o.beta;
-  size_t smem = (size_t)t.stages * (2 * TC_BM * 128 + 2 * (t.bn_max / t.cg) * 128) + 1024 + 64 * 8 + (size_t)(o.C1 * o.C1 + o.C1 + c.cout + 8) * 4 * (o.two_layer ? 1 : 0);
+  {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
+    bool ok = c.cout % 16 == 0 && (!o.hyper_final || o.Cy % 16 == 0) && !o.two_layer && !o.u8 && !o.crop;
+    ok = ok && al(o.hi) && al(o.lo) && al(o.f32) && al(o.q) && al(o.y_hat) && al(o.idx);
+    // n-tiles must start on a 16-column boundary and the mma width is a multiple of 32 only when BN is: chunks are 32 wide,
+    // the last one may be half-used
+    for (auto& bd : t.bands) ok = ok && bd.BN % 16 == 0;
+    P.vec16 = ok ? 1 : 0;
+  }
+  size_t smem = (size_t)t.stages * (2 * TC_BM * 128 + 2 * (t.bn_max / t.cg) * 128) + 1024 + 64 * 8 + (size_t)((o.two_layer ? o.C1 * o.C1 + o.C1 : 0) + c.cout + 8) * 4;
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns
   if (smem > 227 * 1024) { *err = "shared memory budget exceeded"; return TC_ERROR; }
   int units = std::min(drv.num_sms / t.cg, P.total_items);
   if (units <= 0) return TC_OK;
+  static const bool trace_on = tc_env_int("SNTC_TC_TRACE", 0) != 0;
+  long long* d_trace = nullptr;
+  const size_t trace_n = (size_t)units * TC_TRACE_ITEMS * 8;
+  if (trace_on) {
+    if (cudaMalloc((void**)&d_trace, trace_n * 8) != cudaSuccess) { *err = "trace alloc failed"; return TC_ERROR; }
+    cudaMemsetAsync(d_trace, 0, trace_n * 8, s);
+    P.trace = d_trace;
+  }
   if (t.cg == 2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(2 * units)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -908,6 +1078,22 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   if (launches) (*launches)++;
   e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("band_gemm_tc_kernel launch: ") + cudaGetErrorString(e); return TC_ERROR; }
+  if (trace_on) {   // debug only: synchronous dump of the per-item timeline of a few units
+    std::vector<long long> h(trace_n);
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h.data(), d_trace, trace_n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_trace);
+    fprintf(stderr, "[tc-trace] layer cin=%d cout=%d k=%d s=%d items=%d units=%d cg=%d stages=%d bn_max=%d\n", c.cin, c.cout, c.k, c.s, P.total_items, units, t.cg, t.stages, t.bn_max);
+    for (int u : {0, units / 2, units - 1}) {
+      const long long* b = h.data() + (size_t)u * TC_TRACE_ITEMS * 8;
+      long long t0 = b[0];
+      for (int j = 0; j < TC_TRACE_ITEMS && b[j * 8 + 5] != 0; ++j) {
+        const long long* r = b + j * 8;
+        fprintf(stderr, "[tc-trace]  unit %3d item %5lld: tma %7lld..%7lld  mma start %7lld first-data %7lld issued %7lld  epi %7lld..%7lld\n", u, r[7],
+                r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0);
+      }
+    }
+  }
   return TC_OK;
 }
 
