@@ -12,6 +12,7 @@
 #include "sntc_plan.hpp"
 #include "sntc_kernels_f32.cuh"
 #include "sntc_kernels_tc.cuh"
+#include "sntc_kernels_tail_tc.cuh"
 
 using namespace sntc;
 
@@ -695,7 +696,7 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         if (op_on_tc(m, t, is_hyper, i)) max_pl = std::max(max_pl, (size_t)B * ch * cw * c.cin * 2);
         ch *= c.s; cw *= c.s;
         max_f32 = std::max(max_f32, (size_t)B * ch * cw * c.cout * 4);
-        max_pl = std::max(max_pl, (size_t)B * ch * cw * c.cout * 2);
+        max_pl = std::max(max_pl, (size_t)B * ch * cw * std::max(c.cout, 32) * 2);   // >= the 16-padded planes of the tail input
       }
     }
   }
@@ -755,8 +756,18 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
           } else {
             o.tl_act = nx.act;
           }
-          float* dst = next_buf();
-          o.f32 = dst; nxt.f32 = dst;
+          // the tail conv that follows runs on the tensor cores: hand it fp16 planes (channels padded to 16), no fp32 copy
+          const bool tail_tc = !is_hyper && i + 2 < t.ops.size() && t.ops[i + 2].type == OP_CONVT_RGB &&
+                               t.ops[i + 2].conv < (int)m->tc.syn_tail.size() && m->tc.syn_tail[t.ops[i + 2].conv].ok &&
+                               m->tc.syn_tail[t.ops[i + 2].conv].CP == (o.C1 + 15) / 16 * 16;
+          if (tail_tc) {
+            __half *hi, *lo;
+            next_planes(&hi, &lo);
+            o.hi = hi; o.lo = lo; nxt.hi = hi; nxt.lo = lo;
+          } else {
+            float* dst = next_buf();
+            o.f32 = dst; nxt.f32 = dst;
+          }
           skip_next = true;
         } else if (next_tc) {
           __half *hi, *lo;
@@ -773,6 +784,19 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         ch *= c.s; cw *= c.s; cc = c.cout;
         cur = nxt;
         if (skip_next) { cc = o.C1; ++i; }
+        continue;
+      }
+      if (op.type == OP_CONVT_RGB && cur.hi && !is_hyper && op.conv < (int)m->tc.syn_tail.size() && m->tc.syn_tail[op.conv].ok) {
+        // ---- tensor-core tail: stride-2 conv to <= 4 channels + crop + uint8 ----
+        TailTc& tt = m->tc.syn_tail[op.conv];
+        TailTcOut to;
+        if (fin) { to.f32 = fin->full; to.u8 = fin->u8; to.crop = fin->crop; to.H = fin->H; to.W = fin->W; }
+        std::string err;
+        ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
+        if (tail_tc_run(ctx->tc, c, tt, tt.bias, cur.hi, cur.lo, B, ch, cw, to, s, &ctx->launches, &err) != TC_OK)
+          return fail(SNTC_E_CUDA, "tensor-core tail: " + err);
+        ch *= c.s; cw *= c.s; cc = c.cout;
+        cur = Cur{};
         continue;
       }
       // ---- fp32 CUDA-core kernels ----

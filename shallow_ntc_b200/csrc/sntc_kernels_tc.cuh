@@ -440,7 +440,7 @@ __device__ __forceinline__ void tc_epi_scalar8(const TcParams& P, const TcBandRe
 // t = act(base + bias) (+ res + bias'), act = IGDN1 / GDN1 / relu / leaky / none   (common/transforms.py:331-360)
 template <int C1, bool RES>
 __device__ __forceinline__ void tc_epi_two_layer_pixel(const TcParams& P, const float* sgamma, const float* sbeta, const float* sbias,
-                                                        const uint32_t* raw, float* dst) {
+                                                        const uint32_t* raw, float* dst, __half* phi, __half* plo, size_t kq_stride) {
   constexpr int PW = RES ? 2 * C1 : C1;
   float x[C1];
 #pragma unroll
@@ -466,8 +466,28 @@ __device__ __forceinline__ void tc_epi_two_layer_pixel(const TcParams& P, const 
     for (int j = 0; j < C1; ++j) t[j] += fmaf(__uint_as_float(raw[C1 + j]), P.inv_scale, sbias[C1 + j]);
   }
   (void)PW;
+  if (dst) {
 #pragma unroll
-  for (int j = 0; j < C1; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
+    for (int j = 0; j < C1; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
+  }
+  if (phi) {   // fp16 hi/lo planes, channels padded to a multiple of 16, one 16-byte octet per store (octet stride kq_stride)
+    constexpr int CP = (C1 + 15) / 16 * 16;
+#pragma unroll
+    for (int g = 0; g < CP / 8; ++g) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c0 = 8 * g + 2 * i;
+        __half h0 = __float2half(0.f), l0 = h0, h1 = h0, l1 = h0;
+        if (c0 < C1) split_f16(t[c0 < C1 ? c0 : 0], h0, l0);
+        if (c0 + 1 < C1) split_f16(t[c0 + 1 < C1 ? c0 + 1 : 0], h1, l1);
+        h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint4*>(phi + (size_t)g * kq_stride) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(plo + (size_t)g * kq_stride) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
 }
 
 template <int C1, bool RES>
@@ -484,8 +504,12 @@ __device__ __forceinline__ void tc_epi_two_layer(const TcParams& P, const TcBand
     const int ph = (it.n0 + pp * PW) / PW;
     const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
     if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) continue;
-    float* dst = P.out_f32 + (((size_t)b * P.hout + oy) * P.wout + ox) * C1;
-    tc_epi_two_layer_pixel<C1, RES>(P, sgamma, sbeta, sbias, raw, dst);
+    const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
+    constexpr int CP = (C1 + 15) / 16 * 16;
+    // planes for the tensor-core tail are octet-planar: [B][hout][CP/8][wout][8]
+    const size_t poff = (((size_t)b * P.hout + oy) * (CP / 8) * P.wout + ox) * 8;
+    tc_epi_two_layer_pixel<C1, RES>(P, sgamma, sbeta, sbias, raw, P.out_f32 ? P.out_f32 + pix * C1 : nullptr,
+                                    P.out_hi ? P.out_hi + poff : nullptr, P.out_hi ? P.out_lo + poff : nullptr, (size_t)P.wout * 8);
   }
 }
 
@@ -810,8 +834,19 @@ struct TcDevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// tensor-core tail of a two-layer synthesis (kernel + packing in sntc_kernels_tail_tc.cuh)
+struct TailTc {
+  bool ok = false;
+  int CP = 0, KQ = 0, stages = 0;
+  float scale = 1.f;
+  __half* d_w = nullptr;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  bool attr_set = false;
+};
+
 struct TcModelState {
   std::vector<TcConv> hyper, syn;     // parallel to Transform::convs
+  std::vector<TailTc> syn_tail;       // parallel to syn: tensor-core tail of a two-layer synthesis (sntc_kernels_tail_tc.cuh)
   TcDevBuf plane[4];                  // hi/lo ping-pong activation planes
   TcDevBuf yh[2];                     // hi/lo planes of y_hat (output of the fused hyper-synthesis head)
   bool smem_attr_set = false;
@@ -956,6 +991,9 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
   return true;
 }
 
+inline bool tail_tc_supported(const ConvLayer& c);
+inline bool tail_tc_pack(const ConvLayer& c, const HostWeights& hw, TailTc& t, std::vector<void*>& owned, std::string* err);
+
 inline bool tc_finalize(TcDriver& drv, TcModelState& st, Transform* hyper, Transform* syn, const HostWeights& hw,
                         std::vector<void*>& owned, std::string* err) {
   if (!drv.encode) { *err = drv.err.empty() ? "cuTensorMapEncodeTiled unavailable" : drv.err; return false; }
@@ -979,6 +1017,21 @@ inline bool tc_finalize(TcDriver& drv, TcModelState& st, Transform* hyper, Trans
     return true;
   };
   if (!pack(hyper, st.hyper) || !pack(syn, st.syn)) return false;
+  if (syn && tc_env_int("SNTC_TC_TAIL", 0)) {
+    // Tail of a two-layer synthesis on the tensor cores (sntc_kernels_tail_tc.cuh).  OFF by default: measured on B200 it
+    // ties with the CUDA-core tail (0.17 vs 0.18 ms per 24-image step) because every M=128 x K=16 MMA costs ~95 clk of
+    // A-operand delivery however small N is, and it slows the layer-1 epilogue (octet-planar fp16 stores, +0.03 ms).
+    st.syn_tail.resize(syn->convs.size());
+    for (size_t oi = 2; oi < syn->ops.size(); ++oi) {
+      const Op& op = syn->ops[oi];
+      if (op.type != OP_CONVT_RGB || syn->ops[oi - 2].type != OP_CONVT) continue;
+      const int prev = syn->ops[oi - 2].conv;
+      if (prev >= (int)st.syn.size() || !st.syn[prev].ok || !st.syn[prev].fused_two_layer) continue;
+      const ConvLayer& c = syn->convs[op.conv];
+      if (!tail_tc_supported(c)) continue;
+      if (!tail_tc_pack(c, hw, st.syn_tail[op.conv], owned, err)) return false;
+    }
+  }
   if (!st.smem_attr_set) {
     cudaError_t e = cudaFuncSetAttribute(band_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(band_gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -176,3 +176,18 @@ def test_streaming_pipeline_matches_direct_decode(gpu_ctx, q_dtype):
   for i in range(5):
     ref = model.decompress(z[i * B:(i + 1) * B], q[i * B:(i + 1) * B], (H, W))
     assert np.array_equal(outs[i]["image"], ref["image"]) and np.array_equal(outs[i]["idx"], ref["idx"])
+
+
+@pytest.mark.parametrize("name,B,H,W", [("two_layer_syn", 2, 128, 192), ("two_layer_syn2", 1, 100, 150), ("two_layer_syn2:24", 1, 128, 128)])
+def test_tensor_core_tail_kernel_matches_oracle(gpu_ctx, monkeypatch, name, B, H, W):
+  """The experimental tcgen05 tail (SNTC_TC_TAIL=1: halo-reuse A patch, un-swizzled descriptors, [w_hi | w_lo] in N;
+  off by default) meets the same gates as the CUDA-core tail, and is really the kernel that ran."""
+  monkeypatch.setenv("SNTC_TC_TAIL", "1")
+  model, wts, z, q = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
+  ref = oracle_decode(model, wts, z, q, H, W)
+  got = model.decompress(z, q, (H, W), return_float=True, return_yhat=True)
+  print(name, check_against_oracle(got, ref, precision="tc"))
+  monkeypatch.setenv("SNTC_TC_TAIL", "0")
+  base, _, _, _ = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
+  ref2 = base.decompress(z, q, (H, W), return_float=True)
+  assert np.abs(ref2["float"] - got["float"]).max() < 1e-4
