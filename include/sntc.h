@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SNTC_VERSION 100
+#define SNTC_VERSION 101
 
 /* status codes */
 #define SNTC_OK 0
@@ -99,6 +99,12 @@ typedef struct sntc_transform_desc {
 #define SNTC_PRECISION_FP32 0      /* CUDA-core FFMA, fp32 throughout */
 #define SNTC_PRECISION_TC_F16X3 1  /* tcgen05 split-fp16 3-pass, fp32 accumulate in TMEM (fp32-class accuracy) */
 
+/* prior of the hyper-latent z (mshyper/models.py:135): tfc.NoisyDeepFactorized(batch_shape=(Cz,)), num_filters (3,3,3).
+ * With SNTC_PRIOR_DEEP_FACTORIZED the model expects the raw tfc variables prior.matrix_{0..3} [Cz,f_out,f_in],
+ * prior.bias_{0..3} [Cz,f_out,1], prior.factor_{0..2} [Cz,f_out,1] (softplus / tanh are applied when packing). */
+#define SNTC_PRIOR_NONE 0
+#define SNTC_PRIOR_DEEP_FACTORIZED 1
+
 /* index rounding rule of the scale table row */
 #define SNTC_INDEX_RINT 0
 #define SNTC_INDEX_TRUNC 1
@@ -112,7 +118,7 @@ typedef struct sntc_model_desc {
   int32_t num_scales;             /* NUM_SCALES, mshyper/models.py:28 (64) */
   int32_t index_rounding;         /* SNTC_INDEX_* */
   int32_t precision;              /* SNTC_PRECISION_* */
-  int32_t reserved;
+  int32_t prior;                  /* SNTC_PRIOR_*: the hyper-latent prior self._prior, mshyper/models.py:135 (only needed for bits_z) */
 } sntc_model_desc;
 
 /* per-image decode metrics: mse_psnr(), common/image_utils.py:26-38 */
@@ -121,6 +127,15 @@ typedef struct sntc_image_metrics {
   double psnr;
   uint64_t ssd; /* exact integer sum of squared uint8 differences */
 } sntc_image_metrics;
+
+/* per-image rate terms of frame_loss_given_latent_rvs(training=False), in bits (mshyper/models.py:246-259, 278-279):
+ *   bits_y = latent_bits       = -sum log2 NoisyNormal(0, SCALE_FN(clamp(exp(raw_sigma), 0, S-1))).prob(q_y)
+ *   bits_z = hyper_latent_bits = -sum log2 NoisyDeepFactorized.prob(z_hat)          (0 when the model has no prior)
+ * bpp of an image = (bits_y + bits_z) / (H * W)                                      (:300-310) */
+typedef struct sntc_image_rate {
+  double bits_y;
+  double bits_z;
+} sntc_image_rate;
 
 typedef struct sntc_ctx sntc_ctx;
 typedef struct sntc_model sntc_model;
@@ -171,6 +186,13 @@ int sntc_synthesis(sntc_model* m, const sntc_tensor* y_hat, sntc_tensor* out, vo
 int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q_y, int H, int W,
                 sntc_tensor* out_u8, sntc_tensor* out_idx, sntc_tensor* out_yhat, sntc_tensor* out_f32,
                 const sntc_tensor* original_u8, sntc_image_metrics* metrics, void* stream);
+
+/* sntc_decode plus the rate term: rate[B] receives bits_y / bits_z per image (nullable = sntc_decode).
+ * bits_y is accumulated in the epilogue of the last hyper-synthesis GEMM (tensor-core path) from the same
+ * raw sigma that produces idx; mu / sigma still never reach HBM.  Mean-scale hyperprior models only. */
+int sntc_decode_rd(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q_y, int H, int W,
+                   sntc_tensor* out_u8, sntc_tensor* out_idx, sntc_tensor* out_yhat, sntc_tensor* out_f32,
+                   const sntc_tensor* original_u8, sntc_image_metrics* metrics, sntc_image_rate* rate, void* stream);
 
 /* ---- profile hook: profile_utils.with_timing (common/profile_utils.py:62-76) ----
  * Device time in ms of the stages of the last sntc_decode on this model (CUDA events on the

@@ -336,15 +336,71 @@ def mse_psnr(a_u8, b_u8, max_val=255.0):
   return mses, psnrs
 
 
-def gaussian_bits(q, i_c):
-  """a7 (next row f2): bits under NoisyNormal(scale=SCALE_FN(i_c)) of integer symbol q (loc removed)."""
-  from scipy.special import ndtr
-  sig = scale_fn(i_c)
-  qq = np.abs(np.asarray(q, dtype=np.float64))
-  upper = ndtr((0.5 - qq) / sig)
-  lower = ndtr((-0.5 - qq) / sig)
-  like = np.maximum(upper - lower, 1e-300)
-  return -np.log2(like)
+def noisy_normal_bits(q, i_c):
+  """a7: bits of the integer symbol q = round(y - mu) under tfc.NoisyNormal(loc=0, scale=SCALE_FN(i_c)) -- what
+  LocationScaleIndexedEntropyModel.__call__(y, indexes, loc=mu, training=False) sums into latent_bits
+  (mshyper/models.py:246-248, 278-279).  i_c is the CONTINUOUS clamped index (compression=False never rounds it).
+  P = Phi((q+.5)/s) - Phi((q-.5)/s), evaluated in the log domain on the upper tail like tfc's UniformNoiseAdapter
+  (log survival functions of the two bin edges), so far tails stay finite."""
+  from scipy.special import log_ndtr
+  sig = scale_fn(np.asarray(i_c, dtype=np.float64))
+  aq = np.abs(np.asarray(q, dtype=np.float64))
+  la = log_ndtr(-(aq - 0.5) / sig)
+  lb = log_ndtr(-(aq + 0.5) / sig)
+  with np.errstate(divide="ignore"):
+    lp = la + np.log(-np.expm1(lb - la))
+  return -lp / math.log(2.0)
+
+
+gaussian_bits = noisy_normal_bits   # earlier name
+
+
+def _softplus(x):
+  return np.logaddexp(0.0, x)
+
+
+def _log_sigmoid(x):
+  return -np.logaddexp(0.0, -x)
+
+
+def deep_factorized_logits(x, wts, prefix="prior"):
+  """tfc.DeepFactorized._logits_cumulative with num_filters=(3,3,3) (the default the reference uses,
+  mshyper/models.py:135).  x [..., C]; variables are the RAW tfc variables: matrix_i [C,f_out,f_in] (softplus applied
+  here), bias_i [C,f_out,1], factor_i [C,f_out,1] (tanh applied here)."""
+  x = np.asarray(x, dtype=np.float64)
+  h = x[..., None]                                   # [..., C, f=1]
+  for i in range(4):
+    m = _softplus(np.asarray(wts[f"{prefix}.matrix_{i}"], dtype=np.float64))      # [C, fo, fi]
+    h = np.einsum("coi,...ci->...co", m, h) + np.asarray(wts[f"{prefix}.bias_{i}"], dtype=np.float64)[:, :, 0]
+    if i < 3:
+      h = h + np.tanh(np.asarray(wts[f"{prefix}.factor_{i}"], dtype=np.float64)[:, :, 0]) * np.tanh(h)
+  return h[..., 0]
+
+
+def deep_factorized_bits(z_hat, wts, prefix="prior"):
+  """hyper_latent_bits element-wise: -log2( c(z+.5) - c(z-.5) ), c = sigmoid(logits_cumulative), under
+  tfc.NoisyDeepFactorized (ContinuousBatchedEntropyModel.__call__(z, training=False), mshyper/models.py:249-252),
+  with the side of the median chosen so that no two numbers close to 1 are subtracted."""
+  z = np.asarray(z_hat, dtype=np.float64)
+  lower = deep_factorized_logits(z - 0.5, wts, prefix)
+  upper = deep_factorized_logits(z + 0.5, wts, prefix)
+  sgn = np.where(lower + upper > 0, -1.0, 1.0)
+  u, l = sgn * upper, sgn * lower
+  big, small = np.maximum(u, l), np.minimum(u, l)
+  lb, ls = _log_sigmoid(big), _log_sigmoid(small)
+  with np.errstate(divide="ignore"):
+    lp = lb + np.log(-np.expm1(ls - lb))
+  return -lp / math.log(2.0)
+
+
+def rate_bits(wts, raw_sigma, q_y, z_hat=None, prefix="prior"):
+  """(bits_y [B], bits_z [B] or None): the rate half of frame_loss_given_latent_rvs(training=False), :278-279, 300-310."""
+  i_c, _, _ = scale_indexes(raw_sigma)
+  by = noisy_normal_bits(q_y, i_c).reshape(q_y.shape[0], -1).sum(1)
+  bz = None
+  if z_hat is not None and f"{prefix}.matrix_0" in wts:
+    bz = deep_factorized_bits(z_hat, wts, prefix).reshape(z_hat.shape[0], -1).sum(1)
+  return by, bz
 
 
 def mshyper_decode(wts, synthesis_cls, z_hat, q_y, H, W, synthesis_kwargs=None,
@@ -364,6 +420,7 @@ def mshyper_decode(wts, synthesis_cls, z_hat, q_y, H, W, synthesis_kwargs=None,
              recon=recon, recon_u8=floats_to_pixels(recon))                                       # :314
   if original_u8 is not None:
     out["mse"], out["psnr"] = mse_psnr(original_u8, out["recon_u8"])                              # :315
+  out["bits_y"], out["bits_z"] = rate_bits(wts, raw_sigma, q_y, z_hat)                            # :278-279, 300-310
   return out
 
 

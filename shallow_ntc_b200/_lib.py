@@ -21,6 +21,7 @@ T_JPEG_LIKE_SYNTHESIS, T_TWO_LAYER, T_TWO_LAYER_RES, T_MBT2018, T_BLS2017, T_CNN
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_IGDN1, ACT_GDN1 = 0, 1, 2, 3, 4
 PRECISION_FP32, PRECISION_TC_F16X3 = 0, 1
 INDEX_RINT, INDEX_TRUNC = 0, 1
+PRIOR_NONE, PRIOR_DEEP_FACTORIZED = 0, 1
 
 
 class SntcError(RuntimeError):
@@ -43,11 +44,15 @@ class TransformDesc(C.Structure):
 
 class ModelDesc(C.Structure):
   _fields_ = [("struct_size", C.c_int32), ("hyper", TransformDesc), ("synthesis", TransformDesc),
-              ("num_scales", C.c_int32), ("index_rounding", C.c_int32), ("precision", C.c_int32), ("reserved", C.c_int32)]
+              ("num_scales", C.c_int32), ("index_rounding", C.c_int32), ("precision", C.c_int32), ("prior", C.c_int32)]
 
 
 class ImageMetrics(C.Structure):
   _fields_ = [("mse", C.c_double), ("psnr", C.c_double), ("ssd", C.c_uint64)]
+
+
+class ImageRate(C.Structure):
+  _fields_ = [("bits_y", C.c_double), ("bits_z", C.c_double)]
 
 
 # name -> (restype, argtypes); every symbol include/sntc.h declares
@@ -70,6 +75,8 @@ _PROTOS = {
   "sntc_synthesis": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), _P]),
   "sntc_decode": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor),
                             C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(ImageMetrics), _P]),
+  "sntc_decode_rd": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor),
+                               C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(ImageMetrics), C.POINTER(ImageRate), _P]),
   "sntc_last_stage_times_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
   "sntc_profile_enable": (C.c_int, [_P, C.c_int]),
   "sntc_profile_count": (C.c_int, [_P]),

@@ -11,6 +11,7 @@
 #include "../../include/sntc.h"
 #include "sntc_plan.hpp"
 #include "sntc_kernels_f32.cuh"
+#include "sntc_kernels_rate.cuh"
 #include "sntc_kernels_tc.cuh"
 #include "sntc_kernels_tail_tc.cuh"
 
@@ -75,6 +76,9 @@ struct sntc_model {
   DevBuf ws_a, ws_b, ws_c;             // ping-pong activations + misc
   DevBuf st_z, st_q, st_u8, st_idx, st_yhat, st_f32, st_orig;   // staging for host tensors
   DevBuf d_hs, d_yhat, d_ssd;
+  DevBuf d_rate_slots, d_rate_img, d_rate_zslots, d_rate;   // rate term: partial slots, slot->image map, per-image [bits_y, bits_z]
+  float* d_prior = nullptr;             // NoisyDeepFactorized parameters [Cz][DF_STRIDE] (softplus / tanh applied)
+  double* h_rate = nullptr; int h_rate_cap = 0;   // pinned
   TcModelState tc;                      // tensor-core plan state (tensor maps, fp16 planes)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
@@ -284,6 +288,18 @@ extern "C" int sntc_model_create(sntc_ctx* ctx, const sntc_model_desc* desc, snt
         return fail(SNTC_E_UNSUPPORTED, "sntc_model_create: layer input channels must be a multiple of 4");
   if (m->has_hyper) for (auto& v : transform_variables(m->hyper)) m->vars.push_back(v);
   if (m->has_syn) for (auto& v : transform_variables(m->syn)) m->vars.push_back(v);
+  if (desc->prior != SNTC_PRIOR_NONE) {
+    if (desc->prior != SNTC_PRIOR_DEEP_FACTORIZED) return fail(SNTC_E_INVALID, "sntc_model_create: unknown prior");
+    if (!m->has_hyper) return fail(SNTC_E_INVALID, "sntc_model_create: a hyper-latent prior needs a hyper-synthesis transform");
+    // tfc.NoisyDeepFactorized(batch_shape=(Cz,)) with the default num_filters=(3,3,3)   mshyper/models.py:135
+    const int f[5] = {1, 3, 3, 3, 1};
+    const int64_t Cz = m->hyper.in_channels;
+    for (int i = 0; i < 4; ++i) {
+      m->vars.push_back({"prior.matrix_" + std::to_string(i), {Cz, f[i + 1], f[i]}});
+      m->vars.push_back({"prior.bias_" + std::to_string(i), {Cz, f[i + 1], 1}});
+      if (i < 3) m->vars.push_back({"prior.factor_" + std::to_string(i), {Cz, f[i + 1], 1}});
+    }
+  }
   *out = m.release();
   return SNTC_OK;
 }
@@ -294,13 +310,14 @@ extern "C" int sntc_model_destroy(sntc_model* m) {
   cudaStreamSynchronize(m->ctx->stream);
   for (void* p : m->owned) cudaFree(p);
   for (DevBuf* b : {&m->ws_a, &m->ws_b, &m->ws_c, &m->st_z, &m->st_q, &m->st_u8, &m->st_idx, &m->st_yhat, &m->st_f32,
-                    &m->st_orig, &m->d_hs, &m->d_yhat, &m->d_ssd})
+                    &m->st_orig, &m->d_hs, &m->d_yhat, &m->d_ssd, &m->d_rate_slots, &m->d_rate_img, &m->d_rate_zslots, &m->d_rate})
     b->release();
   m->tc.release();
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
   for (auto& r : m->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto& e : m->prof_pool) cudaEventDestroy(e);
   if (m->h_ssd) cudaFreeHost(m->h_ssd);
+  if (m->h_rate) cudaFreeHost(m->h_rate);
   delete m;
   return SNTC_OK;
 }
@@ -385,6 +402,27 @@ extern "C" int sntc_model_finalize(sntc_model* m) {
     std::string err;
     if (!tc_finalize(m->ctx->tc, m->tc, m->has_hyper ? &m->hyper : nullptr, m->has_syn ? &m->syn : nullptr, m->hw, m->owned, &err))
       return fail(SNTC_E_CUDA, "sntc_model_finalize (tensor-core path): " + err);
+  }
+  if (m->desc.prior == SNTC_PRIOR_DEEP_FACTORIZED) {
+    const int Cz = m->hyper.in_channels;
+    std::vector<float> pk((size_t)Cz * DF_STRIDE, 0.f);
+    auto sp = [](float x) { return x > 20.f ? x : std::log1p(std::exp(x)); };
+    const int off_m[4] = {0, 9, 24, 39}, off_b[4] = {3, 18, 33, 42}, off_f[3] = {6, 21, 36};
+    const int f[5] = {1, 3, 3, 3, 1};
+    for (int i = 0; i < 4; ++i) {
+      const auto& M = m->hw.at("prior.matrix_" + std::to_string(i)).second;
+      const auto& Bv = m->hw.at("prior.bias_" + std::to_string(i)).second;
+      const int fo = f[i + 1], fi = f[i];
+      for (int c = 0; c < Cz; ++c) {
+        for (int a = 0; a < fo * fi; ++a) pk[(size_t)c * DF_STRIDE + off_m[i] + a] = sp(M[(size_t)c * fo * fi + a]);
+        for (int a = 0; a < fo; ++a) pk[(size_t)c * DF_STRIDE + off_b[i] + a] = Bv[(size_t)c * fo + a];
+        if (i < 3) {
+          const auto& F = m->hw.at("prior.factor_" + std::to_string(i)).second;
+          for (int a = 0; a < fo; ++a) pk[(size_t)c * DF_STRIDE + off_f[i] + a] = std::tanh(F[(size_t)c * fo + a]);
+        }
+      }
+    }
+    TRY(upload(m, pk.data(), pk.size() * 4, (void**)&m->d_prior));
   }
   for (auto& e : m->ev) CU_TRY(cudaEventCreate(&e));
   m->hw.clear();
@@ -666,6 +704,7 @@ struct Cur { const float* f32 = nullptr; const __half* hi = nullptr; const __hal
 struct HyperFuse {
   const void* q = nullptr; int q_kind = 0; int Cy = 0; float max_index = 63.f; bool trunc = false;
   float* y_hat = nullptr; uint8_t* idx = nullptr;
+  bool want_rate = false; RateConst rc{}; double* rate_slots = nullptr; int* rate_slot_img = nullptr; size_t rate_nslots = 0;
   bool done = false; const __half* yh_hi = nullptr; const __half* yh_lo = nullptr;   // out: planes of y_hat
 };
 
@@ -737,6 +776,14 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         if (last && hf) {
           o.hyper_final = true; o.q = hf->q; o.q_kind = hf->q_kind; o.Cy = hf->Cy; o.max_index = hf->max_index; o.trunc = hf->trunc;
           o.y_hat = hf->y_hat; o.idx = hf->idx;
+          if (hf->want_rate) {   // bits_y partials: one slot per (work item, CTA, epilogue warp)
+            const size_t ns = tc_rate_slots(tcv, B, ch, cw);
+            TRY(m->d_rate_slots.ensure(ns * 8));
+            TRY(m->d_rate_img.ensure(ns * 4));
+            CU_TRY(cudaMemsetAsync(m->d_rate_img.p, 0xFF, ns * 4, s));
+            o.rate_slots = (double*)m->d_rate_slots.p; o.rate_slot_img = (int*)m->d_rate_img.p; o.rate_slot_cap = ns; o.rc = hf->rc;
+            hf->rate_slots = o.rate_slots; hf->rate_slot_img = o.rate_slot_img; hf->rate_nslots = ns;
+          }
           size_t pl = (size_t)B * ch * c.s * cw * c.s * hf->Cy * 2;
           if (!m->tc.yh[0].ensure(pl) || !m->tc.yh[1].ensure(pl)) return fail(SNTC_E_CUDA, "cudaMalloc failed for the y_hat planes");
           o.hi = (__half*)m->tc.yh[0].p; o.lo = (__half*)m->tc.yh[1].p;
@@ -886,10 +933,11 @@ extern "C" int sntc_synthesis(sntc_model* m, const sntc_tensor* y_hat, sntc_tens
   return SNTC_OK;
 }
 
-extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q_y, int H, int W,
-                           sntc_tensor* out_u8, sntc_tensor* out_idx, sntc_tensor* out_yhat, sntc_tensor* out_f32,
-                           const sntc_tensor* original_u8, sntc_image_metrics* metrics, void* stream) {
+static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q_y, int H, int W,
+                       sntc_tensor* out_u8, sntc_tensor* out_idx, sntc_tensor* out_yhat, sntc_tensor* out_f32,
+                       const sntc_tensor* original_u8, sntc_image_metrics* metrics, sntc_image_rate* rate, void* stream) {
   if (!m) return fail(SNTC_E_INVALID, "sntc_decode: model is NULL");
+  if (rate && !m->has_hyper) return fail(SNTC_E_INVALID, "sntc_decode_rd: the rate term is implemented for the mean-scale hyperprior model only");
   if (!m->finalized) return fail(SNTC_E_STATE, "sntc_decode: model not finalized (weights missing?)");
   if (!m->has_syn) return fail(SNTC_E_STATE, "sntc_decode: model has no synthesis transform");
   if (!q_y) return fail(SNTC_E_INVALID, "sntc_decode: q_y is NULL");
@@ -946,6 +994,31 @@ extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_t
 
   CU_TRY(cudaEventRecord(m->ev[0], s));
   Cur ycur;
+  RateConst rc{};
+  if (rate) {
+    // Fixed configs for the ScaleIndexedEntropyModel, float32 like the reference computes them   mshyper/models.py:27-32
+    const float smin = 0.11f, smax = 256.f;
+    rc.max_index = (float)(m->desc.num_scales - 1);
+    rc.log_scale_min = std::log(smin);
+    rc.scale_factor = (std::log(smax) - std::log(smin)) / (float)(m->desc.num_scales - 1);
+    TRY(m->d_rate.ensure((size_t)B * 16));
+    CU_TRY(cudaMemsetAsync(m->d_rate.p, 0, (size_t)B * 16, s));
+    if (m->h_rate_cap < B) {
+      if (m->h_rate) cudaFreeHost(m->h_rate);
+      CU_TRY(cudaHostAlloc((void**)&m->h_rate, (size_t)B * 16, cudaHostAllocDefault));
+      m->h_rate_cap = B;
+    }
+    if (m->d_prior) {   // hyper_latent_bits under NoisyDeepFactorized   :249-252
+      const size_t per = (size_t)hz * wz * m->hyper.in_channels;
+      const int bpi = (int)std::min<size_t>((per + 256 * 4 - 1) / (256 * 4), 256);
+      TRY(m->d_rate_zslots.ensure((size_t)B * bpi * 8));
+      ProfScope ps(m, s, "rate.bits_z", 0);
+      rate_z_kernel<<<dim3(bpi, B), 256, 0, s>>>((const float*)d_z, per, m->hyper.in_channels, m->d_prior, (double*)m->d_rate_zslots.p);
+      rate_reduce_kernel<<<B, 256, 0, s>>>((const double*)m->d_rate_zslots.p, nullptr, 0, bpi, (double*)m->d_rate.p + 1, 2);
+      ctx->launches += 2;
+      CU_TRY(cudaGetLastError());
+    }
+  }
   if (m->has_hyper) {
     bool fused = false;
     const bool tc = m->desc.precision == SNTC_PRECISION_TC_F16X3;
@@ -957,10 +1030,16 @@ extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_t
       const bool syn_tc = op_on_tc(m, m->syn, false, 0);
       hf.y_hat = (out_yhat || !syn_tc) ? (float*)d_yhat : nullptr;   // fp32 y_hat only if someone reads it
       hf.idx = (uint8_t*)d_idx;
+      hf.want_rate = rate != nullptr; hf.rc = rc;
       Cur c0; c0.f32 = (const float*)d_z;
       TRY(run_transform(m, m->hyper, true, c0, B, hz, wz, nullptr, &hf, s));
       fused = hf.done;
       if (fused) { ycur.f32 = hf.y_hat; ycur.hi = hf.yh_hi; ycur.lo = hf.yh_lo; }
+      if (fused && rate) {
+        rate_reduce_kernel<<<B, 256, 0, s>>>(hf.rate_slots, hf.rate_slot_img, (int)hf.rate_nslots, 0, (double*)m->d_rate.p, 2);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+      }
     }
     if (!fused) {
       TRY(m->d_hs.ensure(n_lat * 2 * 4));
@@ -978,6 +1057,15 @@ extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_t
       ctx->launches++;
       CU_TRY(cudaGetLastError());
       ycur.f32 = (const float*)d_yhat;
+      if (rate) {   // rate term a7 from the materialised raw sigma
+        const size_t per = (size_t)hy * wy;
+        const int bpi = (int)std::min<size_t>((per * Cy + 256 * 8 - 1) / (256 * 8), 512);
+        TRY(m->d_rate_slots.ensure((size_t)B * bpi * 8));
+        rate_y_kernel<<<dim3(bpi, B), 256, 0, s>>>((const float*)m->d_hs.p, d_q, q_kind, per, Cy, rc, (double*)m->d_rate_slots.p);
+        rate_reduce_kernel<<<B, 256, 0, s>>>((const double*)m->d_rate_slots.p, nullptr, 0, bpi, (double*)m->d_rate.p, 2);
+        ctx->launches += 2;
+        CU_TRY(cudaGetLastError());
+      }
     } else {
       CU_TRY(cudaEventRecord(m->ev[1], s));
     }
@@ -1013,6 +1101,10 @@ extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_t
     CU_TRY(cudaMemcpyAsync(m->h_ssd, m->d_ssd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
     need_sync = true;
   }
+  if (rate) {
+    CU_TRY(cudaMemcpyAsync(m->h_rate, m->d_rate.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s));
+    need_sync = true;
+  }
   CU_TRY(cudaEventRecord(m->ev[3], s));
   m->ev_valid = true;
   TRY(unstage_out(out_u8, n_img, d_u8, s, &need_sync));
@@ -1020,6 +1112,8 @@ extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_t
   if (out_f32) TRY(unstage_out(out_f32, n_img * 4, d_f32, s, &need_sync));
   if (out_yhat && !on_device(out_yhat)) TRY(unstage_out(out_yhat, n_lat * 4, d_yhat, s, &need_sync));
   if (need_sync) CU_TRY(cudaStreamSynchronize(s));
+  if (rate)
+    for (int b = 0; b < B; ++b) { rate[b].bits_y = m->h_rate[2 * b]; rate[b].bits_z = m->h_rate[2 * b + 1]; }
   if (metrics) {
     double npx = (double)H * W * Co;
     for (int b = 0; b < B; ++b) {
@@ -1030,6 +1124,18 @@ extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_t
     }
   }
   return SNTC_OK;
+}
+
+extern "C" int sntc_decode(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q_y, int H, int W,
+                           sntc_tensor* out_u8, sntc_tensor* out_idx, sntc_tensor* out_yhat, sntc_tensor* out_f32,
+                           const sntc_tensor* original_u8, sntc_image_metrics* metrics, void* stream) {
+  return decode_impl(m, z_hat, q_y, H, W, out_u8, out_idx, out_yhat, out_f32, original_u8, metrics, nullptr, stream);
+}
+
+extern "C" int sntc_decode_rd(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q_y, int H, int W,
+                              sntc_tensor* out_u8, sntc_tensor* out_idx, sntc_tensor* out_yhat, sntc_tensor* out_f32,
+                              const sntc_tensor* original_u8, sntc_image_metrics* metrics, sntc_image_rate* rate, void* stream) {
+  return decode_impl(m, z_hat, q_y, H, W, out_u8, out_idx, out_yhat, out_f32, original_u8, metrics, rate, stream);
 }
 
 extern "C" int sntc_last_stage_times_ms(sntc_model* m, float out[4]) {

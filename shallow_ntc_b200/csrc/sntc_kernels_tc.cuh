@@ -24,6 +24,7 @@
 #include <string>
 #include <vector>
 #include "sntc_plan.hpp"
+#include "sntc_kernels_rate.cuh"
 
 namespace sntc {
 
@@ -69,6 +70,7 @@ struct TcParams {
   float* y_hat; uint8_t* idx;              // + out_hi/out_lo = planes of y_hat [B,hout,wout,Cy]
   // TC_EPI_TWO_LAYER: columns of one output pixel = base[0,C1) (|| res[C1,2C1)); out_f32 = t [B,hout,wout,C1]
   int C1, has_res, tl_act, tl_inverse; const float* gamma; int gamma_stride; const float* beta;
+  double* rate_slots; int* rate_slot_img; RateConst rc;   // TC_EPI_HYPER_FINAL: per-(item, CTA, epilogue warp) partial bits_y
   int vec16;          // fast epilogue: cout % 16 == 0, Cy % 16 == 0 and every epilogue tensor 32-byte aligned
   long long* trace;   // debug timeline (SNTC_TC_TRACE=1): [unit][TC_TRACE_ITEMS][8] clock64 stamps, leader CTA only
 };
@@ -376,8 +378,8 @@ __device__ __forceinline__ void load_q16(const void* q, int kind, size_t e, floa
     }
   }
 }
-__device__ __forceinline__ void tc_epi_vec16(const TcParams& P, const float* sbias, int b, int oy, int ox, int co, const uint32_t* raw) {
-  if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) return;
+__device__ __forceinline__ float tc_epi_vec16(const TcParams& P, const float* sbias, int b, int oy, int ox, int co, const uint32_t* raw) {
+  if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) return 0.f;
   const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
   float v[16];
 #pragma unroll
@@ -404,12 +406,20 @@ __device__ __forceinline__ void tc_epi_vec16(const TcParams& P, const float* sbi
                ((uint32_t)scale_index(v[4 * i + 2], P.max_index, P.trunc) << 16) | ((uint32_t)scale_index(v[4 * i + 3], P.max_index, P.trunc) << 24);
       *reinterpret_cast<uint4*>(P.idx + pix * P.Cy + (co - P.Cy)) = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    return;
+    float bits = 0.f;
+    if (co >= P.Cy && P.rate_slots) {   // rate term a7: bits of q under NoisyNormal(scale = SCALE_FN(i_c))   :278-279
+      float qv[16];
+      load_q16(P.q, P.q_kind, pix * P.Cy + (co - P.Cy), qv);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bits += noisy_normal_bits(qv[i], v[i], P.rc);
+    }
+    return bits;
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], P.act);
   if (P.out_hi) store16_planes(P.out_hi, P.out_lo, pix * P.cout + co, v);
   if (P.out_f32) store16_f32(P.out_f32 + pix * P.cout + co, v);
+  return 0.f;
 }
 
 // The band fields the epilogue needs, copied to registers once per work item: the band table lives in global
@@ -696,6 +706,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
           int co = it.n0 % P.cout, ph = it.n0 / P.cout, c_at = 0;
           int last_ph = -1, oy = 0, ox = 0;
           uint32_t raw[32], nxt[32];
+          float bits = 0.f;
           int c = 32 * eh;
           if (c < it.mma_n) tcx::tmem_ld32_nowait(trow + (uint32_t)c, nxt);
           for (; c < it.mma_n; c += 32 * EH) {
@@ -714,7 +725,17 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
                 last_ph = ph;
                 oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p; ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
               }
-              tc_epi_vec16(P, sbias, it.b, oy, ox, co, raw + 16 * h);
+              bits += tc_epi_vec16(P, sbias, it.b, oy, ox, co, raw + 16 * h);
+            }
+          }
+          if (P.rate_slots) {   // one deterministic partial per (item, CTA, epilogue warp)
+            double d = (double)bits;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) d += __shfl_down_sync(0xffffffffu, d, off);
+            if (lane == 0) {
+              const size_t slot = ((size_t)item * CG + rank) * TC_EPI_WARPS + (warp - 4);
+              P.rate_slots[slot] = d;
+              P.rate_slot_img[slot] = it.dup ? -1 : it.b;
             }
           }
         } else {
@@ -1047,6 +1068,7 @@ struct TcConvOut {
   // hyper-final fusion
   bool hyper_final = false; const void* q = nullptr; int q_kind = 0; int Cy = 0; float max_index = 63.f; bool trunc = false;
   float* y_hat = nullptr; uint8_t* idx = nullptr;
+  double* rate_slots = nullptr; int* rate_slot_img = nullptr; RateConst rc{}; size_t rate_slot_cap = 0;   // bits_y partials (nullable)
   // two-layer fusion: f32 receives t = act(base) (+ res), [B,hout,wout,C1]
   bool two_layer = false; int C1 = 0; bool has_res = false; int tl_act = SNTC_ACT_NONE; bool tl_inverse = true;
   const float* gamma = nullptr; int gamma_stride = 0; const float* beta = nullptr;
@@ -1059,6 +1081,17 @@ inline void tc_choose_patch(int h, int w, int* TH, int* TW) {
     long cost = (long)((h + c[0] - 1) / c[0]) * ((w + c[1] - 1) / c[1]);
     if (best < 0 || cost < best) { best = cost; *TH = c[0]; *TW = c[1]; }
   }
+}
+
+// Number of bits_y partial slots the hyper-final epilogue of this layer writes for a [B,h,w] input.
+inline size_t tc_rate_slots(const TcConv& t, int B, int h, int w) {
+  int TH, TW;
+  tc_choose_patch(h, w, &TH, &TW);
+  const int mtiles = ((h + TH - 1) / TH) * ((w + TW - 1) / TW) * B;
+  const int groups = (mtiles + t.cg - 1) / t.cg;
+  size_t items = 0;
+  for (auto& bd : t.bands) items += (size_t)groups * bd.ntiles;
+  return items * t.cg * TC_EPI_WARPS;
 }
 
 // One persistent launch for all bands of one conv layer.  Input: fp16 planes [B,h,w,cin].
@@ -1094,6 +1127,7 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   P.q = o.q; P.q_kind = o.q_kind; P.Cy = o.Cy; P.max_index = o.max_index; P.trunc = o.trunc ? 1 : 0; P.y_hat = o.y_hat; P.idx = o.idx;
   P.C1 = o.C1; P.has_res = o.has_res ? 1 : 0; P.tl_act = o.tl_act; P.tl_inverse = o.tl_inverse ? 1 : 0;
   P.gamma = o.gamma; P.gamma_stride = o.gamma_stride; P.beta = o.beta;
+  P.rate_slots = o.rate_slots; P.rate_slot_img = o.rate_slot_img; P.rc = o.rc;
   {
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
     bool ok = c.cout % 16 == 0 && (!o.hyper_final || o.Cy % 16 == 0) && !o.two_layer && !o.u8 && !o.crop;
@@ -1102,6 +1136,9 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
     // the last one may be half-used
     for (auto& bd : t.bands) ok = ok && bd.BN % 16 == 0;
     P.vec16 = ok ? 1 : 0;
+  }
+  if (o.rate_slots && (!P.vec16 || (size_t)P.total_items * t.cg * TC_EPI_WARPS > o.rate_slot_cap)) {
+    *err = "rate term: needs Cy % 16 == 0, 32-byte aligned tensors and a large enough slot buffer"; return TC_ERROR;
   }
   size_t smem = (size_t)t.stages * (2 * TC_BM * 128 + 2 * (t.bn_max / t.cg) * 128) + 1024 + 64 * 8 + (size_t)((o.two_layer ? o.C1 * o.C1 + o.C1 : 0) + c.cout + 8) * 4;
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns

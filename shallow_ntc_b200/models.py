@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import lib, check, ModelDesc, TransformDesc, ImageMetrics
+from ._lib import lib, check, ModelDesc, TransformDesc, ImageMetrics, ImageRate
 from .tensors import Context, as_tensor, empty_like_kind, DeviceArray
 from .transforms import class_builder as transform_builder
 
@@ -48,9 +48,10 @@ class _NativeModel:
 
 
 def _create_model(ctx: Context, hyper: TransformDesc, syn: TransformDesc, weights: dict, precision="fp32",
-                  index_rounding="rint", num_scales=NUM_SCALES) -> _NativeModel:
+                  index_rounding="rint", num_scales=NUM_SCALES, prior=False) -> _NativeModel:
   desc = ModelDesc(struct_size=C.sizeof(ModelDesc), hyper=hyper, synthesis=syn, num_scales=num_scales,
-                   index_rounding=_ROUNDING[index_rounding], precision=_PRECISION[precision])
+                   index_rounding=_ROUNDING[index_rounding], precision=_PRECISION[precision],
+                   prior=_lib.PRIOR_DEEP_FACTORIZED if prior else _lib.PRIOR_NONE)
   h = C.c_void_p()
   check(lib.sntc_model_create(ctx.handle, C.byref(desc), C.byref(h)))
   m = _NativeModel(ctx, h)
@@ -83,8 +84,9 @@ class Model:
   factorized-prior model (``factorized/models.py``: no z, no scale indexes, DOWNSAMPLE_FACTOR 16)."""
 
   def __init__(self, transform_config, bottleneck_size=None, hyperprior=True, profile=False, device=0,
-               precision="fp32", index_rounding="rint", ctx: Context | None = None, **_ignored_training_kwargs):
+               precision="fp32", index_rounding="rint", ctx: Context | None = None, prior=False, **_ignored_training_kwargs):
     self._transform_config = transform_config
+    self._with_prior = bool(prior) and hyperprior    # self._prior = tfc.NoisyDeepFactorized(...)   mshyper/models.py:135
     self._profile = profile
     self.precision = precision
     self.index_rounding = index_rounding
@@ -129,6 +131,13 @@ class Model:
     if self._hyper_synthesis is not None:
       v.update(self._hyper_synthesis.variable_shapes(self._hyper_synthesis.in_channels))
     v.update(self._synthesis.variable_shapes(self._bottleneck_size))
+    if self._with_prior:   # raw tfc.DeepFactorized variables, num_filters=(3,3,3)
+      f, Cz = (1, 3, 3, 3, 1), self.hyper_channels
+      for i in range(4):
+        v[f"prior.matrix_{i}"] = (Cz, f[i + 1], f[i])
+        v[f"prior.bias_{i}"] = (Cz, f[i + 1], 1)
+        if i < 3:
+          v[f"prior.factor_{i}"] = (Cz, f[i + 1], 1)
     return v
 
   def latent_shapes(self, batch, H, W):
@@ -155,7 +164,7 @@ class Model:
     hyper = (self._hyper_synthesis.desc(self._hyper_synthesis.in_channels) if self._hyper_synthesis is not None
              else TransformDesc(kind=_lib.T_NONE))
     syn = self._synthesis.desc(self._bottleneck_size)
-    self._native = _create_model(self._ctx, hyper, syn, self._weights, self.precision, self.index_rounding)
+    self._native = _create_model(self._ctx, hyper, syn, self._weights, self.precision, self.index_rounding, prior=self._with_prior)
 
   @property
   def ctx(self) -> Context:
@@ -165,7 +174,7 @@ class Model:
 
   # ---------------------------------------------------------------------------------------------
   def decompress(self, z_hat, q_y, image_hw, *, return_idx=True, return_yhat=False, return_float=False,
-                 original=None, out=None, stream=None, sync=True):
+                 original=None, return_bits=False, out=None, stream=None, sync=True):
     """Decode a batch from its integer symbols.
 
     z_hat [B, Hp/64, Wp/64, Cz] float32 (None for the factorized model); q_y [B, Hp/16, Wp/16, Cy]
@@ -175,6 +184,8 @@ class Model:
     [B,H,W,3] and, as requested, ``idx`` uint8 (scale-table rows), ``y_hat``, ``float`` (cropped float
     reconstruction in [-0.5, 0.5]), ``mse`` / ``psnr`` per image (when ``original`` uint8 is given), and
     ``hyper_synthesis_time`` / ``synthesis_time`` seconds when ``profile=True`` (profile_utils.with_timing).
+    ``return_bits=True`` adds the rate term (mshyper/models.py:278-279, 300-310): ``bits_y``, ``bits_z`` per image
+    (``bits_z`` = 0 unless the model was built with ``prior=True``) and ``bpp`` = (bits_y + bits_z) / (H * W).
     ``out`` may carry pre-allocated buffers under the same keys."""
     self._ensure_native()
     ctx = self._ctx
@@ -200,11 +211,16 @@ class Model:
     t_f = buf("float", (B, H, W, Co), np.float32, return_float)
     t_orig = as_tensor(original, ctx.device)
     metrics = (ImageMetrics * B)() if original is not None else None
-    check(lib.sntc_decode(self._native.handle, z.byref() if z else None, q.byref(), H, W, t_img.byref(),
-                          t_idx.byref() if t_idx else None, t_yh.byref() if t_yh else None, t_f.byref() if t_f else None,
-                          t_orig.byref() if t_orig else None, metrics, stream))
+    rate = (ImageRate * B)() if return_bits else None
+    check(lib.sntc_decode_rd(self._native.handle, z.byref() if z else None, q.byref(), H, W, t_img.byref(),
+                             t_idx.byref() if t_idx else None, t_yh.byref() if t_yh else None, t_f.byref() if t_f else None,
+                             t_orig.byref() if t_orig else None, metrics, rate, stream))
     if sync:
       ctx.sync()
+    if rate is not None:
+      out["bits_y"] = np.array([r.bits_y for r in rate])
+      out["bits_z"] = np.array([r.bits_z for r in rate])
+      out["bpp"] = (out["bits_y"] + out["bits_z"]) / float(H * W)
     if metrics is not None:
       out["mse"] = np.array([m.mse for m in metrics])
       out["psnr"] = np.array([m.psnr for m in metrics])

@@ -48,6 +48,7 @@ def make_weights(variable_shapes: dict, kind="init", seed=WEIGHT_SEED, synthesis
   the OUT_GAIN applied to the last synthesis layer."""
   assert kind in ("init", "stress")
   rng = np.random.default_rng(seed)
+  rng_prior = np.random.default_rng(seed + 1)   # own stream: the other weights do not depend on whether a prior is present
   w = {}
   for name in sorted(variable_shapes):
     shape = tuple(variable_shapes[name])
@@ -58,6 +59,8 @@ def make_weights(variable_shapes: dict, kind="init", seed=WEIGHT_SEED, synthesis
       w[name] = (rng.uniform(-0.05, 0.05, size=shape) if kind == "stress" else np.zeros(shape)).astype(np.float32)
     elif name.endswith(".beta"):
       w[name] = (1.0 + (rng.uniform(0, 0.5, size=shape) if kind == "stress" else 0.0) * np.ones(shape)).astype(np.float32)
+    elif name.startswith("prior."):
+      w[name] = _deep_factorized_init(name, shape, rng_prior, kind)
     elif name.endswith(".gamma"):
       g = 0.1 * np.eye(shape[0])
       if kind == "stress":
@@ -78,6 +81,22 @@ def make_weights(variable_shapes: dict, kind="init", seed=WEIGHT_SEED, synthesis
     w[f"synthesis.{last}.kernel"] *= np.float32(gain)
     w[f"synthesis.{last}.bias"] *= np.float32(gain)
   return w
+
+
+def _deep_factorized_init(name, shape, rng, kind, init_scale=10.0, num_filters=(3, 3, 3)):
+  """tfc.DeepFactorized variable initialisers: matrix_i = log(expm1(1 / scale / f_out)) with
+  scale = init_scale ** (1 / (len(num_filters) + 1)), bias_i ~ U(-.5, .5), factor_i = 0.  "stress" perturbs matrices
+  and gives non-zero factors so that the tanh gates matter."""
+  f_out = shape[1]
+  if ".matrix_" in name:
+    scale = init_scale ** (1.0 / (len(num_filters) + 1))
+    m = np.full(shape, np.log(np.expm1(1.0 / scale / f_out)))
+    if kind == "stress":
+      m = m + rng.uniform(-0.3, 0.3, size=shape)
+    return m.astype(np.float32)
+  if ".bias_" in name:
+    return rng.uniform(-0.5, 0.5, size=shape).astype(np.float32)
+  return (rng.uniform(-0.8, 0.8, size=shape) if kind == "stress" else np.zeros(shape)).astype(np.float32)
 
 
 def _scale_sigma_head(w, kname, rng):

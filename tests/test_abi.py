@@ -32,7 +32,9 @@ def test_struct_layouts_match_the_header():
   assert ctypes.sizeof(_lib.TransformDesc) == 48
   assert ctypes.sizeof(_lib.ModelDesc) == 4 + 2 * 48 + 16
   assert ctypes.sizeof(_lib.ImageMetrics) == 24
-  assert _lib.lib.sntc_version() == 100
+  assert ctypes.sizeof(_lib.ImageRate) == 16
+  assert _lib.ModelDesc.prior.offset == 4 + 2 * 48 + 12
+  assert _lib.lib.sntc_version() == 101
 
 
 def test_sass_contains_tcgen05_and_tma():

@@ -191,3 +191,52 @@ def test_tensor_core_tail_kernel_matches_oracle(gpu_ctx, monkeypatch, name, B, H
   base, _, _, _ = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
   ref2 = base.decompress(z, q, (H, W), return_float=True)
   assert np.abs(ref2["float"] - got["float"]).max() < 1e-4
+
+
+# --------------------------------------------------------------------------------------------------
+# rate term
+
+def _rate_case(name, B, H, W, precision, ctx):
+  from shallow_ntc_b200 import build_config
+  model = build_config(name, precision=precision, ctx=ctx, prior=True)
+  cls = model._transform_config["synthesis"]["cls"]
+  wts = synthetic.make_weights(model.variable_shapes(), "stress", synthesis_cls=cls)
+  model.load_weights(wts)
+  zs, ys = model.latent_shapes(B, H, W)
+  z, q = synthetic.make_latents(zs, ys)
+  return model, wts, z, q
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+@pytest.mark.parametrize("name,B,H,W", [("two_layer_syn", 3, 128, 192), ("jpegl", 2, 64, 128)])
+def test_rate_term_matches_oracle(gpu_ctx, name, B, H, W, precision):
+  """bits_y / bits_z of sntc_decode_rd against the float64 oracle.  bits_y inherits the accuracy of raw sigma through
+  sigma = SCALE_FN(clamp(exp(raw))): d(bits)/bits ~ 2 * 0.123 * i_c * d(raw) on tail symbols, hence the looser bound on
+  the split-fp16 path; the rate arithmetic itself is checked at 2e-5 against the GPU's own raw sigma."""
+  from oracle import ntc_oracle as O
+  model, wts, z, q = _rate_case(name, B, H, W, precision, gpu_ctx)
+  got = model.decompress(z, q, (H, W), return_bits=True)
+  ref = oracle_decode(model, wts, z, q, H, W)
+  tol_y = 3e-4 if precision == "fp32" else 3e-3
+  assert np.all(np.abs(got["bits_y"] / ref["bits_y"] - 1) < tol_y), (got["bits_y"], ref["bits_y"])
+  assert np.all(np.abs(got["bits_z"] / ref["bits_z"] - 1) < 2e-5), (got["bits_z"], ref["bits_z"])
+  assert np.allclose(got["bpp"], (got["bits_y"] + got["bits_z"]) / (H * W))
+  # the rate arithmetic in isolation: oracle bits from the GPU's own hyper-synthesis output
+  hs = model.hyper_synthesis(z)
+  by, _ = O.rate_bits(wts, hs[..., hs.shape[-1] // 2:].astype(np.float64), q)
+  assert np.all(np.abs(got["bits_y"] / by - 1) < 2e-5), (got["bits_y"], by)
+  # same image, same bits: deterministic partial sums, independent of the batch it is decoded in
+  again = model.decompress(z, q, (H, W), return_bits=True)
+  assert np.array_equal(again["bits_y"], got["bits_y"]) and np.array_equal(again["bits_z"], got["bits_z"])
+  one = model.decompress(z[1:2], q[1:2], (H, W), return_bits=True)
+  assert np.allclose(one["bits_y"], got["bits_y"][1:2], rtol=1e-12) and np.array_equal(one["bits_z"], got["bits_z"][1:2])
+  # decode outputs are unchanged by asking for the rate
+  plain = model.decompress(z, q, (H, W))
+  assert np.array_equal(plain["image"], got["image"]) and np.array_equal(plain["idx"], got["idx"])
+
+
+def test_rate_without_prior_reports_zero_bits_z_and_int8_symbols_agree(gpu_ctx):
+  model, wts, z, q = make_case("two_layer_syn", 2, 64, 128, "stress", "tc", gpu_ctx)
+  a = model.decompress(z, q, (64, 128), return_bits=True)
+  b = model.decompress(z, q.astype(np.int8), (64, 128), return_bits=True)
+  assert np.all(a["bits_z"] == 0) and np.array_equal(a["bits_y"], b["bits_y"]) and np.all(a["bits_y"] > 0)

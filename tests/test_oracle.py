@@ -155,3 +155,58 @@ def test_synthetic_inputs_are_shard_invariant():
   assert np.array_equal(q, np.rint(q)) and np.abs(q).max() <= 127
   assert [synthetic.shard_range(24, r, 8) for r in range(8)] == [(3 * r, 3 * r + 3) for r in range(8)]
   assert [synthetic.shard_range(5, r, 2) for r in range(2)] == [(0, 3), (3, 5)]
+
+
+# --------------------------------------------------------------------------------------------------
+# rate term: known answers of the two entropy models
+
+@pytest.mark.parametrize("i_c", [0.0, 3.7, 20.0, 41.5, 63.0])
+def test_noisy_normal_is_a_probability_mass_function(i_c):
+  """sum over all integers q of P(q | sigma) = 1 (the bins tile the real line), to float64 accuracy."""
+  sig = float(O.scale_fn(i_c))
+  K = int(12 * sig) + 40
+  q = np.arange(-K, K + 1, dtype=np.float64)
+  p = 2.0 ** (-O.noisy_normal_bits(q, np.full_like(q, i_c)))
+  assert abs(p.sum() - 1.0) < 1e-12
+  assert np.allclose(p, p[::-1], rtol=1e-12)          # symmetric in q
+
+
+def test_noisy_normal_bits_matches_direct_difference_and_stays_finite_in_the_tails():
+  from scipy.special import ndtr
+  rng = np.random.default_rng(0)
+  i_c = rng.uniform(0, 63, size=2000)
+  sig = O.scale_fn(i_c)
+  q = np.rint(rng.normal(0, 1, size=2000) * sig)
+  direct = -np.log2(ndtr((q + .5) / sig) - ndtr((q - .5) / sig))
+  ok = np.isfinite(direct) & (direct < 40)
+  assert np.allclose(O.noisy_normal_bits(q, i_c)[ok], direct[ok], rtol=1e-9)
+  far = O.noisy_normal_bits(np.array([127.0, -127.0, 50.0]), np.array([0.0, 0.0, 1.0]))   # sigma ~ 0.11: z ~ 1150
+  assert np.all(np.isfinite(far)) and far[0] == far[1] and far[0] > 9e5
+  # leading term of the tail: -log2 Phi(-a) ~ a^2 / (2 ln 2)
+  a = (127 - .5) / 0.11
+  assert abs(far[0] / (a * a / (2 * np.log(2))) - 1) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["init", "stress"])
+def test_deep_factorized_prior_is_a_monotone_cdf_and_a_pmf(kind):
+  m = build_config("two_layer_syn", prior=True)
+  wts = synthetic.make_weights(m.variable_shapes(), kind, synthesis_cls="TwoLayerResSynthesis")
+  C = 320
+  z = np.arange(-400, 401, dtype=np.float64)[:, None] * np.ones((1, C))
+  lg = O.deep_factorized_logits(z, wts)
+  assert lg.shape == z.shape and np.all(np.diff(lg, axis=0) > 0)      # softplus matrices + |tanh factor| < 1 -> increasing
+  p = 2.0 ** (-O.deep_factorized_bits(z, wts))
+  assert np.all(np.abs(p.sum(0) - 1.0) < 1e-6)                        # mass outside +-400 is negligible (init_scale 10)
+  # parameter count of tfc.NoisyDeepFactorized(batch_shape=(320,)), num_filters (3,3,3): 3+3+3 + 9+3+3 + 9+3+3 + 3+1 = 43 per channel
+  assert O.count_params(wts, "prior") == 43 * C
+
+
+def test_rate_bits_shapes_and_additivity():
+  m = build_config("two_layer_syn", prior=True)
+  wts = synthetic.make_weights(m.variable_shapes(), "stress", synthesis_cls="TwoLayerResSynthesis")
+  zs, ys = m.latent_shapes(3, 64, 64)
+  z, q = synthetic.make_latents(zs, ys)
+  out = O.mshyper_decode(wts, "TwoLayerResSynthesis", z, q, 64, 64, dict(channels=(12, 3), strides=(8, 2), kernel_sizes=(13, 5)))
+  assert out["bits_y"].shape == (3,) and out["bits_z"].shape == (3,)
+  one = O.mshyper_decode(wts, "TwoLayerResSynthesis", z[1:2], q[1:2], 64, 64, dict(channels=(12, 3), strides=(8, 2), kernel_sizes=(13, 5)))
+  assert np.allclose(one["bits_y"], out["bits_y"][1:2], rtol=1e-12) and np.allclose(one["bits_z"], out["bits_z"][1:2], rtol=1e-12)
