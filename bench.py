@@ -38,6 +38,18 @@ def load_peaks():
   return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source="fallback")
 
 
+def ncu_traffic(label, batch):
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `label`, from the committed
+  `ncu --set full` capture (profiles/r01_ncu_traffic.json, taken at batch 24); None when no capture matches."""
+  p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+  try:
+    d = json.load(open(p))
+    e = d["kernels"].get(label)
+    return float(e["dram_bytes_per_launch"]) if e and d.get("batch") == batch else None
+  except Exception:
+    return None
+
+
 class ClockSampler:
   """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
   Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -163,7 +175,7 @@ def main():
   peaks = load_peaks()
 
   def make_model(precision):
-    m = build_config(args.config, precision=precision, ctx=ctx)
+    m = build_config(args.config, precision=precision, ctx=ctx, prior=True)
     cfg = m._transform_config["synthesis"]
     m.load_weights(synthetic.make_weights(m.variable_shapes(), "stress", synthesis_cls=cfg["cls"]))
     m._ensure_native()
@@ -205,7 +217,6 @@ def main():
   barrier()
   sampler = ClockSampler(local)
   sampler.start()
-  model.profile_layers(True)
   l0 = ctx.launch_count
   e0, e1 = ctx.event(), ctx.event()
   barrier()
@@ -217,9 +228,15 @@ def main():
   ms = e0.elapsed_ms(e1)
   barrier()
   launches = ctx.launch_count - l0
+  clocks = sampler.stop()
+  # per-layer breakdown (CUDA events around every layer) in a separate, untimed pass: the extra event records
+  # would otherwise sit between the kernels of the timed region
+  model.profile_layers(True)
+  for i in range(min(args.steps, 50)):
+    step_dev(i)
+  ctx.sync()
   model.profile_layers(False)
   prof = model.layer_profile()
-  clocks = sampler.stop()
 
   # ---- e2e: pinned HOST buffers through the public streaming API (DecodePipeline): every step uploads its
   # symbols (H2D) and downloads image + index map (D2H) inside the timed region; copies overlap the decode of
@@ -248,8 +265,19 @@ def main():
 
   # final quality sum over ranks (the only collective; NCCL all-reduce of 3 doubles)
   orig = synthetic.make_original(out_host["image"][:2], first_index=rank * B)
-  met = model.decompress(sets[(args.steps - 1) % 2][0][:2], sets[(args.steps - 1) % 2][1][:2], (H, W), original=orig)
-  qsum = np.array([met["psnr"].sum(), met["mse"].sum(), float(len(met["psnr"]))])
+  met = model.decompress(sets[(args.steps - 1) % 2][0][:2], sets[(args.steps - 1) % 2][1][:2], (H, W), original=orig, return_bits=True)
+  # [sum psnr, sum mse, sum bits_y, sum bits_z, n_images]: the reference averages per-image metrics (mshyper/models.py:300-317)
+  qsum = np.array([met["psnr"].sum(), met["mse"].sum(), met["bits_y"].sum(), met["bits_z"].sum(), float(len(met["psnr"]))])
+  # cost of asking for the rate term as well (bits_y in the hyper-head epilogue + bits_z kernel), device-resident
+  n_rd = max(3, args.steps // 8)
+  g0, g1 = ctx.event(), ctx.event()
+  g0.record()
+  for i in range(n_rd):
+    dz, dq = dev[i % args.rotate]
+    model.decompress(dz, dq, (H, W), out=out_dev, return_bits=True, sync=False)
+  g1.record()
+  ctx.sync()
+  ms_rd = g0.elapsed_ms(g1) / n_rd
   if dist is not None:
     from shallow_ntc_b200 import parallel
     ms, ms_e2e, ms_e2e_i8 = (float(v) for v in parallel.max_over_ranks(dist, [ms, ms_e2e, ms_e2e_i8], device=f"cuda:{local}"))
@@ -266,7 +294,7 @@ def main():
       per_launch_ms = dom[1]["ms"] / dom[1]["n"]
       ach = 2.0 * dom[1]["macs"] / (per_launch_ms * 1e-3) / 1e12
       roof = dict(bound="tensor", kernel=dom[0], achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"],
-                  traffic=None, peak_source=peaks["source"] + " bf16 dense sustained", share_of_step=dom[1]["ms"] / ms,
+                  traffic=ncu_traffic(dom[0], B), peak_source=peaks["source"] + " bf16 dense sustained", share_of_step=dom[1]["ms"] / ms,
                   ms_per_launch=per_launch_ms, algorithmic_flops_per_launch=2.0 * dom[1]["macs"],
                   hbm_view=dict(algorithmic_gbs=world * B * 3760128 * args.steps / (ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"]))
     line = dict(metric="decoded Mpx/s", value=value, unit="Mpx/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -275,7 +303,8 @@ def main():
                 config=dict(workload=f"mshyper {args.config} decode (BASELINE configs[1]): {B} x 768x512 per GPU, random-init 'stress' weights",
                             images_per_gpu=B, precision=precision, l2="inputs rotate over %d distinct batches; per-step working set > 126 MB L2" % args.rotate,
                             layers_ms={k: round(v["ms"] / max(v["n"], 1), 4) for k, v in prof.items()},
-                            mean_psnr_db=float(qsum[0] / qsum[2])),
+                            mean_psnr_db=float(qsum[0] / qsum[4]), mean_bpp_synthetic=float((qsum[2] + qsum[3]) / qsum[4] / (H * W)),
+                            ms_per_step_with_rate_term=ms_rd),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=e2e, unit="Mpx/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
                          api="DecodePipeline.submit (float32 symbols, pinned host buffers, depth 2)",

@@ -1,0 +1,40 @@
+"""Decode-side mirror of the evaluate loop: ``Model.evaluate`` (mshyper/models.py:415-433) yields one
+metrics record per image and ``eval_lib.eval_workdir`` (common/eval_lib.py:91-105) dumps them as a flat JSON list.
+
+Here the loop starts from decoded symbols instead of images (the encoder is out of scope): every image is decoded by
+libsntc -- batched, which the reference does not do (it evaluates image by image) -- and the per-image record carries
+the scalars the reference's results files hold and this path can produce on the device: ``bpp``, ``psnr``, ``mse``,
+``rd_loss`` (= bpp + rd_lambda * mse, :343), ``instance_id``.  ``msssim`` / ``lpips`` are not computed (out of scope)."""
+from __future__ import annotations
+
+import json
+import numpy as np
+
+
+def evaluate_symbols(model, z_hat, q_y, originals, image_hw=None, batch_size=24, rd_lambda=None, extra=None):
+  """Yields one dict per image, in order.  z_hat / q_y: arrays (or lists of per-image arrays of one shape) of decoded
+  symbols; originals: uint8 [N,H,W,3].  ``extra``: hyper-parameters added to every record (parse_runname's role)."""
+  originals = np.asarray(originals)
+  N = originals.shape[0]
+  H, W = image_hw if image_hw is not None else originals.shape[1:3]
+  for lo in range(0, N, batch_size):
+    hi = min(N, lo + batch_size)
+    z = None if z_hat is None else np.ascontiguousarray(z_hat[lo:hi])
+    out = model.decompress(z, np.ascontiguousarray(q_y[lo:hi]), (H, W), original=np.ascontiguousarray(originals[lo:hi]),
+                           return_bits=model.hyperprior)
+    for i in range(hi - lo):
+      rec = dict(instance_id=lo + i, psnr=float(out["psnr"][i]), mse=float(out["mse"][i]))
+      if "bpp" in out:
+        rec.update(bpp=float(out["bpp"][i]), latent_bpp=float(out["bits_y"][i] / (H * W)), hyper_latent_bpp=float(out["bits_z"][i] / (H * W)))
+        if rd_lambda is not None:
+          rec["rd_loss"] = rec["bpp"] + float(rd_lambda) * rec["mse"]        # mshyper/models.py:343
+      if extra:
+        rec.update(extra)
+      yield rec
+
+
+def dump_json(records, path):
+  """common/eval_lib.py:103 (utils.dump_json): a flat list of per-image dicts."""
+  with open(path, "w") as f:
+    json.dump(list(records), f, indent=2)
+  return path

@@ -232,6 +232,12 @@ class Model:
       out["synthesis_time"] = t[2] * 1e-3
     return out
 
+  def evaluate(self, z_hat, q_y, originals, image_hw=None, **kw):
+    """Model.evaluate (mshyper/models.py:415-433) from decoded symbols: yields one metrics dict per image
+    (see eval_lib.evaluate_symbols)."""
+    from .eval_lib import evaluate_symbols
+    return evaluate_symbols(self, z_hat, q_y, originals, image_hw, **kw)
+
   def profile_layers(self, on: bool):
     """Per-layer CUDA-event timing inside libsntc (sntc_profile_enable)."""
     self._ensure_native()

@@ -240,3 +240,25 @@ def test_rate_without_prior_reports_zero_bits_z_and_int8_symbols_agree(gpu_ctx):
   a = model.decompress(z, q, (64, 128), return_bits=True)
   b = model.decompress(z, q.astype(np.int8), (64, 128), return_bits=True)
   assert np.all(a["bits_z"] == 0) and np.array_equal(a["bits_y"], b["bits_y"]) and np.all(a["bits_y"] > 0)
+
+
+def test_evaluate_loop_records_match_oracle(gpu_ctx, tmp_path):
+  """Row f4: the per-image records of the evaluate loop (bpp, psnr, mse, rd_loss, instance_id) against the oracle,
+  batched decode (batch 2 over 5 images, ragged last batch) == image-by-image."""
+  import json
+  from shallow_ntc_b200 import eval_lib
+  H, W = 64, 128
+  model, wts, z, q = _rate_case("two_layer_syn", 5, H, W, "tc", gpu_ctx)
+  ref = oracle_decode(model, wts, z, q, H, W)
+  orig = synthetic.make_original(ref["recon_u8"])
+  recs = list(model.evaluate(z, q, orig, batch_size=2, rd_lambda=0.08, extra=dict(rd_lambda=0.08)))
+  assert [r["instance_id"] for r in recs] == [0, 1, 2, 3, 4]
+  ref_mse, ref_psnr = __import__("oracle.ntc_oracle", fromlist=["x"]).mse_psnr(orig, ref["recon_u8"])
+  for i, r in enumerate(recs):
+    assert abs(r["psnr"] - ref_psnr[i]) < PSNR_TOL
+    assert abs(r["bpp"] / ((ref["bits_y"][i] + ref["bits_z"][i]) / (H * W)) - 1) < 3e-3
+    assert abs(r["rd_loss"] - (r["bpp"] + 0.08 * r["mse"])) < 1e-12
+  single = list(model.evaluate(z, q, orig, batch_size=1))
+  assert all(abs(a["bpp"] - b["bpp"]) < 1e-12 * max(1.0, a["bpp"]) and a["mse"] == b["mse"] for a, b in zip(recs, single))
+  path = eval_lib.dump_json(recs, tmp_path / "results.json")
+  assert len(json.load(open(path))) == 5
