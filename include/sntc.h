@@ -194,6 +194,32 @@ int sntc_decode_rd(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q
                    sntc_tensor* out_u8, sntc_tensor* out_idx, sntc_tensor* out_yhat, sntc_tensor* out_f32,
                    const sntc_tensor* original_u8, sntc_image_metrics* metrics, sntc_image_rate* rate, void* stream);
 
+/* ---- two-phase decode ----
+ * A real decoder cannot have q_y before it knows the scale-table rows: the range decoder needs idx to pick the CDF
+ * of every symbol (tfc LocationScaleIndexedEntropyModel.decompress(strings, indexes, loc)).  Phase 1 runs
+ * hyper-synthesis and returns idx (mu stays on the device, owned by the model); phase 2 takes the decoded symbols,
+ * forms y_hat = q_y + mu and runs synthesis + pixel epilogue.  Results are identical to sntc_decode. */
+int sntc_decode_hyper(sntc_model* m, const sntc_tensor* z_hat, sntc_tensor* out_idx, void* stream);
+int sntc_decode_latents(sntc_model* m, const sntc_tensor* q_y, int H, int W, sntc_tensor* out_u8, sntc_tensor* out_yhat,
+                        sntc_tensor* out_f32, const sntc_tensor* original_u8, sntc_image_metrics* metrics, void* stream);
+
+/* ---- host entropy coder (CPU; the I/O stage either side of the GPU path) ----
+ * The reference builds its entropy models with compression=False and never produces a bitstream
+ * (mshyper/models.py:246-251), so this defines the missing half: quantised CDF tables in the manner of
+ * tensorflow-compression 2.10 (tail_mass, range_coder_precision, overflow symbol + Elias-gamma escape) and a
+ * byte-oriented range coder.  kind 0 = scale-table rows of NoisyNormal(0, SCALE_FN(i)), one row index (idx) per
+ * symbol; kind 1 = per-channel tables of the hyper-latent prior (row = symbol position % Cz), after
+ * sntc_coder_set_prior with the raw DeepFactorized variables packed [Cz][43] in the order matrix_0[3] bias_0[3]
+ * factor_0[3] matrix_1[9] bias_1[3] factor_1[3] matrix_2[9] bias_2[3] factor_2[3] matrix_3[3] bias_3[1]. */
+typedef struct sntc_coder sntc_coder;
+int sntc_coder_create(int num_scales, double scale_min, double scale_max, double tail_mass, int precision, sntc_coder** out);
+int sntc_coder_destroy(sntc_coder* k);
+int sntc_coder_set_prior(sntc_coder* k, int Cz, const float* raw43);
+int sntc_coder_table(sntc_coder* k, int kind, int row, int32_t* offset, int32_t* nsym, const uint32_t** cdf);
+int sntc_coder_encode(sntc_coder* k, int kind, const int32_t* symbols, const uint8_t* rows, size_t n, uint8_t** bytes, size_t* nbytes);
+int sntc_coder_decode(sntc_coder* k, int kind, const uint8_t* bytes, size_t nbytes, const uint8_t* rows, size_t n, int32_t* symbols);
+void sntc_coder_free(void* p); /* releases *bytes of sntc_coder_encode */
+
 /* ---- profile hook: profile_utils.with_timing (common/profile_utils.py:62-76) ----
  * Device time in ms of the stages of the last sntc_decode on this model (CUDA events on the
  * launching stream): [0] hyper_synthesis_time, [1] dequant/index, [2] synthesis_time, [3] total. */

@@ -77,6 +77,16 @@ _PROTOS = {
                             C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(ImageMetrics), _P]),
   "sntc_decode_rd": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor),
                                C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(ImageMetrics), C.POINTER(ImageRate), _P]),
+  "sntc_decode_hyper": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), _P]),
+  "sntc_decode_latents": (C.c_int, [_P, C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor),
+                                    C.POINTER(Tensor), C.POINTER(ImageMetrics), _P]),
+  "sntc_coder_create": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(_P)]),
+  "sntc_coder_destroy": (C.c_int, [_P]),
+  "sntc_coder_set_prior": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
+  "sntc_coder_table": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_uint32))]),
+  "sntc_coder_encode": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]),
+  "sntc_coder_decode": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_int32)]),
+  "sntc_coder_free": (None, [_P]),
   "sntc_last_stage_times_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
   "sntc_profile_enable": (C.c_int, [_P, C.c_int]),
   "sntc_profile_count": (C.c_int, [_P]),

@@ -1,0 +1,144 @@
+"""Bitstream either side of the GPU path: host range coder (libsntc, CPU) + wire format.
+
+The reference never produces a bitstream (``compression=False`` on every entropy-model call); this module
+defines the ``compress`` / ``decompress`` pair its models lack, in the manner of the tensorflow-compression example
+models: per image one string for the hyper-latent z (per-channel tables of the NoisyDeepFactorized prior) and one for
+the latent symbols q = round(y - mu) (NoisyNormal scale-table rows picked by idx).  Decoding is two-phase because the
+rows are only known after hyper-synthesis (``Model.decode_hyper`` -> idx -> range-decode q -> ``Model.decode_latents``).
+
+Container (little endian): magic ``SNTC`` u8 version=1 | u32 B H W hz wz Cz hy wy Cy | B x (u32 len_z, u32 len_y) | payloads.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+import time
+import numpy as np
+
+from ._lib import lib, check
+
+MAGIC = b"SNTC\x01"
+_PRIOR_ORDER = [("matrix", 0), ("bias", 0), ("factor", 0), ("matrix", 1), ("bias", 1), ("factor", 1),
+                ("matrix", 2), ("bias", 2), ("factor", 2), ("matrix", 3), ("bias", 3)]
+
+
+class EntropyCoder:
+  """CDF tables (tfc-style: tail_mass, range_coder_precision, overflow symbol) + range coder, on the host."""
+
+  def __init__(self, num_scales=64, scale_min=0.11, scale_max=256.0, tail_mass=2.0 ** -8, precision=12, prior_weights=None,
+               prefix="prior"):
+    self.handle = C.c_void_p()
+    check(lib.sntc_coder_create(num_scales, scale_min, scale_max, tail_mass, precision, C.byref(self.handle)))
+    self.precision = precision
+    self.num_channels = 0
+    if prior_weights is not None:
+      self.set_prior(prior_weights, prefix)
+
+  def set_prior(self, weights, prefix="prior"):
+    """Raw tfc.DeepFactorized variables (matrix_i [Cz,fo,fi], bias_i [Cz,fo,1], factor_i [Cz,fo,1])."""
+    Cz = np.asarray(weights[f"{prefix}.matrix_0"]).shape[0]
+    packed = np.concatenate([np.asarray(weights[f"{prefix}.{kind}_{i}"], dtype=np.float32).reshape(Cz, -1) for kind, i in _PRIOR_ORDER], axis=1)
+    assert packed.shape == (Cz, 43)
+    packed = np.ascontiguousarray(packed)
+    check(lib.sntc_coder_set_prior(self.handle, Cz, packed.ctypes.data_as(C.POINTER(C.c_float))))
+    self.num_channels = Cz
+
+  def table(self, kind, row):
+    """(offset, cdf uint32[nsym + 2]) of one table; the last symbol is the overflow (escape) symbol."""
+    off, n, p = C.c_int32(), C.c_int32(), C.POINTER(C.c_uint32)()
+    check(lib.sntc_coder_table(self.handle, kind, row, C.byref(off), C.byref(n), C.byref(p)))
+    return off.value, np.ctypeslib.as_array(p, shape=(n.value + 2,)).copy()
+
+  def _encode(self, kind, symbols, rows):
+    sym = np.ascontiguousarray(np.rint(symbols).astype(np.int32).ravel())
+    r = None if rows is None else np.ascontiguousarray(rows, dtype=np.uint8).ravel()
+    assert r is None or r.size == sym.size
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    check(lib.sntc_coder_encode(self.handle, kind, sym.ctypes.data_as(C.POINTER(C.c_int32)),
+                                r.ctypes.data_as(C.POINTER(C.c_uint8)) if r is not None else None, sym.size, C.byref(out), C.byref(n)))
+    try:
+      return C.string_at(out, n.value)
+    finally:
+      lib.sntc_coder_free(out)
+
+  def _decode(self, kind, data, rows, n):
+    r = None if rows is None else np.ascontiguousarray(rows, dtype=np.uint8).ravel()
+    sym = np.empty(n, dtype=np.int32)
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data) if len(data) else None
+    check(lib.sntc_coder_decode(self.handle, kind, buf, len(data), r.ctypes.data_as(C.POINTER(C.c_uint8)) if r is not None else None,
+                                n, sym.ctypes.data_as(C.POINTER(C.c_int32))))
+    return sym
+
+  def encode_y(self, q, idx):
+    return self._encode(0, q, idx)
+
+  def decode_y(self, data, idx):
+    idx = np.asarray(idx)
+    return self._decode(0, data, idx, idx.size).reshape(idx.shape)
+
+  def encode_z(self, z):
+    assert self.num_channels and np.asarray(z).shape[-1] == self.num_channels
+    return self._encode(1, z, None)
+
+  def decode_z(self, data, shape):
+    assert self.num_channels and shape[-1] == self.num_channels
+    return self._decode(1, data, None, int(np.prod(shape))).reshape(shape)
+
+  def __del__(self):
+    try:
+      if self.handle:
+        lib.sntc_coder_destroy(self.handle)
+    except Exception:
+      pass
+
+
+def pack(strings, B, H, W, z_shape, y_shape):
+  head = MAGIC + struct.pack("<9I", B, H, W, z_shape[1], z_shape[2], z_shape[3], y_shape[1], y_shape[2], y_shape[3])
+  lens = b"".join(struct.pack("<2I", len(sz), len(sy)) for sz, sy in strings)
+  return head + lens + b"".join(sz + sy for sz, sy in strings)
+
+
+def unpack(blob):
+  if blob[:5] != MAGIC:
+    raise ValueError("not an SNTC v1 container")
+  B, H, W, hz, wz, Cz, hy, wy, Cy = struct.unpack_from("<9I", blob, 5)
+  pos = 5 + 36
+  lens = [struct.unpack_from("<2I", blob, pos + 8 * b) for b in range(B)]
+  pos += 8 * B
+  if pos + sum(a + b for a, b in lens) != len(blob):
+    raise ValueError("SNTC container: payload length does not match the header (truncated or corrupt)")
+  strings = []
+  for lz, ly in lens:
+    strings.append((blob[pos:pos + lz], blob[pos + lz:pos + lz + ly]))
+    pos += lz + ly
+  return strings, (B, H, W), (B, hz, wz, Cz), (B, hy, wy, Cy)
+
+
+def compress(model, coder, z_hat, q_y, image_hw):
+  """Symbols -> container bytes.  The scale-table rows come from the GPU (phase 1), exactly as the decoder will see them."""
+  H, W = image_hw
+  z_hat = np.ascontiguousarray(z_hat, dtype=np.float32)
+  idx = model.decode_hyper(z_hat)
+  strings = [(coder.encode_z(z_hat[b]), coder.encode_y(q_y[b], idx[b])) for b in range(z_hat.shape[0])]
+  return pack(strings, z_hat.shape[0], H, W, z_hat.shape, q_y.shape)
+
+
+def decompress(model, coder, blob, timing=None, **kw):
+  """Container bytes -> decompress() dict (``image`` uint8 [B,H,W,3], ...): range-decode z (host) -> hyper-synthesis
+  (GPU) -> idx -> range-decode q (host) -> dequantise + synthesis (GPU).  ``timing``: dict that receives the seconds
+  spent in the host coder (``range_decode_s``) and in the GPU calls (``gpu_s``), reported separately (north_star)."""
+  strings, (B, H, W), zs, ys = unpack(blob)
+  t0 = time.perf_counter()
+  z = np.stack([coder.decode_z(sz, zs[1:]) for sz, _ in strings]).astype(np.float32)
+  t1 = time.perf_counter()
+  idx = model.decode_hyper(z)
+  t2 = time.perf_counter()
+  q = np.stack([coder.decode_y(sy, idx[b]) for b, (_, sy) in enumerate(strings)])
+  q = q.astype(np.int8) if np.abs(q).max(initial=0) <= 127 else q.astype(np.int16)
+  t3 = time.perf_counter()
+  out = model.decode_latents(q, (H, W), **kw)
+  t4 = time.perf_counter()
+  out["idx"], out["z_hat"], out["q_y"] = idx, z, q
+  if timing is not None:
+    timing.update(range_decode_s=(t1 - t0) + (t3 - t2), gpu_s=(t2 - t1) + (t4 - t3))
+  return out

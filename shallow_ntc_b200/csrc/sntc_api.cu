@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "sntc_kernels_rate.cuh"
 #include "sntc_kernels_tc.cuh"
 #include "sntc_kernels_tail_tc.cuh"
+#include "sntc_coder.hpp"
 
 using namespace sntc;
 
@@ -79,6 +81,8 @@ struct sntc_model {
   DevBuf d_rate_slots, d_rate_img, d_rate_zslots, d_rate;   // rate term: partial slots, slot->image map, per-image [bits_y, bits_z]
   float* d_prior = nullptr;             // NoisyDeepFactorized parameters [Cz][DF_STRIDE] (softplus / tanh applied)
   double* h_rate = nullptr; int h_rate_cap = 0;   // pinned
+  DevBuf d_mu;                          // two-phase decode: mu of the last sntc_decode_hyper [B,hy,wy,Cy] f32
+  int ph_B = 0, ph_hy = 0, ph_wy = 0;   // geometry of that call (0 = none pending)
   TcModelState tc;                      // tensor-core plan state (tensor maps, fp16 planes)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
@@ -310,7 +314,7 @@ extern "C" int sntc_model_destroy(sntc_model* m) {
   cudaStreamSynchronize(m->ctx->stream);
   for (void* p : m->owned) cudaFree(p);
   for (DevBuf* b : {&m->ws_a, &m->ws_b, &m->ws_c, &m->st_z, &m->st_q, &m->st_u8, &m->st_idx, &m->st_yhat, &m->st_f32,
-                    &m->st_orig, &m->d_hs, &m->d_yhat, &m->d_ssd, &m->d_rate_slots, &m->d_rate_img, &m->d_rate_zslots, &m->d_rate})
+                    &m->st_orig, &m->d_hs, &m->d_yhat, &m->d_ssd, &m->d_rate_slots, &m->d_rate_img, &m->d_rate_zslots, &m->d_rate, &m->d_mu})
     b->release();
   m->tc.release();
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
@@ -704,6 +708,7 @@ struct Cur { const float* f32 = nullptr; const __half* hi = nullptr; const __hal
 struct HyperFuse {
   const void* q = nullptr; int q_kind = 0; int Cy = 0; float max_index = 63.f; bool trunc = false;
   float* y_hat = nullptr; uint8_t* idx = nullptr;
+  bool no_planes = false;   // phase 1 of the two-phase decode: only fp32 mu + idx leave the epilogue
   bool want_rate = false; RateConst rc{}; double* rate_slots = nullptr; int* rate_slot_img = nullptr; size_t rate_nslots = 0;
   bool done = false; const __half* yh_hi = nullptr; const __half* yh_lo = nullptr;   // out: planes of y_hat
 };
@@ -784,9 +789,11 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
             o.rate_slots = (double*)m->d_rate_slots.p; o.rate_slot_img = (int*)m->d_rate_img.p; o.rate_slot_cap = ns; o.rc = hf->rc;
             hf->rate_slots = o.rate_slots; hf->rate_slot_img = o.rate_slot_img; hf->rate_nslots = ns;
           }
-          size_t pl = (size_t)B * ch * c.s * cw * c.s * hf->Cy * 2;
-          if (!m->tc.yh[0].ensure(pl) || !m->tc.yh[1].ensure(pl)) return fail(SNTC_E_CUDA, "cudaMalloc failed for the y_hat planes");
-          o.hi = (__half*)m->tc.yh[0].p; o.lo = (__half*)m->tc.yh[1].p;
+          if (!hf->no_planes) {
+            size_t pl = (size_t)B * ch * c.s * cw * c.s * hf->Cy * 2;
+            if (!m->tc.yh[0].ensure(pl) || !m->tc.yh[1].ensure(pl)) return fail(SNTC_E_CUDA, "cudaMalloc failed for the y_hat planes");
+            o.hi = (__half*)m->tc.yh[0].p; o.lo = (__half*)m->tc.yh[1].p;
+          }
           hf->done = true; hf->yh_hi = o.hi; hf->yh_lo = o.lo;
         } else if (last) {
           if (fin) { o.f32 = fin->full; o.u8 = fin->u8; o.crop = fin->crop; o.H = fin->H; o.W = fin->W; }
@@ -1137,6 +1144,233 @@ extern "C" int sntc_decode_rd(sntc_model* m, const sntc_tensor* z_hat, const snt
                               const sntc_tensor* original_u8, sntc_image_metrics* metrics, sntc_image_rate* rate, void* stream) {
   return decode_impl(m, z_hat, q_y, H, W, out_u8, out_idx, out_yhat, out_f32, original_u8, metrics, rate, stream);
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Two-phase decode: q_y can only be range-decoded once the scale-table rows are known, so a real decoder runs
+// hyper-synthesis first (-> idx to the host coder, mu stays on the device), then dequantises and synthesises.
+extern "C" int sntc_decode_hyper(sntc_model* m, const sntc_tensor* z_hat, sntc_tensor* out_idx, void* stream) {
+  if (!m) return fail(SNTC_E_INVALID, "sntc_decode_hyper: model is NULL");
+  if (!m->finalized) return fail(SNTC_E_STATE, "sntc_decode_hyper: model not finalized");
+  if (!m->has_hyper || !m->has_syn) return fail(SNTC_E_STATE, "sntc_decode_hyper: needs a mean-scale hyperprior model");
+  TRY(check_tensor(z_hat, "z_hat", SNTC_DL_FLOAT, 32, 4));
+  const int B = (int)z_hat->shape[0], hz = (int)z_hat->shape[1], wz = (int)z_hat->shape[2];
+  if (z_hat->shape[3] != m->hyper.in_channels) return fail(SNTC_E_INVALID, "z_hat: wrong channel count");
+  const int hy = hz * m->hyper.upsample, wy = wz * m->hyper.upsample, Cy = m->syn.in_channels;
+  TRY(check_tensor(out_idx, "out_idx", SNTC_DL_UINT, 8, 4));
+  TRY(expect_shape(out_idx, "out_idx", B, hy, wy, Cy));
+  m->ph_B = 0;
+  if (B == 0) return SNTC_OK;
+  sntc_ctx* ctx = m->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick_stream(ctx, stream);
+  const size_t n_lat = (size_t)B * hy * wy * Cy;
+  const void* d_z; void* d_idx; bool need_sync = false;
+  TRY(stage_in(m, z_hat, tensor_elems(z_hat) * 4, m->st_z, s, &d_z));
+  TRY(stage_out(m, out_idx, n_lat, m->st_idx, &d_idx));
+  TRY(m->d_mu.ensure(n_lat * 4));
+  bool fused = false;
+  if (m->desc.precision == SNTC_PRECISION_TC_F16X3 && op_on_tc(m, m->hyper, true, m->hyper.ops.size() - 1)) {
+    HyperFuse hf;
+    hf.q = nullptr; hf.q_kind = 3; hf.Cy = Cy; hf.max_index = (float)(m->desc.num_scales - 1);
+    hf.trunc = m->desc.index_rounding == SNTC_INDEX_TRUNC;
+    hf.y_hat = (float*)m->d_mu.p; hf.idx = (uint8_t*)d_idx; hf.no_planes = true;
+    Cur c0; c0.f32 = (const float*)d_z;
+    TRY(run_transform(m, m->hyper, true, c0, B, hz, wz, nullptr, &hf, s));
+    fused = hf.done;
+  }
+  if (!fused) {
+    TRY(m->d_hs.ensure(n_lat * 2 * 4));
+    FinalOut fin; fin.full = (float*)m->d_hs.p;
+    Cur c0; c0.f32 = (const float*)d_z;
+    TRY(run_transform(m, m->hyper, true, c0, B, hz, wz, &fin, nullptr, s));
+    DequantParams P{};
+    P.hs = (const float*)m->d_hs.p; P.q = nullptr; P.q_kind = 3; P.npix = (size_t)B * hy * wy; P.C = Cy;
+    P.max_index = (float)(m->desc.num_scales - 1); P.trunc = m->desc.index_rounding == SNTC_INDEX_TRUNC;
+    P.y_hat = (float*)m->d_mu.p; P.idx = (uint8_t*)d_idx;
+    size_t n = P.npix * (Cy / 4);
+    dequant_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(P);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+  }
+  TRY(unstage_out(out_idx, n_lat, d_idx, s, &need_sync));
+  if (need_sync) CU_TRY(cudaStreamSynchronize(s));
+  m->ph_B = B; m->ph_hy = hy; m->ph_wy = wy;
+  return SNTC_OK;
+}
+
+extern "C" int sntc_decode_latents(sntc_model* m, const sntc_tensor* q_y, int H, int W, sntc_tensor* out_u8, sntc_tensor* out_yhat,
+                                   sntc_tensor* out_f32, const sntc_tensor* original_u8, sntc_image_metrics* metrics, void* stream) {
+  if (!m) return fail(SNTC_E_INVALID, "sntc_decode_latents: model is NULL");
+  if (!m->finalized) return fail(SNTC_E_STATE, "sntc_decode_latents: model not finalized");
+  if (m->ph_B == 0) return fail(SNTC_E_STATE, "sntc_decode_latents: no sntc_decode_hyper call is pending");
+  if (!q_y || !q_y->shape || q_y->ndim != 4) return fail(SNTC_E_INVALID, "q_y: expected rank 4");
+  int q_kind;
+  if (q_y->dtype_code == SNTC_DL_FLOAT && q_y->dtype_bits == 32) q_kind = 0;
+  else if (q_y->dtype_code == SNTC_DL_INT && q_y->dtype_bits == 16) q_kind = 1;
+  else if (q_y->dtype_code == SNTC_DL_INT && q_y->dtype_bits == 8) q_kind = 2;
+  else return fail(SNTC_E_INVALID, "q_y: dtype must be float32, int16 or int8");
+  TRY(check_tensor(q_y, "q_y", q_y->dtype_code, q_y->dtype_bits, 4));
+  const int q_bytes = q_kind == 0 ? 4 : (q_kind == 1 ? 2 : 1);
+  const int B = m->ph_B, hy = m->ph_hy, wy = m->ph_wy, Cy = m->syn.in_channels, Co = m->syn.out_channels;
+  TRY(expect_shape(q_y, "q_y", B, hy, wy, Cy));
+  const int Hp = hy * m->syn.upsample, Wp = wy * m->syn.upsample;
+  if (H <= 0 || W <= 0 || H > Hp || W > Wp) return fail(SNTC_E_INVALID, "sntc_decode_latents: image size does not fit the latent grid");
+  TRY(check_tensor(out_u8, "out_u8", SNTC_DL_UINT, 8, 4));
+  TRY(expect_shape(out_u8, "out_u8", B, H, W, Co));
+  if (out_yhat) { TRY(check_tensor(out_yhat, "out_yhat", SNTC_DL_FLOAT, 32, 4)); TRY(expect_shape(out_yhat, "out_yhat", B, hy, wy, Cy)); }
+  if (out_f32) { TRY(check_tensor(out_f32, "out_f32", SNTC_DL_FLOAT, 32, 4)); TRY(expect_shape(out_f32, "out_f32", B, H, W, Co)); }
+  if ((original_u8 != nullptr) != (metrics != nullptr)) return fail(SNTC_E_INVALID, "sntc_decode_latents: original_u8 and metrics go together");
+  if (original_u8) { TRY(check_tensor(original_u8, "original_u8", SNTC_DL_UINT, 8, 4)); TRY(expect_shape(original_u8, "original_u8", B, H, W, Co)); }
+  sntc_ctx* ctx = m->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick_stream(ctx, stream);
+  bool need_sync = false;
+  const size_t n_lat = (size_t)B * hy * wy * Cy, n_img = (size_t)B * H * W * Co;
+  const void* d_q; void* d_u8; void* d_f32 = nullptr; const void* d_orig = nullptr;
+  TRY(stage_in(m, q_y, n_lat * q_bytes, m->st_q, s, &d_q));
+  TRY(stage_out(m, out_u8, n_img, m->st_u8, &d_u8));
+  if (out_f32) TRY(stage_out(m, out_f32, n_img * 4, m->st_f32, &d_f32));
+  if (original_u8) TRY(stage_in(m, original_u8, n_img, m->st_orig, s, &d_orig));
+  const bool syn_tc = op_on_tc(m, m->syn, false, 0);
+  float* d_yhat = nullptr;
+  if (out_yhat && on_device(out_yhat)) d_yhat = (float*)tdata(out_yhat);
+  else if (out_yhat || !syn_tc) { TRY(m->d_yhat.ensure(n_lat * 4)); d_yhat = (float*)m->d_yhat.p; }
+  __half* hi = nullptr; __half* lo = nullptr;
+  if (syn_tc) {
+    if (!m->tc.yh[0].ensure(n_lat * 2) || !m->tc.yh[1].ensure(n_lat * 2)) return fail(SNTC_E_CUDA, "cudaMalloc failed for the y_hat planes");
+    hi = (__half*)m->tc.yh[0].p; lo = (__half*)m->tc.yh[1].p;
+  }
+  {
+    ProfScope ps(m, s, "dequant_planes", 0);
+    const size_t n8 = n_lat / 8;
+    dequant_planes_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>((const float*)m->d_mu.p, d_q, q_kind, n8, d_yhat, hi, lo);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+  }
+  Cur ycur; ycur.f32 = d_yhat; ycur.hi = hi; ycur.lo = lo;
+  {
+    FinalOut fin; fin.u8 = (uint8_t*)d_u8; fin.crop = (float*)d_f32; fin.H = H; fin.W = W;
+    TRY(run_transform(m, m->syn, false, ycur, B, hy, wy, &fin, nullptr, s));
+  }
+  if (original_u8) {
+    TRY(m->d_ssd.ensure((size_t)B * 8));
+    if (m->h_ssd_cap < B) {
+      if (m->h_ssd) cudaFreeHost(m->h_ssd);
+      CU_TRY(cudaHostAlloc((void**)&m->h_ssd, (size_t)B * 8, cudaHostAllocDefault));
+      m->h_ssd_cap = B;
+    }
+    CU_TRY(cudaMemsetAsync(m->d_ssd.p, 0, (size_t)B * 8, s));
+    size_t per = (size_t)H * W * Co;
+    dim3 grid((unsigned)std::min<size_t>((per + 256 * 16 - 1) / (256 * 16), 1024), B);
+    ssd_kernel<<<grid, 256, 0, s>>>((const uint8_t*)d_orig, (const uint8_t*)d_u8, per, (unsigned long long*)m->d_ssd.p);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(m->h_ssd, m->d_ssd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    need_sync = true;
+  }
+  TRY(unstage_out(out_u8, n_img, d_u8, s, &need_sync));
+  if (out_f32) TRY(unstage_out(out_f32, n_img * 4, d_f32, s, &need_sync));
+  if (out_yhat && !on_device(out_yhat)) TRY(unstage_out(out_yhat, n_lat * 4, d_yhat, s, &need_sync));
+  if (need_sync) CU_TRY(cudaStreamSynchronize(s));
+  if (metrics) {
+    double npx = (double)H * W * Co;
+    for (int b = 0; b < B; ++b) {
+      metrics[b].ssd = m->h_ssd[b];
+      metrics[b].mse = (double)m->h_ssd[b] / npx;
+      metrics[b].psnr = -10.0 * (std::log(metrics[b].mse) - 2.0 * std::log(255.0)) / std::log(10.0);
+    }
+  }
+  return SNTC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host entropy coder (I/O stage; see sntc_coder.hpp)
+struct sntc_coder { Coder c; };
+
+extern "C" int sntc_coder_create(int num_scales, double scale_min, double scale_max, double tail_mass, int precision, sntc_coder** out) {
+  if (!out) return fail(SNTC_E_INVALID, "sntc_coder_create: out is NULL");
+  *out = nullptr;
+  if (num_scales < 1 || num_scales > 256 || !(scale_min > 0) || !(scale_max >= scale_min) || !(tail_mass > 0 && tail_mass < 1) || precision < 8 || precision > 16)
+    return fail(SNTC_E_INVALID, "sntc_coder_create: bad parameter");
+  auto k = std::make_unique<sntc_coder>();
+  k->c.precision = precision; k->c.tail_mass = tail_mass;
+  // SCALE_FN(i) = exp(log(SCALE_MIN) + SCALE_FACTOR * i)   mshyper/models.py:27-32
+  const double factor = num_scales > 1 ? (std::log(scale_max) - std::log(scale_min)) / (num_scales - 1.0) : 0.0;
+  for (int i = 0; i < num_scales; ++i) {
+    k->c.scale_rows.push_back(build_normal_table(std::exp(std::log(scale_min) + factor * i), tail_mass, precision));
+    if (k->c.scale_rows.back().nsym + 1 > (1 << precision)) return fail(SNTC_E_INVALID, "sntc_coder_create: precision too small for the widest scale");
+  }
+  *out = k.release();
+  return SNTC_OK;
+}
+
+extern "C" int sntc_coder_destroy(sntc_coder* k) { delete k; return SNTC_OK; }
+
+extern "C" int sntc_coder_set_prior(sntc_coder* k, int Cz, const float* raw43) {
+  if (!k || !raw43 || Cz <= 0) return fail(SNTC_E_INVALID, "sntc_coder_set_prior: bad argument");
+  auto sp = [](double x) { return x > 30 ? x : std::log1p(std::exp(x)); };
+  k->c.prior_rows.clear();
+  for (int c = 0; c < Cz; ++c) {
+    const float* p = raw43 + (size_t)c * 43;   // matrix_0[3] bias_0[3] factor_0[3] matrix_1[9] bias_1[3] factor_1[3] matrix_2[9] bias_2[3] factor_2[3] matrix_3[3] bias_3[1]
+    DeepFactorizedChannel ch;
+    for (int i = 0; i < 3; ++i) { ch.m0[i] = sp(p[i]); ch.b0[i] = p[3 + i]; ch.f0[i] = std::tanh((double)p[6 + i]); }
+    for (int i = 0; i < 9; ++i) { ch.m1[i] = sp(p[9 + i]); ch.m2[i] = sp(p[24 + i]); }
+    for (int i = 0; i < 3; ++i) { ch.b1[i] = p[18 + i]; ch.f1[i] = std::tanh((double)p[21 + i]); ch.b2[i] = p[33 + i]; ch.f2[i] = std::tanh((double)p[36 + i]); ch.m3[i] = sp(p[39 + i]); }
+    ch.b3 = p[42];
+    k->c.prior_rows.push_back(build_prior_table(ch, k->c.tail_mass, k->c.precision));
+    if (k->c.prior_rows.back().nsym + 1 > (1 << k->c.precision)) return fail(SNTC_E_INVALID, "sntc_coder_set_prior: precision too small for the prior's support");
+  }
+  return SNTC_OK;
+}
+
+static const std::vector<CdfTable>* coder_tables(sntc_coder* k, int kind) {
+  if (!k) return nullptr;
+  return kind == 0 ? &k->c.scale_rows : (kind == 1 ? &k->c.prior_rows : nullptr);
+}
+
+extern "C" int sntc_coder_table(sntc_coder* k, int kind, int row, int32_t* offset, int32_t* nsym, const uint32_t** cdf) {
+  const std::vector<CdfTable>* t = coder_tables(k, kind);
+  if (!t || row < 0 || row >= (int)t->size()) return fail(SNTC_E_INVALID, "sntc_coder_table: no such table");
+  if (offset) *offset = (*t)[row].offset;
+  if (nsym) *nsym = (*t)[row].nsym;
+  if (cdf) *cdf = (*t)[row].cdf.data();
+  return SNTC_OK;
+}
+
+extern "C" int sntc_coder_encode(sntc_coder* k, int kind, const int32_t* symbols, const uint8_t* rows, size_t n, uint8_t** bytes, size_t* nbytes) {
+  const std::vector<CdfTable>* t = coder_tables(k, kind);
+  if (!t || t->empty() || !symbols || !bytes || !nbytes || (kind == 0 && !rows)) return fail(SNTC_E_INVALID, "sntc_coder_encode: bad argument");
+  RangeEncoder enc;
+  const size_t nrow = t->size();
+  for (size_t i = 0; i < n; ++i) {
+    const size_t r = kind == 0 ? rows[i] : i % nrow;
+    if (r >= nrow) return fail(SNTC_E_INVALID, "sntc_coder_encode: table row out of range");
+    encode_symbol(enc, (*t)[r], symbols[i], k->c.precision);
+  }
+  std::vector<uint8_t> out = enc.finish();
+  *bytes = (uint8_t*)malloc(out.size() ? out.size() : 1);
+  if (!*bytes) return fail(SNTC_E_INVALID, "sntc_coder_encode: out of memory");
+  memcpy(*bytes, out.data(), out.size());
+  *nbytes = out.size();
+  return SNTC_OK;
+}
+
+extern "C" int sntc_coder_decode(sntc_coder* k, int kind, const uint8_t* bytes, size_t nbytes, const uint8_t* rows, size_t n, int32_t* symbols) {
+  const std::vector<CdfTable>* t = coder_tables(k, kind);
+  if (!t || t->empty() || !symbols || (!bytes && nbytes) || (kind == 0 && !rows)) return fail(SNTC_E_INVALID, "sntc_coder_decode: bad argument");
+  RangeDecoder dec(bytes, nbytes);
+  const size_t nrow = t->size();
+  for (size_t i = 0; i < n; ++i) {
+    const size_t r = kind == 0 ? rows[i] : i % nrow;
+    if (r >= nrow) return fail(SNTC_E_INVALID, "sntc_coder_decode: table row out of range");
+    symbols[i] = decode_symbol(dec, (*t)[r], k->c.precision);
+  }
+  if (dec.overrun()) return fail(SNTC_E_INVALID, "sntc_coder_decode: bitstream ended before all symbols were decoded (truncated or corrupt)");
+  return SNTC_OK;
+}
+
+extern "C" void sntc_coder_free(void* p) { free(p); }
 
 extern "C" int sntc_last_stage_times_ms(sntc_model* m, float out[4]) {
   if (!m || !out) return fail(SNTC_E_INVALID, "sntc_last_stage_times_ms: bad argument");

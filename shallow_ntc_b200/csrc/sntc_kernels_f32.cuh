@@ -2,6 +2,7 @@
 // kernels shared with the tensor-core path.  All tensors NHWC.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace sntc {
@@ -523,6 +524,7 @@ struct DequantParams {
 };
 
 __device__ __forceinline__ float4 load_q4(const void* q, int kind, size_t e) {
+  if (kind == 3) return make_float4(0.f, 0.f, 0.f, 0.f);   // no symbols yet (phase 1 of the two-phase decode): y_hat = mu
   if (kind == 0) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(q) + e));
   if (kind == 1) {
     short4 v = *reinterpret_cast<const short4*>(reinterpret_cast<const int16_t*>(q) + e);
@@ -557,6 +559,35 @@ __global__ void dequant_index_kernel(const DequantParams P) {
     o.x = scale_index(sg.x, P.max_index, P.trunc); o.y = scale_index(sg.y, P.max_index, P.trunc);
     o.z = scale_index(sg.z, P.max_index, P.trunc); o.w = scale_index(sg.w, P.max_index, P.trunc);
     *reinterpret_cast<uchar4*>(P.idx + e) = o;
+  }
+}
+
+// Phase 2 of the two-phase decode: y_hat = q + mu (mshyper/models.py:278) from the mu kept by phase 1; writes fp32
+// and/or the fp16 hi/lo planes the tensor-core synthesis reads.  One thread per 8 elements.
+__global__ void dequant_planes_kernel(const float* __restrict__ mu, const void* __restrict__ q, int kind, size_t n8,
+                                      float* __restrict__ y_hat, __half* __restrict__ hi, __half* __restrict__ lo) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const size_t e = i * 8;
+  const float4 m0 = __ldg(reinterpret_cast<const float4*>(mu + e)), m1 = __ldg(reinterpret_cast<const float4*>(mu + e + 4));
+  const float4 q0 = load_q4(q, kind, e), q1 = load_q4(q, kind, e + 4);
+  const float y[8] = {__fadd_rn(q0.x, m0.x), __fadd_rn(q0.y, m0.y), __fadd_rn(q0.z, m0.z), __fadd_rn(q0.w, m0.w),
+                      __fadd_rn(q1.x, m1.x), __fadd_rn(q1.y, m1.y), __fadd_rn(q1.z, m1.z), __fadd_rn(q1.w, m1.w)};
+  if (y_hat) {
+    *reinterpret_cast<float4*>(y_hat + e) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(y_hat + e + 4) = make_float4(y[4], y[5], y[6], y[7]);
+  }
+  if (hi) {
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float c = fminf(fmaxf(y[k], -65504.f), 65504.f);
+      h[k] = __float2half_rn(c);
+      l[k] = __float2half_rn(c - __half2float(h[k]));
+    }
+    *reinterpret_cast<uint4*>(hi + e) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + e) = *reinterpret_cast<const uint4*>(l);
   }
 }
 

@@ -360,7 +360,10 @@ __device__ __forceinline__ void store16_f32(float* o, const float* v) {
   tcx::stg256(o + 8, reinterpret_cast<const uint32_t*>(v) + 8);
 }
 __device__ __forceinline__ void load_q16(const void* q, int kind, size_t e, float* out) {
-  if (kind == 0) {
+  if (kind == 3) {   // no symbols yet (phase 1 of the two-phase decode)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = 0.f;
+  } else if (kind == 0) {
     tcx::ldg256_nc(reinterpret_cast<const float*>(q) + e, reinterpret_cast<uint32_t*>(out));
     tcx::ldg256_nc(reinterpret_cast<const float*>(q) + e + 8, reinterpret_cast<uint32_t*>(out) + 8);
   } else if (kind == 1) {

@@ -232,6 +232,51 @@ class Model:
       out["synthesis_time"] = t[2] * 1e-3
     return out
 
+  def decode_hyper(self, z_hat, out=None):
+    """Phase 1 of the two-phase decode (sntc_decode_hyper): hyper-synthesis -> scale-table rows idx uint8
+    [B,hy,wy,Cy] for the range decoder; mu stays on the device for ``decode_latents``."""
+    self._ensure_native()
+    z = as_tensor(z_hat, self._ctx.device)
+    B, hz, wz, _ = z.shape
+    up = self._hyper_synthesis.upsample
+    if out is None:
+      out = empty_like_kind(self._ctx, z_hat, (B, hz * up, wz * up, self._bottleneck_size), np.uint8)
+    o = as_tensor(out, self._ctx.device)
+    check(lib.sntc_decode_hyper(self._native.handle, z.byref(), o.byref(), None))
+    self._ctx.sync()
+    return out
+
+  def decode_latents(self, q_y, image_hw, *, return_yhat=False, return_float=False, original=None, out=None):
+    """Phase 2 (sntc_decode_latents): y_hat = q_y + mu (mu of the last ``decode_hyper``), synthesis, crop, uint8."""
+    self._ensure_native()
+    ctx = self._ctx
+    H, W = int(image_hw[0]), int(image_hw[1])
+    q = as_tensor(q_y, ctx.device)
+    B, hy, wy, Cy = q.shape
+    Co = self._synthesis.out_channels
+    out = dict(out or {})
+
+    def buf(key, shape, dtype, want):
+      if not want:
+        return None
+      if key not in out:
+        out[key] = empty_like_kind(ctx, q_y, shape, dtype)
+      return as_tensor(out[key], ctx.device)
+
+    t_img = buf("image", (B, H, W, Co), np.uint8, True)
+    t_yh = buf("y_hat", (B, hy, wy, Cy), np.float32, return_yhat)
+    t_f = buf("float", (B, H, W, Co), np.float32, return_float)
+    t_orig = as_tensor(original, ctx.device)
+    metrics = (ImageMetrics * B)() if original is not None else None
+    check(lib.sntc_decode_latents(self._native.handle, q.byref(), H, W, t_img.byref(), t_yh.byref() if t_yh else None,
+                                  t_f.byref() if t_f else None, t_orig.byref() if t_orig else None, metrics, None))
+    ctx.sync()
+    if metrics is not None:
+      out["mse"] = np.array([m.mse for m in metrics])
+      out["psnr"] = np.array([m.psnr for m in metrics])
+      out["ssd"] = np.array([m.ssd for m in metrics], dtype=np.uint64)
+    return out
+
   def evaluate(self, z_hat, q_y, originals, image_hw=None, **kw):
     """Model.evaluate (mshyper/models.py:415-433) from decoded symbols: yields one metrics dict per image
     (see eval_lib.evaluate_symbols)."""
