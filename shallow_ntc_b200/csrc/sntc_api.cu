@@ -644,7 +644,13 @@ static int run_rgb_f32(sntc_ctx* ctx, const ConvLayer& c, const float* in, int B
       TailWeights<5, 12> Wt;
       memcpy(&Wt, c.h_w_tail.data(), sizeof(Wt));
       dim3 grid((Q.wout + 63) / 64, (Q.hout + 31) / 32, B);
-      tail_s2_const_kernel<5, 1, 12, 4><<<grid, 128, 0, s>>>(Q, Wt);
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = grid; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = tc_pdl() ? 1 : 0;
+      CU_TRY(cudaLaunchKernelEx(&cfg, tail_s2_const_kernel<5, 1, 12, 4>, Q, Wt));
       ctx->launches++;
       CU_TRY(cudaGetLastError());
       return SNTC_OK;

@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(32 * TR, 4) tail_s2_const_kernel(const TailPar
   constexpr int NY = ((P + RY - 1) >> 1) - (P >> 1) + T, NX = ((P + 1) >> 1) - (P >> 1) + T;
   constexpr int TILE_Y = (RY / 2) * (TR - 1) + NY, TILE_X = (TCX - 1) + NX;
   __shared__ __align__(16) float sx[TILE_Y * TILE_X * C1];
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched as a programmatic dependent of the layer-1 kernel
   const int b = blockIdx.z;
   const int oy0 = blockIdx.y * (RY * TR), ox0 = blockIdx.x * (2 * TCX);
   const int ny0 = oy0 / 2 + (P >> 1) - (T - 1), nx0 = ox0 / 2 + (P >> 1) - (T - 1);
