@@ -15,6 +15,7 @@
 #include "sntc_kernels_rate.cuh"
 #include "sntc_kernels_tc.cuh"
 #include "sntc_kernels_tail_tc.cuh"
+#include "sntc_kernels_tail_mma.cuh"
 #include "sntc_coder.hpp"
 
 using namespace sntc;
@@ -84,6 +85,7 @@ struct sntc_model {
   DevBuf d_mu;                          // two-phase decode: mu of the last sntc_decode_hyper [B,hy,wy,Cy] f32
   int ph_B = 0, ph_hy = 0, ph_wy = 0;   // geometry of that call (0 = none pending)
   TcModelState tc;                      // tensor-core plan state (tensor maps, fp16 planes)
+  std::vector<TailMma> tail_mma;       // parallel to syn.convs: warp-MMA tail of a two-layer synthesis (tc precision only)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
   unsigned long long* h_ssd = nullptr;  // pinned
@@ -406,6 +408,15 @@ extern "C" int sntc_model_finalize(sntc_model* m) {
     std::string err;
     if (!tc_finalize(m->ctx->tc, m->tc, m->has_hyper ? &m->hyper : nullptr, m->has_syn ? &m->syn : nullptr, m->hw, m->owned, &err))
       return fail(SNTC_E_CUDA, "sntc_model_finalize (tensor-core path): " + err);
+    // warp-MMA tail of a two-layer synthesis (sntc_kernels_tail_mma.cuh); SNTC_TAIL_MMA=0 keeps the FFMA tail
+    if (m->has_syn && tc_env_int("SNTC_TAIL_MMA", 1)) {
+      m->tail_mma.assign(m->syn.convs.size(), TailMma{});
+      for (auto& op : m->syn.ops) {
+        if (op.type != OP_CONVT_RGB || !tail_mma_supported(m->syn.convs[op.conv])) continue;
+        if (!tail_mma_pack(m->syn.convs[op.conv], m->hw, m->tail_mma[op.conv], m->owned, &err))
+          return fail(SNTC_E_CUDA, "sntc_model_finalize (warp-MMA tail): " + err);
+      }
+    }
   }
   if (m->desc.prior == SNTC_PRIOR_DEEP_FACTORIZED) {
     const int Cz = m->hyper.in_channels;
@@ -855,6 +866,18 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
         if (tail_tc_run(ctx->tc, c, tt, tt.bias, cur.hi, cur.lo, B, ch, cw, to, s, &ctx->launches, &err) != TC_OK)
           return fail(SNTC_E_CUDA, "tensor-core tail: " + err);
+        ch *= c.s; cw *= c.s; cc = c.cout;
+        cur = Cur{};
+        continue;
+      }
+      if (op.type == OP_CONVT_RGB && cur.f32 && !is_hyper && op.conv < (int)m->tail_mma.size() && m->tail_mma[op.conv].ok) {
+        // ---- warp-MMA tail (split-fp16 mma.sync): stride-2 conv to 3 channels + crop + uint8 ----
+        TailMmaOut to;
+        if (fin) { to.f32 = fin->full; to.u8 = fin->u8; to.crop = fin->crop; to.H = fin->H; to.W = fin->W; }
+        std::string err;
+        ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
+        if (tail_mma_run(c, m->tail_mma[op.conv], cur.f32, B, ch, cw, to, tc_pdl(), s, &ctx->launches, &err) != 0)
+          return fail(SNTC_E_CUDA, "warp-MMA tail: " + err);
         ch *= c.s; cw *= c.s; cc = c.cout;
         cur = Cur{};
         continue;

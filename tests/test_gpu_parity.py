@@ -193,6 +193,27 @@ def test_tensor_core_tail_kernel_matches_oracle(gpu_ctx, monkeypatch, name, B, H
   assert np.abs(ref2["float"] - got["float"]).max() < 1e-4
 
 
+@pytest.mark.parametrize("name,B,H,W", [("two_layer_syn", 2, 128, 192), ("two_layer_syn2", 1, 100, 150), ("two_layer_syn2", 2, 97, 149),
+                                        ("two_layer_syn", 1, 512, 768)])
+def test_warp_mma_tail_kernel(gpu_ctx, monkeypatch, name, B, H, W):
+  """The warp-MMA tail (sntc_kernels_tail_mma.cuh, default for C1 = 12 on the tensor-core path): same gates against the
+  oracle as every other kernel; its uint8-only fast path writes exactly the bytes of its generic path (odd widths,
+  crops and ragged tiles included); and it agrees with the FFMA tail (SNTC_TAIL_MMA=0) far inside the tolerance."""
+  model, wts, z, q = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
+  got = model.decompress(z, q, (H, W), return_float=True, return_yhat=True)
+  if H * W <= 128 * 192:
+    ref = oracle_decode(model, wts, z, q, H, W)
+    print(name, check_against_oracle(got, ref, precision="tc"))
+  fast = model.decompress(z, q, (H, W))
+  assert np.array_equal(fast["image"], got["image"])
+  monkeypatch.setenv("SNTC_TAIL_MMA", "0")
+  base, _, _, _ = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
+  ffma = base.decompress(z, q, (H, W), return_float=True)
+  assert np.abs(ffma["float"] - got["float"]).max() < 2e-6
+  d = np.abs(ffma["image"].astype(int) - got["image"].astype(int))
+  assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
 # --------------------------------------------------------------------------------------------------
 # rate term (SURVEY a7 / f2)
 
