@@ -147,7 +147,11 @@ def main():
   ap.add_argument("--precision", default=os.environ.get("SNTC_PRECISION", "auto"))
   ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through (working set > L2)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--height", type=int, default=512, help="image height (side runs of the other BASELINE configs; the headline is 512x768)")
+  ap.add_argument("--width", type=int, default=768)
   args = ap.parse_args()
+  global H, W
+  H, W = args.height, args.width
   args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
   cores = os.cpu_count()
 
@@ -200,8 +204,11 @@ def main():
   for r in range(args.rotate):
     z, q = synthetic.make_latents(zs, ys, first_index=(rank * args.rotate + r) * B)
     sets.append((z, q))
-  dev = [(ctx.to_device(z), ctx.to_device(q)) for z, q in sets]
-  out_dev = dict(image=ctx.empty((B, H, W, 3), np.uint8), idx=ctx.empty(ys, np.uint8))
+  hyper = zs is not None                      # the factorized model (bls2017) has no z_hat and no scale indexes
+  dev = [(ctx.to_device(z) if hyper else None, ctx.to_device(q)) for z, q in sets]
+  out_dev = dict(image=ctx.empty((B, H, W, 3), np.uint8))
+  if hyper:
+    out_dev["idx"] = ctx.empty(ys, np.uint8)
 
   def step_dev(i):
     dz, dq = dev[i % args.rotate]
@@ -221,8 +228,10 @@ def main():
   e0, e1 = ctx.event(), ctx.event()
   barrier()
   e0.record()
+  th0 = time.perf_counter()
   for i in range(args.steps):
     step_dev(i)
+  host_ms = (time.perf_counter() - th0) * 1e3 / args.steps   # host time to enqueue one step (must stay below the device time)
   e1.record()
   ctx.sync()
   ms = e0.elapsed_ms(e1)
@@ -244,8 +253,8 @@ def main():
   from shallow_ntc_b200 import DecodePipeline
 
   def run_e2e(q_dtype):
-    pin = [(ctx.pinned_like(z), ctx.pinned_like(q.astype(q_dtype))) for z, q in sets[:2]]
-    outs = [dict(image=ctx.pinned_empty((B, H, W, 3), np.uint8), idx=ctx.pinned_empty(ys, np.uint8)) for _ in range(2)]
+    pin = [(ctx.pinned_like(z) if hyper else None, ctx.pinned_like(q.astype(q_dtype))) for z, q in sets[:2]]
+    outs = [dict(image=ctx.pinned_empty((B, H, W, 3), np.uint8), idx=ctx.pinned_empty(ys, np.uint8) if hyper else None) for _ in range(2)]
     pipe = DecodePipeline(model, B, (H, W), q_dtype=q_dtype, depth=2)
     for i in range(3):
       pipe.submit(pin[i % 2][0], pin[i % 2][1], outs[i % 2]["image"], outs[i % 2]["idx"])
@@ -257,7 +266,8 @@ def main():
       pipe.submit(pin[i % 2][0], pin[i % 2][1], outs[i % 2]["image"], outs[i % 2]["idx"])
     f1.record(pipe.s_out.handle)
     pipe.drain()
-    return f0.elapsed_ms(f1), int(pin[0][0].nbytes + pin[0][1].nbytes), int(outs[0]["image"].nbytes + outs[0]["idx"].nbytes), outs
+    return (f0.elapsed_ms(f1), int((pin[0][0].nbytes if hyper else 0) + pin[0][1].nbytes),
+            int(outs[0]["image"].nbytes + (outs[0]["idx"].nbytes if hyper else 0)), outs)
 
   ms_e2e, h2d, d2h, out_hosts = run_e2e(np.float32)
   ms_e2e_i8, h2d_i8, _, _ = run_e2e(np.int8)
@@ -265,16 +275,18 @@ def main():
 
   # final quality sum over ranks (the only collective; NCCL all-reduce of 3 doubles)
   orig = synthetic.make_original(out_host["image"][:2], first_index=rank * B)
-  met = model.decompress(sets[(args.steps - 1) % 2][0][:2], sets[(args.steps - 1) % 2][1][:2], (H, W), original=orig, return_bits=True)
+  zq = sets[(args.steps - 1) % 2]
+  met = model.decompress(zq[0][:2] if hyper else None, zq[1][:2], (H, W), original=orig, return_bits=hyper)
   # [sum psnr, sum mse, sum bits_y, sum bits_z, n_images]: the reference averages per-image metrics (mshyper/models.py:300-317)
-  qsum = np.array([met["psnr"].sum(), met["mse"].sum(), met["bits_y"].sum(), met["bits_z"].sum(), float(len(met["psnr"]))])
+  qsum = np.array([met["psnr"].sum(), met["mse"].sum(), met["bits_y"].sum() if hyper else 0.0, met["bits_z"].sum() if hyper else 0.0,
+                   float(len(met["psnr"]))])
   # cost of asking for the rate term as well (bits_y in the hyper-head epilogue + bits_z kernel), device-resident
   n_rd = max(3, args.steps // 8)
   g0, g1 = ctx.event(), ctx.event()
   g0.record()
   for i in range(n_rd):
     dz, dq = dev[i % args.rotate]
-    model.decompress(dz, dq, (H, W), out=out_dev, return_bits=True, sync=False)
+    model.decompress(dz, dq, (H, W), out=out_dev, return_bits=hyper, sync=False)
   g1.record()
   ctx.sync()
   ms_rd = g0.elapsed_ms(g1) / n_rd
@@ -284,27 +296,32 @@ def main():
     qsum = parallel.reduce_metric_sums(dist, qsum, device=f"cuda:{local}")     # NCCL: the only collective
 
   if rank == 0:
+    headline = args.config == "two_layer_syn" and (H, W) == (512, 768)
+    workload = (f"mshyper two_layer_syn decode (BASELINE configs[1]): {B} x 768x512 per GPU, random-init 'stress' weights" if headline else
+                f"{args.config} decode (side run, not the headline workload): {B} x {W}x{H} per GPU, random-init 'stress' weights")
     px_step = world * B * H * W
     value = px_step * args.steps / (ms * 1e-3) / 1e6
     e2e = px_step * args.steps / (ms_e2e * 1e-3) / 1e6
     # dominant kernel = the layer with the largest share of device time
     dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
     roof = None
+    # algorithmic HBM bytes per step: symbols in (f32) + image and index map out
+    alg_bytes = sets[0][1].nbytes + (sets[0][0].nbytes if hyper else 0) + B * H * W * 3 + (int(np.prod(ys)) if hyper else 0)
     if dom[0] is not None and dom[1]["macs"] > 0:
       per_launch_ms = dom[1]["ms"] / dom[1]["n"]
       ach = 2.0 * dom[1]["macs"] / (per_launch_ms * 1e-3) / 1e12
       roof = dict(bound="tensor", kernel=dom[0], achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"],
-                  traffic=ncu_traffic(dom[0], B), peak_source=peaks["source"] + " bf16 dense sustained", share_of_step=dom[1]["ms"] / ms,
+                  traffic=ncu_traffic(dom[0], B), peak_source=peaks["source"] + " bf16 dense sustained", share_of_step=per_launch_ms / (ms / args.steps),
                   ms_per_launch=per_launch_ms, algorithmic_flops_per_launch=2.0 * dom[1]["macs"],
-                  hbm_view=dict(algorithmic_gbs=world * B * 3760128 * args.steps / (ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"]))
+                  hbm_view=dict(algorithmic_gbs=world * alg_bytes * args.steps / (ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"]))
     line = dict(metric="decoded Mpx/s", value=value, unit="Mpx/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32" if precision == "fp32" else "f16x3-split/f32-accum", data="synthetic",
-                config=dict(workload=f"mshyper {args.config} decode (BASELINE configs[1]): {B} x 768x512 per GPU, random-init 'stress' weights",
+                config=dict(workload=workload,
                             images_per_gpu=B, precision=precision, l2="inputs rotate over %d distinct batches; per-step working set > 126 MB L2" % args.rotate,
                             layers_ms={k: round(v["ms"] / max(v["n"], 1), 4) for k, v in prof.items()},
                             mean_psnr_db=float(qsum[0] / qsum[4]), mean_bpp_synthetic=float((qsum[2] + qsum[3]) / qsum[4] / (H * W)),
-                            ms_per_step_with_rate_term=ms_rd),
+                            ms_per_step_with_rate_term=ms_rd, host_enqueue_ms_per_step=round(host_ms, 4)),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=e2e, unit="Mpx/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
                          api="DecodePipeline.submit (float32 symbols, pinned host buffers, depth 2)",

@@ -876,7 +876,7 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         if (fin) { to.f32 = fin->full; to.u8 = fin->u8; to.crop = fin->crop; to.H = fin->H; to.W = fin->W; }
         std::string err;
         ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
-        if (tail_mma_run(c, m->tail_mma[op.conv], cur.f32, B, ch, cw, to, tc_pdl(), s, &ctx->launches, &err) != 0)
+        if (tail_mma_run(ctx->tc, c, m->tail_mma[op.conv], cur.f32, B, ch, cw, to, tc_pdl(), s, &ctx->launches, &err) != 0)
           return fail(SNTC_E_CUDA, "warp-MMA tail: " + err);
         ch *= c.s; cw *= c.s; cc = c.cout;
         cur = Cur{};

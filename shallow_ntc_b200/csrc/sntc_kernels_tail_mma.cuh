@@ -22,6 +22,7 @@
 #include <vector>
 #include "sntc_plan.hpp"
 #include "sntc_kernels_f32.cuh"
+#include "sntc_kernels_tc.cuh"
 
 namespace sntc {
 
@@ -71,13 +72,28 @@ __device__ __forceinline__ uint32_t tm_pixel(float x) {
 }
 
 // FAST: the only destination is the uint8 image and W is even (every thread's two bytes are one aligned 16-bit store)
+//
+// Persistent CTAs (3 per SM) loop over the tiles.  The fp32 halo tile of t arrives by ONE TMA tiled load per tile
+// (4-D map (c, x, y, b), box (C1, 66, 10, 1); out-of-image coordinates are zero-filled = the conv padding) into a raw
+// staging buffer; the load of tile n+1 is issued as soon as tile n has been converted, so it overlaps the MMA phase.
 template <int C1, bool FAST>
-__global__ void __launch_bounds__(TM_THREADS, 3) tail_s2_mma_kernel(const TailMmaParams Q) {
+__global__ void __launch_bounds__(TM_THREADS, 3) tail_s2_mma_kernel(const __grid_constant__ CUtensorMap mapT, const TailMmaParams Q) {
   static_assert(C1 % 4 == 0 && C1 <= 16, "one K=16 step per tap");
-  constexpr int PLANE = 2 * TM_TYH * TM_TXH;                      // uint4 units per plane: [octet][row][x]
-  __shared__ __align__(16) uint4 st[2 * PLANE];                   // [plane hi/lo][octet][row][x] x 8 fp16
-  const int b = blockIdx.z, ty0 = blockIdx.y * TM_RW, tx0 = blockIdx.x * TM_TX;
+  constexpr int NPX = TM_TYH * TM_TXH;
+  constexpr int PLANE = 2 * NPX;                                  // uint4 units per plane: [octet][row][x]
+  constexpr uint32_t RAW_BYTES = (uint32_t)NPX * C1 * 4;
+  extern __shared__ uint8_t tm_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tm_smem_raw) + 127) & ~(uintptr_t)127);
+  const float4* raw = reinterpret_cast<const float4*>(smem);                            // [row][x][C1] fp32, written by TMA
+  uint4* st = reinterpret_cast<uint4*>(smem + ((RAW_BYTES + 127u) & ~127u));            // [plane hi/lo][octet][row][x] x 8 fp16
+  uint64_t* bar = reinterpret_cast<uint64_t*>(st + 2 * PLANE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = (Q.win + TM_TX - 1) / TM_TX, tiles_y = (Q.hin + TM_RW - 1) / TM_RW;
+  const int ntiles = tiles_x * tiles_y * Q.B;
+  auto tile_origin = [&](int t, int& b, int& ty0, int& tx0) {
+    const int txi = t % tiles_x, r = t / tiles_x;
+    tx0 = txi * TM_TX; ty0 = (r % tiles_y) * TM_RW; b = r / tiles_y;
+  };
 
   // weight fragments -> registers (does not depend on the previous kernel)
   uint32_t wf[TM_NFRAG][2][2];
@@ -88,137 +104,157 @@ __global__ void __launch_bounds__(TM_THREADS, 3) tail_s2_mma_kernel(const TailMm
       const uint2 v = __ldg(Q.wfrag + (f * 2 + p) * 32 + lane);
       wf[f][p][0] = v.x; wf[f][p][1] = v.y;
     }
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent of layer 1
-
-  // ---- stage the halo tile: rows ty0-1 .. ty0+RW, columns tx0-1 .. tx0+TX, channel quads 0..3 (zero beyond C1):
-  // per tile row 66 x 4 quads; thread t takes quads t, t+128 and (t < 8) t+256: dense, coalesced 16-byte loads ----
-  {
-    const float* img = Q.x + (size_t)b * Q.hin * Q.win * C1;
-    constexpr int ROWQ = TM_TXH * 4;
-    constexpr int NU = (ROWQ + TM_THREADS - 1) / TM_THREADS;
-    int off[NU], spos[NU];
-    bool ld[NU], stv[NU];
+  if (threadIdx.x == 0) {
+    tcx::prefetch_tmap(&mapT);
+    tcx::mbar_init(bar, 1);
+    tcx::fence_barrier_init();
+  }
+  if (C1 < 16) {   // channels C1..15 of every pixel are constant zeros: written once
+    for (int px = threadIdx.x; px < NPX; px += TM_THREADS)
 #pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      const int q = threadIdx.x + u * TM_THREADS, xx = q >> 2, c4 = q & 3, nx = tx0 - 1 + xx;
-      stv[u] = q < ROWQ;
-      ld[u] = stv[u] && c4 * 4 < C1 && nx >= 0 && nx < Q.win;
-      off[u] = nx * C1 + c4 * 4;
-      spos[u] = (((c4 >> 1) * TM_TYH) * TM_TXH + xx) * 2 + (c4 & 1);   // uint2 index inside a plane, tile row 0
-    }
-#pragma unroll 2
-    for (int yy = 0; yy < TM_TYH; ++yy) {
-      const int ny = ty0 - 1 + yy;
-      const bool rowok = ny >= 0 && ny < Q.hin;
-      const float* rowp = img + (size_t)(rowok ? ny : 0) * Q.win * C1;
-      float4 v[NU];
-#pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rowok && ld[u]) v[u] = __ldg(reinterpret_cast<const float4*>(rowp + off[u]));
+      for (int c4 = C1 / 4; c4 < 4; ++c4) {
+        const int pos = ((c4 >> 1) * NPX + px) * 2 + (c4 & 1);
+        reinterpret_cast<uint2*>(st)[pos] = make_uint2(0u, 0u);
+        reinterpret_cast<uint2*>(st + PLANE)[pos] = make_uint2(0u, 0u);
       }
-#pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        if (!stv[u]) continue;
-        uint2 hi, lo;
-        tm_split4(v[u], hi, lo);
-        reinterpret_cast<uint2*>(st)[spos[u] + yy * (TM_TXH * 2)] = hi;
-        reinterpret_cast<uint2*>(st + PLANE)[spos[u] + yy * (TM_TXH * 2)] = lo;
-      }
-    }
   }
   __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent of layer 1
+  int tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < ntiles) {
+    int b, ty0, tx0;
+    tile_origin(tile, b, ty0, tx0);
+    tcx::mbar_expect_tx(bar, RAW_BYTES);
+    tcx::tma_load_4d(smem, &mapT, bar, 0, tx0 - 1, ty0 - 1, b);
+  }
 
-  // ---- MMA phase ----
   const int xs = warp * 16;                                       // this warp's strip inside the tile
   // ldmatrix.x4: lanes 0-7 -> rows 0-7 / k 0-7, 8-15 -> rows 8-15 / k 0-7, 16-23 -> rows 0-7 / k 8-15, 24-31 -> rows 8-15 / k 8-15
   const int lrow = lane & 15, loct = lane >> 4;
   const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(st + (loct * TM_TYH) * TM_TXH + xs + lrow);
   constexpr uint32_t PLANE_B = PLANE * 16, ROW_B = TM_TXH * 16;
-  uint32_t A[3][3][2][4];                                         // [row slot][jx + 1][hi/lo][regs]
-  auto load_row = [&](uint32_t (*dst)[2][4], int yy) {
-#pragma unroll
-    for (int jx = 0; jx < 3; ++jx)
-#pragma unroll
-      for (int p = 0; p < 2; ++p) tm_ldmatrix_x4(dst[jx][p], a_base + p * PLANE_B + yy * ROW_B + jx * 16);
-  };
-  load_row(A[0], 0);
-  load_row(A[1], 1);
   const int g = lane >> 2, q = lane & 3;
   // this thread's accumulator columns n = 2q, 2q+1 = bytes 2q, 2q+1 of the 6 bytes of output pixels (2x, 2x+1); q = 3 is padding
   const float bias0 = q == 1 ? Q.bias[2] : (q == 2 ? Q.bias[1] : Q.bias[0]);
   const float bias1 = q == 1 ? Q.bias[0] : (q == 2 ? Q.bias[2] : Q.bias[1]);
-  const int x_lo = tx0 + xs + g;                                  // t-pixel of c0/c1; c2/c3: x_lo + 8
   const int rowb = Q.W * 3;
-  uint8_t* u8p = Q.out_u8 ? Q.out_u8 + ((size_t)b * Q.H + 2 * ty0) * rowb + 6 * x_lo + 2 * q : nullptr;
-  bool okx[2];
+  uint32_t phase = 0;
+
+  for (; tile < ntiles; tile += gridDim.x) {
+    int b, ty0, tx0;
+    tile_origin(tile, b, ty0, tx0);
+    // ---- raw fp32 tile -> fp16 hi/lo planes ----
+    tcx::mbar_wait(bar, phase);
+    phase ^= 1u;
+    constexpr int NQ = NPX * (C1 / 4);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < NQ; i += TM_THREADS) {
+      const int px = i / (C1 / 4), c4 = i - px * (C1 / 4);
+      uint2 hi, lo;
+      tm_split4(raw[i], hi, lo);
+      const int pos = ((c4 >> 1) * NPX + px) * 2 + (c4 & 1);
+      reinterpret_cast<uint2*>(st)[pos] = hi;
+      reinterpret_cast<uint2*>(st + PLANE)[pos] = lo;
+    }
+    __syncthreads();                                              // planes complete; raw buffer free
+    if (threadIdx.x == 0 && tile + (int)gridDim.x < ntiles) {
+      int nb, nty0, ntx0;
+      tile_origin(tile + gridDim.x, nb, nty0, ntx0);
+      tcx::fence_proxy_async();                                   // generic reads of `raw` are ordered before the async-proxy overwrite
+      tcx::mbar_expect_tx(bar, RAW_BYTES);
+      tcx::tma_load_4d(smem, &mapT, bar, 0, ntx0 - 1, nty0 - 1, nb);
+    }
+
+    // ---- MMA phase ----
+    uint32_t A[3][3][2][4];                                       // [row slot][jx + 1][hi/lo][regs]
+    auto load_row = [&](uint32_t (*dst)[2][4], int yy) {
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) okx[hh] = q < 3 && x_lo + 8 * hh < Q.win && 2 * (x_lo + 8 * hh) < Q.W;
+      for (int jx = 0; jx < 3; ++jx)
 #pragma unroll
-  for (int i = 0; i < TM_RW; ++i) {
-    load_row(A[(i + 2) % 3], i + 2);
-    float acc[2][2][4];
+        for (int p = 0; p < 2; ++p) tm_ldmatrix_x4(dst[jx][p], a_base + p * PLANE_B + yy * ROW_B + jx * 16);
+    };
+    load_row(A[0], 0);
+    load_row(A[1], 1);
+    const int x_lo = tx0 + xs + g;                                // t-pixel of c0/c1; c2/c3: x_lo + 8
+    uint8_t* u8p = Q.out_u8 ? Q.out_u8 + ((size_t)b * Q.H + 2 * ty0) * rowb + 6 * x_lo + 2 * q : nullptr;
+    bool okx[2];
 #pragma unroll
-    for (int f = 0; f < TM_NFRAG; ++f) {
-      const int nt = f < 6 ? 0 : 1;
-      const int d = nt == 0 ? f / 3 : (f - 6) / 3;               // dy + 1
-      const int jx = f % 3;
-      const uint32_t (*a)[4] = A[(i + d) % 3][jx];
-      if (f == 0 || f == 6) {
-        tm_mma16816_first(acc[nt][0], a[0], wf[f][0]);            // hi * hi
-        tm_mma16816_first(acc[nt][1], a[1], wf[f][0]);            // lo * hi
+    for (int hh = 0; hh < 2; ++hh) okx[hh] = q < 3 && x_lo + 8 * hh < Q.win && 2 * (x_lo + 8 * hh) < Q.W;
+#pragma unroll
+    for (int i = 0; i < TM_RW; ++i) {
+      load_row(A[(i + 2) % 3], i + 2);
+      float acc[2][2][4];                                         // [parity][hi*hi | cross terms][regs]
+      {
+        float acx[2][4];                                          // hi * lo: its own dependency chain (6 chains per warp in flight)
+#pragma unroll
+        for (int f = 0; f < TM_NFRAG; ++f) {
+          const int nt = f < 6 ? 0 : 1;
+          const int d = nt == 0 ? f / 3 : (f - 6) / 3;           // dy + 1
+          const int jx = f % 3;
+          const uint32_t (*a)[4] = A[(i + d) % 3][jx];
+          if (f == 0 || f == 6) {
+            tm_mma16816_first(acc[nt][0], a[0], wf[f][0]);        // hi * hi
+            tm_mma16816_first(acc[nt][1], a[1], wf[f][0]);        // lo * hi
+            tm_mma16816_first(acx[nt], a[0], wf[f][1]);           // hi * lo
+          } else {
+            tm_mma16816(acc[nt][0], a[0], wf[f][0]);
+            tm_mma16816(acc[nt][1], a[1], wf[f][0]);
+            tm_mma16816(acx[nt], a[0], wf[f][1]);
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[nt][1][e] += acx[nt][e];
+      }
+      const int ty = ty0 + i;
+      if (ty >= Q.hin) continue;
+      if (FAST) {
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          if (2 * ty + nt >= Q.H) continue;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (!okx[hh]) continue;
+            const float v0 = fmaf(acc[nt][0][2 * hh] + acc[nt][1][2 * hh], Q.inv_scale, bias0);
+            const float v1 = fmaf(acc[nt][0][2 * hh + 1] + acc[nt][1][2 * hh + 1], Q.inv_scale, bias1);
+            *reinterpret_cast<uint16_t*>(u8p + (2 * i + nt) * rowb + 48 * hh) = (uint16_t)(tm_pixel(v0) | (tm_pixel(v1) << 8));
+          }
+        }
       } else {
-        tm_mma16816(acc[nt][0], a[0], wf[f][0]);
-        tm_mma16816(acc[nt][1], a[1], wf[f][0]);
-      }
-      tm_mma16816(acc[nt][1], a[0], wf[f][1]);                    // hi * lo
-    }
-    const int ty = ty0 + i;
-    if (ty >= Q.hin) continue;
-    if (FAST) {
+        if (q == 3) continue;
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        if (2 * ty + nt >= Q.H) continue;
+        for (int nt = 0; nt < 2; ++nt) {
+          const int oy = 2 * ty + nt;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          if (!okx[hh]) continue;
-          const float v0 = fmaf(acc[nt][0][2 * hh] + acc[nt][1][2 * hh], Q.inv_scale, bias0);
-          const float v1 = fmaf(acc[nt][0][2 * hh + 1] + acc[nt][1][2 * hh + 1], Q.inv_scale, bias1);
-          *reinterpret_cast<uint16_t*>(u8p + (2 * i + nt) * rowb + 48 * hh) = (uint16_t)(tm_pixel(v0) | (tm_pixel(v1) << 8));
-        }
-      }
-    } else {
-      if (q == 3) continue;
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int oy = 2 * ty + nt;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int x = x_lo + 8 * hh;
-          if (x >= Q.win) continue;
-          const float v0 = fmaf(acc[nt][0][2 * hh] + acc[nt][1][2 * hh], Q.inv_scale, bias0);
-          const float v1 = fmaf(acc[nt][0][2 * hh + 1] + acc[nt][1][2 * hh + 1], Q.inv_scale, bias1);
-          const int n0 = 2 * q;
-          const int ox0 = 2 * x + n0 / 3, ox1 = 2 * x + (n0 + 1) / 3;
-          if (Q.out) {
-            float* o = Q.out + (((size_t)b * Q.hout + oy) * Q.wout + 2 * x) * 3 + n0;
-            o[0] = v0; o[1] = v1;
-          }
-          if (oy < Q.H) {
-            if (Q.out_u8) {
-              uint8_t* o = Q.out_u8 + (((size_t)b * Q.H + oy) * Q.W + 2 * x) * 3 + n0;
-              if (ox0 < Q.W) o[0] = (uint8_t)tm_pixel(v0);
-              if (ox1 < Q.W) o[1] = (uint8_t)tm_pixel(v1);
+          for (int hh = 0; hh < 2; ++hh) {
+            const int x = x_lo + 8 * hh;
+            if (x >= Q.win) continue;
+            const float v0 = fmaf(acc[nt][0][2 * hh] + acc[nt][1][2 * hh], Q.inv_scale, bias0);
+            const float v1 = fmaf(acc[nt][0][2 * hh + 1] + acc[nt][1][2 * hh + 1], Q.inv_scale, bias1);
+            const int n0 = 2 * q;
+            const int ox0 = 2 * x + n0 / 3, ox1 = 2 * x + (n0 + 1) / 3;
+            if (Q.out) {
+              float* o = Q.out + (((size_t)b * Q.hout + oy) * Q.wout + 2 * x) * 3 + n0;
+              o[0] = v0; o[1] = v1;
             }
-            if (Q.out_crop) {
-              float* o = Q.out_crop + (((size_t)b * Q.H + oy) * Q.W + 2 * x) * 3 + n0;
-              if (ox0 < Q.W) o[0] = v0;
-              if (ox1 < Q.W) o[1] = v1;
+            if (oy < Q.H) {
+              if (Q.out_u8) {
+                uint8_t* o = Q.out_u8 + (((size_t)b * Q.H + oy) * Q.W + 2 * x) * 3 + n0;
+                if (ox0 < Q.W) o[0] = (uint8_t)tm_pixel(v0);
+                if (ox1 < Q.W) o[1] = (uint8_t)tm_pixel(v1);
+              }
+              if (Q.out_crop) {
+                float* o = Q.out_crop + (((size_t)b * Q.H + oy) * Q.W + 2 * x) * 3 + n0;
+                if (ox0 < Q.W) o[0] = v0;
+                if (ox1 < Q.W) o[1] = v1;
+              }
             }
           }
         }
       }
     }
+    __syncthreads();                                              // every warp is done with the planes before the next conversion
   }
 }
 
@@ -229,6 +265,8 @@ struct TailMma {
   float scale = 1.f;
   uint2* d_wfrag = nullptr;
   float bias[3] = {0.f, 0.f, 0.f};
+  bool attr_set = false;
+  int ctas_per_sm = 0;            // resident CTAs per SM of the variant in use (occupancy query), sizes the persistent grid
 };
 
 inline bool tail_mma_supported(const ConvLayer& c) {
@@ -278,23 +316,56 @@ inline bool tail_mma_pack(const ConvLayer& c, const HostWeights& hw, TailMma& t,
 
 struct TailMmaOut { float* f32 = nullptr; uint8_t* u8 = nullptr; float* crop = nullptr; int H = 0, W = 0; };
 
-inline int tail_mma_run(const ConvLayer& c, const TailMma& t, const float* in, int B, int h, int w, const TailMmaOut& o, bool pdl,
+inline size_t tail_mma_smem(int C1) {
+  const size_t raw = ((size_t)TM_TYH * TM_TXH * C1 * 4 + 127) / 128 * 128;
+  return 128 + raw + (size_t)2 * 2 * TM_TYH * TM_TXH * 16 + 16;
+}
+
+inline int tail_mma_run(TcDriver& drv, const ConvLayer& c, TailMma& t, const float* in, int B, int h, int w, const TailMmaOut& o, bool pdl,
                         cudaStream_t s, uint64_t* launches, std::string* err) {
+  if (!drv.encode) { *err = "cuTensorMapEncodeTiled unavailable"; return 2; }
   TailMmaParams Q{};
   Q.x = in; Q.B = B; Q.hin = h; Q.win = w; Q.wfrag = t.d_wfrag; Q.inv_scale = 1.f / t.scale;
   for (int i = 0; i < 3; ++i) Q.bias[i] = t.bias[i];
   Q.out = o.f32; Q.hout = 2 * h; Q.wout = 2 * w; Q.out_u8 = o.u8; Q.out_crop = o.crop; Q.H = o.H; Q.W = o.W;
+  // t [B,h,w,C1] fp32 as a 4-D tensor (c, x, y, b); box = one halo tile
+  CUtensorMap mapT;
+  {
+    const int C1 = c.cin;
+    cuuint64_t dims[4] = {(cuuint64_t)C1, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C1 * 4, (cuuint64_t)w * C1 * 4, (cuuint64_t)h * w * C1 * 4};
+    cuuint32_t box[4] = {(cuuint32_t)C1, (cuuint32_t)TM_TXH, (cuuint32_t)TM_TYH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = drv.encode(&mapT, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled(tail) failed: " + std::to_string((int)r); return 2; }
+  }
+  const size_t smem = tail_mma_smem(c.cin);
+  if (!t.attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tail_s2_mma_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_mma_smem(12));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_s2_mma_kernel<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_mma_smem(12));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_s2_mma_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_mma_smem(16));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_s2_mma_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_mma_smem(16));
+    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute (tail): ") + cudaGetErrorString(e); return 2; }
+    t.attr_set = true;
+    int n = 0;
+    e = c.cin == 12 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tail_s2_mma_kernel<12, true>, TM_THREADS, smem)
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tail_s2_mma_kernel<16, true>, TM_THREADS, smem);
+    t.ctas_per_sm = (e == cudaSuccess && n > 0) ? n : 1;
+  }
+  const int ntiles = ((w + TM_TX - 1) / TM_TX) * ((h + TM_RW - 1) / TM_RW) * B;
+  if (ntiles <= 0) return 0;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)((w + TM_TX - 1) / TM_TX), (unsigned)((h + TM_RW - 1) / TM_RW), (unsigned)B);
-  cfg.blockDim = dim3(TM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cfg.gridDim = dim3((unsigned)std::min(ntiles, t.ctas_per_sm * drv.num_sms));
+  cfg.blockDim = dim3(TM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
   const bool fast = o.u8 && !o.f32 && !o.crop && (o.W % 2) == 0;
   cudaError_t e;
-  if (c.cin == 12) e = fast ? cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<12, true>, Q) : cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<12, false>, Q);
-  else e = fast ? cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<16, true>, Q) : cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<16, false>, Q);
+  if (c.cin == 12) e = fast ? cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<12, true>, mapT, Q) : cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<12, false>, mapT, Q);
+  else e = fast ? cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<16, true>, mapT, Q) : cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<16, false>, mapT, Q);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("tail_s2_mma_kernel launch: ") + cudaGetErrorString(e); return 2; }
   if (launches) (*launches)++;
