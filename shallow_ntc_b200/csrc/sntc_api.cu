@@ -243,7 +243,7 @@ extern "C" int sntc_event_elapsed_ms(sntc_ctx* ctx, void* start, void* stop, flo
 
 // ------------------------------------------------------------------------------------------------
 // model
-static void mark_final_op(Transform& t) {
+static void mark_final_op(Transform& t, int precision) {
   // The last conv of a synthesis transform with <= 3 output channels and only tiny bands runs on the
   // cell kernel (all phases per thread); otherwise it stays a band GEMM with the pixel epilogue.
   if (t.ops.empty()) return;
@@ -252,7 +252,12 @@ static void mark_final_op(Transform& t) {
   ConvLayer& c = t.convs[last.conv];
   int maxN = 0;
   for (auto& b : c.bands) maxN = std::max(maxN, b.N);
-  if (c.cout <= 3 && maxN < 64 && (c.s == 1 || c.s == 2 || c.s == 4)) last.type = OP_CONVT_RGB;
+  if (c.cout <= 3 && maxN < 64 && (c.s == 1 || c.s == 2 || c.s == 4)) {
+    // tensor-core precision and a TMA-addressable input (deep decoders: 192 / 256 channels): all s*s output residues of a
+    // cell become ONE band (N = s*s*cout) of the tcgen05 band GEMM; SNTC_TC_FINAL=0 keeps the CUDA-core cell kernel
+    if (precision == SNTC_PRECISION_TC_F16X3 && tc_conv_supported(c) && c.s > 1 && tc_env_int("SNTC_TC_FINAL", 1)) finish_conv_merged(c);
+    else last.type = OP_CONVT_RGB;
+  }
 }
 
 extern "C" int sntc_model_create(sntc_ctx* ctx, const sntc_model_desc* desc, sntc_model** out) {
@@ -287,7 +292,7 @@ extern "C" int sntc_model_create(sntc_ctx* ctx, const sntc_model_desc* desc, snt
     return fail(SNTC_E_INVALID, "sntc_model_create: hyper-synthesis must output 2*Cy channels (mu || sigma)");
   if (m->has_syn && m->syn.in_channels % 4 != 0) return fail(SNTC_E_UNSUPPORTED, "sntc_model_create: latent channels must be a multiple of 4");
   if (m->has_syn && m->syn.out_channels > 3) return fail(SNTC_E_UNSUPPORTED, "sntc_model_create: more than 3 image channels");
-  if (m->has_syn) mark_final_op(m->syn);
+  if (m->has_syn) mark_final_op(m->syn, desc->precision);
   for (Transform* t : {&m->hyper, &m->syn})
     for (auto& c : t->convs)
       if (!c.append_ones && c.cin % 4 != 0)
@@ -379,8 +384,10 @@ extern "C" int sntc_model_finalize(sntc_model* m) {
         std::vector<float> b = pack_bias(c, m->hw);
         TRY(upload(m, b.data(), b.size() * 4, (void**)&c.d_bias));
         if (op.type == OP_CONVT) {
-          std::vector<float> w = pack_band_weights(c, m->hw);
-          TRY(upload(m, w.data(), w.size() * 4, (void**)&c.d_w));
+          if (!c.merged) {   // merged final layers exist on the tensor-core path only
+            std::vector<float> w = pack_band_weights(c, m->hw);
+            TRY(upload(m, w.data(), w.size() * 4, (void**)&c.d_w));
+          }
         } else {
           std::vector<float> w = pack_rgb_weights(c, m->hw);
           TRY(upload(m, w.data(), w.size() * 4, (void**)&c.d_w_rgb));
@@ -738,6 +745,12 @@ static bool op_on_tc(sntc_model* m, Transform& t, bool is_hyper, size_t i) {
   return op.conv < (int)tc.size() && tc[op.conv].ok;
 }
 
+static bool gdn_on_tc(sntc_model* m, Transform& t, bool is_hyper, size_t i) {
+  if (is_hyper || m->desc.precision != SNTC_PRECISION_TC_F16X3 || i >= t.ops.size()) return false;
+  const Op& op = t.ops[i];
+  return op.type == OP_GDN && op.gdn < (int)m->tc.syn_gdn.size() && m->tc.syn_gdn[op.gdn].ok;
+}
+
 // Runs `t` on `cur` [B,h,w,Cin].  Conv layers run on the tensor cores when the model was created with
 // SNTC_PRECISION_TC_F16X3 (and the layer is TMA-addressable), otherwise on the fp32 CUDA-core kernels;
 // pointwise stages and the tiny final conv always run on CUDA cores.  Intermediates ping-pong in the
@@ -844,6 +857,14 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
           __half *hi, *lo;
           next_planes(&hi, &lo);
           o.hi = hi; o.lo = lo; nxt.hi = hi; nxt.lo = lo;
+        } else if (gdn_on_tc(m, t, is_hyper, i + 1)) {
+          // a GDN stage on the tensor cores follows: x as fp32 (scaled by the norm there) + planes of the pooling input
+          const GdnLayer& g = t.gdns[t.ops[i + 1].gdn];
+          __half *hi, *lo;
+          next_planes(&hi, &lo);
+          float* dst = next_buf();
+          o.hi = hi; o.lo = lo; o.f32 = dst; o.plane_xform = g.kind == GDN_1 ? A_ABS : A_SQUARE;
+          nxt.hi = hi; nxt.lo = lo; nxt.f32 = dst;
         } else {
           float* dst = next_buf();
           o.f32 = dst; nxt.f32 = dst;
@@ -900,8 +921,31 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
       cur = Cur{}; cur.f32 = dst;
     } else if (op.type == OP_GDN) {
       if (!cur.f32) return fail(SNTC_E_STATE, "executor: GDN needs an fp32 input");
-      float* dst = next_buf();
       const GdnLayer& gl = t.gdns[op.gdn];
+      if (cur.hi && gdn_on_tc(m, t, is_hyper, i)) {
+        // ---- norm pool on the tensor cores: [pixels x C] (planes of |x| / x^2) * gamma, epilogue x * norm ----
+        TcGdn& tg = m->tc.syn_gdn[op.gdn];
+        TcConvOut o;
+        Cur nxt;
+        o.gx = cur.f32;
+        o.gdn_mode = gl.kind == GDN_1 ? (gl.inverse ? G_MUL : G_DIV) : (gl.inverse ? G_MUL_SQRT : G_DIV_SQRT);
+        if (!last && op_on_tc(m, t, is_hyper, i + 1)) {
+          __half *hi, *lo;
+          next_planes(&hi, &lo);
+          o.hi = hi; o.lo = lo; nxt.hi = hi; nxt.lo = lo;
+        } else {
+          float* dst = next_buf();
+          o.f32 = dst; nxt.f32 = dst;
+        }
+        std::string err;
+        ProfScope ps(m, s, gl.beta.substr(0, gl.beta.size() - 5), (double)B * ch * cw * gl.C * gl.C);
+        // a 1x1 "image" row of B*ch*cw pixels would overflow the TMA box arithmetic for large batches: keep [B,ch,cw]
+        if (tc_run_conv(ctx->tc, tg.conv, tg.tc, cur.hi, cur.lo, B, ch, cw, o, s, &ctx->launches, &err) != TC_OK)
+          return fail(SNTC_E_CUDA, "tensor-core GDN: " + err);
+        cur = nxt;
+        continue;
+      }
+      float* dst = next_buf();
       ProfScope ps(m, s, gl.beta.substr(0, gl.beta.size() - 5), (double)B * ch * cw * gl.C * gl.C);
       TRY(run_gdn_f32(ctx, gl, cur.f32, (size_t)B * ch * cw, dst, s));
       cur = Cur{}; cur.f32 = dst;

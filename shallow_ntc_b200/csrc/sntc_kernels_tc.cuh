@@ -24,6 +24,7 @@
 #include <string>
 #include <vector>
 #include "sntc_plan.hpp"
+#include "sntc_kernels_f32.cuh"
 #include "sntc_kernels_rate.cuh"
 
 namespace sntc {
@@ -45,7 +46,8 @@ struct alignas(64) TcBandDev {
   int phy0, nphx, phx0, Ty, Tx, mloy, mlox;
   int N, BN, ntiles;
   int item_begin;                 // first work item (m-tile, n-tile) of this band in the layer's item list
-  int pad_[5];
+  int oshift;                     // added to the output coordinate (merged bands: s*dlo + p, see ConvLayer::merged)
+  int pad_[4];
 };
 
 struct TcParams {
@@ -71,6 +73,10 @@ struct TcParams {
   // TC_EPI_TWO_LAYER: columns of one output pixel = base[0,C1) (|| res[C1,2C1)); out_f32 = t [B,hout,wout,C1]
   int C1, has_res, tl_act, tl_inverse; const float* gamma; int gamma_stride; const float* beta;
   double* rate_slots; int* rate_slot_img; RateConst rc;   // TC_EPI_HYPER_FINAL: per-(item, CTA, epilogue warp) partial bits_y
+  // TC_EPI_PLAIN extras for the GDN stages of the deep decoders (transforms.py:8-63, tfc.GDN):
+  //   plane_xform: the fp16 planes receive f(x) (A_ABS / A_SQUARE = the GDN pooling input) while out_f32 receives x;
+  //   gdn_mode: this GEMM *is* the GDN norm pool (1x1, gamma): out = gx * norm | gx / norm, norm = acc + beta (or its sqrt)
+  int plane_xform, gdn_mode; const float* gx;
   int vec16;          // fast epilogue: cout % 16 == 0, Cy % 16 == 0 and every epilogue tensor 32-byte aligned
   long long* trace;   // debug timeline (SNTC_TC_TRACE=1): [unit][TC_TRACE_ITEMS][8] clock64 stamps, leader CTA only
 };
@@ -424,14 +430,34 @@ __device__ __forceinline__ float tc_epi_vec16(const TcParams& P, const float* sb
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], P.act);
-  if (P.out_hi) store16_planes(P.out_hi, P.out_lo, pix * P.cout + co, v);
+  if (P.gdn_mode != G_NONE) {   // v = beta + f(x) gamma: scale the layer input x by the norm
+    float x[16];
+    tcx::ldg256_nc(P.gx + pix * P.cout + co, reinterpret_cast<uint32_t*>(x));
+    tcx::ldg256_nc(P.gx + pix * P.cout + co + 8, reinterpret_cast<uint32_t*>(x) + 8);
+    const bool root = P.gdn_mode == G_MUL_SQRT || P.gdn_mode == G_DIV_SQRT, mul = P.gdn_mode == G_MUL || P.gdn_mode == G_MUL_SQRT;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float nrm = root ? sqrtf(fmaxf(v[i], 0.f)) : v[i];
+      v[i] = mul ? x[i] * nrm : x[i] / nrm;
+    }
+  }
   if (P.out_f32) store16_f32(P.out_f32 + pix * P.cout + co, v);
+  if (P.out_hi) {
+    if (P.plane_xform == A_ABS) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fabsf(v[i]);
+    } else if (P.plane_xform == A_SQUARE) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = v[i] * v[i];
+    }
+    store16_planes(P.out_hi, P.out_lo, pix * P.cout + co, v);
+  }
   return 0.f;
 }
 
 // The band fields the epilogue needs, copied to registers once per work item: the band table lives in global
 // memory and the epilogue's own stores would otherwise force a reload (possible aliasing) per column group.
-struct TcBandRegs { int N, nphx, phy0, phx0; };
+struct TcBandRegs { int N, nphx, phy0, phx0, oshift; };
 
 // generic scalar epilogue (final layers with cout = 3, ...)
 __device__ __forceinline__ void tc_epi_scalar8(const TcParams& P, const TcBandRegs& bd, const float* sbias, int b, int my, int mx, int n, const float* v) {
@@ -440,7 +466,7 @@ __device__ __forceinline__ void tc_epi_scalar8(const TcParams& P, const TcBandRe
     const int nn = n + i;
     if (nn >= bd.N) break;
     const int co = nn % P.cout, ph = nn / P.cout;
-    const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
+    const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p + bd.oshift, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p + bd.oshift;
     if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) continue;
     float x = apply_act(fmaf(v[i], P.inv_scale, sbias[co]), P.act);
     const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
@@ -519,7 +545,7 @@ __device__ __forceinline__ void tc_epi_two_layer(const TcParams& P, const TcBand
     tcx::tmem_ld_wait();
     if (!cell_ok) continue;
     const int ph = (it.n0 + pp * PW) / PW;
-    const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
+    const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p + bd.oshift, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p + bd.oshift;
     if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) continue;
     const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
     constexpr int CP = (C1 + 15) / 16 * 16;
@@ -692,7 +718,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     for (int item = unit0; item < P.total_items; item += nunits, ++j) {
       const TcItem it = tc_decode_item<CG>(P, item, rank);
       const TcBandDev& bdg = P.bands[it.band];
-      const TcBandRegs bd{bdg.N, bdg.nphx, bdg.phy0, bdg.phx0};
+      const TcBandRegs bd{bdg.N, bdg.nphx, bdg.phy0, bdg.phx0, bdg.oshift};
       const int nk = bdg.Ty * bdg.Tx * P.kblocks;
       const uint32_t buf = j & 1u;
       const int iy = it.iy0 + r / P.TW, ix = it.ix0 + r % P.TW;
@@ -732,7 +758,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
               while (co >= P.cout) { co -= P.cout; ++ph; }
               if (ph != last_ph) {
                 last_ph = ph;
-                oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p; ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
+                oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p + bd.oshift; ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p + bd.oshift;
               }
               bits += tc_epi_vec16(P, sbias, it.b, oy, ox, co, raw + 16 * h);
             }
@@ -775,7 +801,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
               while (co >= P.cout) { co -= P.cout; ++ph; }
               if (ph != last_ph) {
                 last_ph = ph;
-                oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p; ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p;
+                oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p + bd.oshift; ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p + bd.oshift;
               }
               tc_epi_vec8(P, sbias, it.b, oy, ox, co, v);
             } else {
@@ -875,8 +901,16 @@ struct TailTc {
   bool attr_set = false;
 };
 
+// GDN norm pool of a deep decoder as a 1x1 band GEMM (gamma [in,out] as a [1,1,Cin,Cout] kernel, beta as the bias)
+struct TcGdn {
+  bool ok = false;
+  ConvLayer conv;
+  TcConv tc;
+};
+
 struct TcModelState {
   std::vector<TcConv> hyper, syn;     // parallel to Transform::convs
+  std::vector<TcGdn> syn_gdn;         // parallel to syn->gdns
   std::vector<TailTc> syn_tail;       // parallel to syn: tensor-core tail of a two-layer synthesis (sntc_kernels_tail_tc.cuh)
   TcDevBuf plane[4];                  // hi/lo ping-pong activation planes
   TcDevBuf yh[2];                     // hi/lo planes of y_hat (output of the fused hyper-synthesis head)
@@ -977,8 +1011,8 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
     for (int fy = 0; fy < b.nphy; ++fy) for (int fx = 0; fx < b.nphx; ++fx) for (int co = 0; co < c.cout; ++co) {
       size_t row = row0 + (size_t)(fy * b.nphx + fx) * c.cout + co;
       for (int jy = 0; jy < b.Ty; ++jy) for (int jx = 0; jx < b.Tx; ++jx) {
-        int ay = b.phy0 + fy + c.s * jy, ax = b.phx0 + fx + c.s * jx;
-        if (ay >= c.k || ax >= c.k) continue;
+        int ay = band_tap_index(c, b.phy0, fy, jy), ax = band_tap_index(c, b.phx0, fx, jx);
+        if (ay < 0 || ax < 0 || ay >= c.k || ax >= c.k) continue;
         size_t col0 = (size_t)(jy * b.Tx + jx) * t.ktot_pad;
         for (int ci = 0; ci < c.cin; ++ci) {
           float w = conv_w(c, hw, ay, ax, co, ci) * t.scale;
@@ -1008,6 +1042,7 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
     // band index -> (yi, xi) in row-major order of (by, bx)
     d.mloy = c.by[bi / c.bx.size()].mlo; d.mlox = c.bx[bi % c.bx.size()].mlo;
     d.N = b.N;
+    d.oshift = c.merged ? c.s * c.dlo + c.p : 0;
     if (b.N <= tc_bn_max()) d.BN = (b.N + base_unit - 1) / base_unit * base_unit;   // single tile: no pixel-alignment constraint
     else d.BN = tc_choose_bn(b.N, unit);
     d.ntiles = (b.N + d.BN - 1) / d.BN;
@@ -1055,6 +1090,27 @@ inline bool tc_finalize(TcDriver& drv, TcModelState& st, Transform* hyper, Trans
     return true;
   };
   if (!pack(hyper, st.hyper) || !pack(syn, st.syn)) return false;
+  if (syn && tc_env_int("SNTC_TC_GDN", 1)) {
+    // GDN stages between tensor-core layers (mbt2018 / bls2017 / cnn): norm pool on the tensor cores; SNTC_TC_GDN=0 keeps
+    // the FFMA band GEMM
+    st.syn_gdn.resize(syn->gdns.size());
+    for (size_t oi = 1; oi < syn->ops.size(); ++oi) {
+      const Op& op = syn->ops[oi];
+      if (op.type != OP_GDN || syn->ops[oi - 1].type != OP_CONVT) continue;
+      const int prev = syn->ops[oi - 1].conv;
+      if (prev >= (int)st.syn.size() || !st.syn[prev].ok) continue;
+      const GdnLayer& g = syn->gdns[op.gdn];
+      if (g.C < 64 || g.C % 16 != 0 || !g.d_beta) continue;
+      TcGdn& tg = st.syn_gdn[op.gdn];
+      ConvLayer& c = tg.conv;
+      c.k = 1; c.s = 1; c.p = 0; c.cin = g.C; c.cout = g.C; c.layout = LAYOUT_TFC_IO; c.has_bias = true; c.act = SNTC_ACT_NONE;
+      c.sources = {ConvSource{g.gamma, g.beta, g.C}};
+      finish_conv(c);
+      c.d_bias = g.d_beta;
+      if (!tc_pack_conv(drv, c, hw, tg.tc, 0, owned, err)) return false;
+      tg.ok = tg.tc.ok;
+    }
+  }
   if (syn && tc_env_int("SNTC_TC_TAIL", 0)) {
     // Tail of a two-layer synthesis on the tensor cores (sntc_kernels_tail_tc.cuh).  OFF by default: measured on B200 it
     // ties with the CUDA-core tail (0.17 vs 0.18 ms per 24-image step) because every M=128 x K=16 MMA costs ~95 clk of
@@ -1089,6 +1145,8 @@ struct TcConvOut {
   // two-layer fusion: f32 receives t = act(base) (+ res), [B,hout,wout,C1]
   bool two_layer = false; int C1 = 0; bool has_res = false; int tl_act = SNTC_ACT_NONE; bool tl_inverse = true;
   const float* gamma = nullptr; int gamma_stride = 0; const float* beta = nullptr;
+  // GDN stages (see TcParams): pooled planes out / norm-pool GEMM epilogue
+  int plane_xform = A_NONE; int gdn_mode = G_NONE; const float* gx = nullptr;
 };
 
 inline void tc_choose_patch(int h, int w, int* TH, int* TW) {
@@ -1145,14 +1203,18 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   P.C1 = o.C1; P.has_res = o.has_res ? 1 : 0; P.tl_act = o.tl_act; P.tl_inverse = o.tl_inverse ? 1 : 0;
   P.gamma = o.gamma; P.gamma_stride = o.gamma_stride; P.beta = o.beta;
   P.rate_slots = o.rate_slots; P.rate_slot_img = o.rate_slot_img; P.rc = o.rc;
+  P.plane_xform = o.plane_xform; P.gdn_mode = o.gdn_mode; P.gx = o.gx;
   {
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
     bool ok = c.cout % 16 == 0 && (!o.hyper_final || o.Cy % 16 == 0) && !o.two_layer && !o.u8 && !o.crop;
-    ok = ok && al(o.hi) && al(o.lo) && al(o.f32) && al(o.q) && al(o.y_hat) && al(o.idx);
+    ok = ok && al(o.hi) && al(o.lo) && al(o.f32) && al(o.q) && al(o.y_hat) && al(o.idx) && al(o.gx);
     // n-tiles must start on a 16-column boundary and the mma width is a multiple of 32 only when BN is: chunks are 32 wide,
     // the last one may be half-used
     for (auto& bd : t.bands) ok = ok && bd.BN % 16 == 0;
     P.vec16 = ok ? 1 : 0;
+  }
+  if ((o.plane_xform != A_NONE || o.gdn_mode != G_NONE) && !P.vec16) {
+    *err = "GDN stage on the tensor cores: needs C % 16 == 0 and 32-byte aligned tensors"; return TC_ERROR;
   }
   if (o.rate_slots && (!P.vec16 || (size_t)P.total_items * t.cg * TC_EPI_WARPS > o.rate_slot_cap)) {
     *err = "rate term: needs Cy % 16 == 0, 32-byte aligned tensors and a large enough slot buffer"; return TC_ERROR;

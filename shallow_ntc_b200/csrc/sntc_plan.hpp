@@ -69,6 +69,10 @@ struct ConvLayer {
   int layout = LAYOUT_KERAS_OI;
   bool has_bias = true;
   bool append_ones = false;  // JPEGLikeSynthesis(use_offset=True): input gets a constant-1 channel
+  // Merged form (final layers with tiny Cout on the tensor-core path): ONE band holds all s*s output residues
+  // r = o mod s of a cell (o = s*i + r), with a uniform tap window d = i - n in [dlo, dlo + T): a = r + p + s*d
+  // (taps outside [0,k) are zero weights).  N = s*s*cout instead of a handful of 3-column bands.
+  bool merged = false; int dlo = 0;
   int act = SNTC_ACT_NONE;   // only NONE / RELU / LEAKY_RELU are fused into the conv
   std::vector<ConvSource> sources;  // concatenated along Cout (base || res)
   std::vector<Band1D> by, bx;
@@ -131,6 +135,31 @@ inline void finish_conv(ConvLayer& c) {
     c.bands.push_back(b);
   }
   c.w_floats = off;
+}
+
+// Kernel index of (residue / phase f, tap j) of a band along one axis; < 0 or >= k means "no such tap" (zero weight).
+inline int band_tap_index(const ConvLayer& c, int phi0, int f, int j) {
+  return c.merged ? f + c.p + c.s * (c.dlo + j) : phi0 + f + c.s * j;
+}
+
+// Re-plans `c` in the merged form (see ConvLayer::merged).
+inline void finish_conv_merged(ConvLayer& c) {
+  c.cin_pad = ((c.cin + (c.append_ones ? 1 : 0)) + 3) / 4 * 4;
+  int dlo = 1 << 30, dhi = -(1 << 30);
+  for (int r = 0; r < c.s; ++r)
+    for (int d = -c.k; d <= c.k; ++d) {
+      const int a = r + c.p + c.s * d;
+      if (a >= 0 && a < c.k) { dlo = std::min(dlo, d); dhi = std::max(dhi, d); }
+    }
+  c.merged = true; c.dlo = dlo;
+  const int T = dhi - dlo + 1;
+  c.by = {Band1D{0, c.s, T, -dlo}};
+  c.bx = c.by;
+  Band b{};
+  b.phy0 = 0; b.nphy = c.s; b.Ty = T; b.phx0 = 0; b.nphx = c.s; b.Tx = T;
+  b.N = c.s * c.s * c.cout; b.Npad = (b.N + 3) / 4 * 4; b.K = T * T * c.cin_pad; b.w_off = 0;
+  c.bands = {b};
+  c.w_floats = (size_t)b.K * b.Npad;
 }
 
 inline ConvLayer make_conv(const std::string& prefix, const std::string& name, int k, int s, int cin, int cout,
