@@ -383,6 +383,7 @@ extern "C" int sntc_model_finalize(sntc_model* m) {
         ConvLayer& c = t->convs[op.conv];
         std::vector<float> b = pack_bias(c, m->hw);
         TRY(upload(m, b.data(), b.size() * 4, (void**)&c.d_bias));
+        c.h_bias = b;
         if (op.type == OP_CONVT) {
           if (!c.merged) {   // merged final layers exist on the tensor-core path only
             std::vector<float> w = pack_band_weights(c, m->hw);
@@ -406,6 +407,7 @@ extern "C" int sntc_model_finalize(sntc_model* m) {
         g.Npad = (g.C + 3) / 4 * 4;
         std::vector<float> gp((size_t)g.C * g.Npad, 0.f);
         for (int i = 0; i < g.C; ++i) for (int j = 0; j < g.C; ++j) gp[(size_t)i * g.Npad + j] = gamma[(size_t)i * g.C + j];
+        if (g.C <= 64) { g.h_beta = beta; g.h_gamma = gamma; }
         TRY(upload(m, beta.data(), beta.size() * 4, (void**)&g.d_beta));
         TRY(upload(m, gp.data(), gp.size() * 4, (void**)&g.d_gamma));
       }
@@ -836,6 +838,7 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
           if (nx.gdn >= 0) {
             const GdnLayer& g = t.gdns[nx.gdn];
             o.gamma = g.d_gamma; o.gamma_stride = g.Npad; o.beta = g.d_beta; o.tl_inverse = g.inverse;
+            o.h_gamma = g.h_gamma.data(); o.h_beta = g.h_beta.data();
             o.tl_act = g.inverse ? SNTC_ACT_IGDN1 : SNTC_ACT_GDN1;
           } else {
             o.tl_act = nx.act;

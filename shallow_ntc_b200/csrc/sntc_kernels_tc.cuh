@@ -52,6 +52,8 @@ struct alignas(64) TcBandDev {
 
 struct TcParams {
   const TcBandDev* bands; int nbands; int total_items;
+  int ipg;            // > 0: items are m-tile-group major (item = group * ipg + slot, bands[].item_begin = first slot of the band:
+                      // a unit walks through all bands, so heavy-MMA and heavy-epilogue items alternate); 0: band major
   int B, hin, win, s, p;
   int TH, TW, tiles_y, tiles_x;
   int kblocks;        // 64-channel blocks per tap
@@ -78,6 +80,9 @@ struct TcParams {
   //   gdn_mode: this GEMM *is* the GDN norm pool (1x1, gamma): out = gx * norm | gx / norm, norm = acc + beta (or its sqrt)
   int plane_xform, gdn_mode; const float* gx;
   int vec16;          // fast epilogue: cout % 16 == 0, Cy % 16 == 0 and every epilogue tensor 32-byte aligned
+  // TC_EPI_TWO_LAYER constants as kernel parameters: with the loops over (i, j) fully unrolled every gamma / beta / bias
+  // is a constant-bank operand of its FFMA (no shared-memory loads in the per-pixel IGDN)
+  float tl_gamma[24 * 24]; float tl_beta[24]; float tl_bias[48];
   long long* trace;   // debug timeline (SNTC_TC_TRACE=1): [unit][TC_TRACE_ITEMS][8] clock64 stamps, leader CTA only
 };
 
@@ -289,12 +294,20 @@ struct TcItem {
 template <int CG>
 __device__ __forceinline__ TcItem tc_decode_item(const TcParams& P, int item, int rank) {
   TcItem it;
-  int bi = 0;
-  for (int i = 1; i < P.nbands; ++i)
-    if (item >= P.bands[i].item_begin) bi = i;
+  int bi = 0, nt, mg;
+  if (P.ipg > 0) {
+    mg = item / P.ipg;
+    const int slot = item - mg * P.ipg;
+    for (int i = 1; i < P.nbands; ++i)
+      if (slot >= P.bands[i].item_begin) bi = i;
+    nt = slot - P.bands[bi].item_begin;
+  } else {
+    for (int i = 1; i < P.nbands; ++i)
+      if (item >= P.bands[i].item_begin) bi = i;
+    const int local = item - P.bands[bi].item_begin;
+    nt = local % P.bands[bi].ntiles; mg = local / P.bands[bi].ntiles;
+  }
   const TcBandDev& bd = P.bands[bi];
-  int local = item - bd.item_begin;
-  int nt = local % bd.ntiles, mg = local / bd.ntiles;
   int mt = mg * CG + rank;
   it.dup = mt >= P.mtiles;
   if (it.dup) mt = P.mtiles - 1;
@@ -482,21 +495,21 @@ __device__ __forceinline__ void tc_epi_scalar8(const TcParams& P, const TcBandRe
 // Two-layer synthesis, layer 1: one output pixel = C1 base columns (|| C1 residual columns).
 // t = act(base + bias) (+ res + bias'), act = IGDN1 / GDN1 / relu / leaky / none   (common/transforms.py:331-360)
 template <int C1, bool RES>
-__device__ __forceinline__ void tc_epi_two_layer_pixel(const TcParams& P, const float* sgamma, const float* sbeta, const float* sbias,
+__device__ __forceinline__ void tc_epi_two_layer_pixel(const TcParams& P,
                                                         const uint32_t* raw, float* dst, __half* phi, __half* plo, size_t kq_stride) {
   constexpr int PW = RES ? 2 * C1 : C1;
   float x[C1];
 #pragma unroll
-  for (int j = 0; j < C1; ++j) x[j] = fmaf(__uint_as_float(raw[j]), P.inv_scale, sbias[j]);
+  for (int j = 0; j < C1; ++j) x[j] = fmaf(__uint_as_float(raw[j]), P.inv_scale, P.tl_bias[j]);
   float t[C1];
   if (P.tl_act == SNTC_ACT_IGDN1 || P.tl_act == SNTC_ACT_GDN1) {
 #pragma unroll
-    for (int j = 0; j < C1; ++j) t[j] = sbeta[j];
+    for (int j = 0; j < C1; ++j) t[j] = P.tl_beta[j];
 #pragma unroll
     for (int i = 0; i < C1; ++i) {
       const float a = fabsf(x[i]);
 #pragma unroll
-      for (int j = 0; j < C1; ++j) t[j] = fmaf(a, sgamma[i * C1 + j], t[j]);
+      for (int j = 0; j < C1; ++j) t[j] = fmaf(a, P.tl_gamma[i * C1 + j], t[j]);
     }
 #pragma unroll
     for (int j = 0; j < C1; ++j) t[j] = P.tl_inverse ? x[j] * t[j] : x[j] / t[j];
@@ -506,7 +519,7 @@ __device__ __forceinline__ void tc_epi_two_layer_pixel(const TcParams& P, const 
   }
   if (RES) {
 #pragma unroll
-    for (int j = 0; j < C1; ++j) t[j] += fmaf(__uint_as_float(raw[C1 + j]), P.inv_scale, sbias[C1 + j]);
+    for (int j = 0; j < C1; ++j) t[j] += fmaf(__uint_as_float(raw[C1 + j]), P.inv_scale, P.tl_bias[C1 + j]);
   }
   (void)PW;
   if (dst) {
@@ -535,14 +548,22 @@ __device__ __forceinline__ void tc_epi_two_layer_pixel(const TcParams& P, const 
 
 template <int C1, bool RES>
 __device__ __forceinline__ void tc_epi_two_layer(const TcParams& P, const TcBandRegs& bd, const TcItem& it, uint32_t trow, int b, int my, int mx,
-                                                 bool cell_ok, const float* sgamma, const float* sbeta, const float* sbias, int pp0, int pstep) {
+                                                 bool cell_ok, int pp0, int pstep) {
   constexpr int PW = RES ? 2 * C1 : C1;
   const int npx = it.nrows / PW;
-  for (int pp = pp0; pp < npx; pp += pstep) {
-    uint32_t raw[PW];
+  uint32_t raw[PW], nxt[PW];
+  if (pp0 < npx) {
 #pragma unroll
-    for (int c = 0; c < PW; c += 4) tcx::tmem_ld4_nowait(trow + (uint32_t)(pp * PW + c), raw + c);
+    for (int c = 0; c < PW; c += 4) tcx::tmem_ld4_nowait(trow + (uint32_t)(pp0 * PW + c), nxt + c);
+  }
+  for (int pp = pp0; pp < npx; pp += pstep) {
     tcx::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < PW; ++c) raw[c] = nxt[c];
+    if (pp + pstep < npx) {   // the next pixel's accumulator columns are in flight while this one is processed
+#pragma unroll
+      for (int c = 0; c < PW; c += 4) tcx::tmem_ld4_nowait(trow + (uint32_t)((pp + pstep) * PW + c), nxt + c);
+    }
     if (!cell_ok) continue;
     const int ph = (it.n0 + pp * PW) / PW;
     const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p + bd.oshift, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p + bd.oshift;
@@ -551,7 +572,7 @@ __device__ __forceinline__ void tc_epi_two_layer(const TcParams& P, const TcBand
     constexpr int CP = (C1 + 15) / 16 * 16;
     // planes for the tensor-core tail are octet-planar: [B][hout][CP/8][wout][8]
     const size_t poff = (((size_t)b * P.hout + oy) * (CP / 8) * P.wout + ox) * 8;
-    tc_epi_two_layer_pixel<C1, RES>(P, sgamma, sbeta, sbias, raw, P.out_f32 ? P.out_f32 + pix * C1 : nullptr,
+    tc_epi_two_layer_pixel<C1, RES>(P, raw, P.out_f32 ? P.out_f32 + pix * C1 : nullptr,
                                     P.out_hi ? P.out_hi + poff : nullptr, P.out_hi ? P.out_lo + poff : nullptr, (size_t)P.wout * 8);
   }
 }
@@ -569,7 +590,9 @@ template <int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: the compiler keeps the address space (LDS / STS,
+  // not generic loads) for everything derived from `smem`
+  uint8_t* smem = smem_raw + ((1024u - (tcx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t a_bytes = TC_BM * 128;                        // one A plane tile
   const uint32_t b_slot = (uint32_t)(P.bn_max / CG) * 128;     // smem reserved per W plane tile (this CTA's rows)
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_slot;
@@ -578,7 +601,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
   uint64_t* tmem_full_bar = empty_bar + P.stages;         // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* sconst = reinterpret_cast<float*>(tmem_slot + 4);   // two-layer epilogue constants: gamma | beta | bias
+  float* sconst = reinterpret_cast<float*>(tmem_slot + 4);   // epilogue constants: bias [cout]
 
   // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops
   // (and the operands of the TMA / MMA instructions) on the uniform datapath
@@ -595,11 +618,9 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     tcx::fence_barrier_init();
   }
   if (warp == 2) { if (CG == 2) tcx::tmem_alloc_2sm(tmem_slot, 2 * TC_ACC_COLS); else tcx::tmem_alloc(tmem_slot, 2 * TC_ACC_COLS); }
-  if (warp >= 4) {   // epilogue constants -> shared memory: gamma [C1*C1] | beta [C1] | bias [cout]  (C1 = 0 unless two-layer)
-    const int t = threadIdx.x - 128, C1 = P.epi == TC_EPI_TWO_LAYER ? P.C1 : 0, nb = P.cout, nt = 32 * TC_EPI_WARPS;
-    if (C1 && P.gamma) for (int i = t; i < C1 * C1; i += nt) sconst[i] = P.gamma[(size_t)(i / C1) * P.gamma_stride + (i % C1)];
-    if (C1 && P.beta) for (int i = t; i < C1; i += nt) sconst[C1 * C1 + i] = P.beta[i];
-    for (int i = t; i < nb; i += nt) sconst[C1 * C1 + C1 + i] = P.bias[i];
+  if (warp >= 4) {   // epilogue constants -> shared memory: bias [cout]
+    const int t = threadIdx.x - 128, nb = P.cout, nt = 32 * TC_EPI_WARPS;
+    for (int i = t; i < nb; i += nt) sconst[i] = P.bias[i];
   }
   tcx::tc_fence_before();
   if (CG == 2) tcx::cluster_sync_all(); else __syncthreads();
@@ -712,8 +733,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     const int eh = (warp - 4) >> 2;             // which of the quarter's warps: they take alternate column chunks / pixels
     constexpr int EH = TC_EPI_WARPS / 4;
     const int r = ew * 32 + lane;               // row of the tile = cell
-    const int C1s = P.epi == TC_EPI_TWO_LAYER ? P.C1 : 0;
-    const float* sgamma = sconst; const float* sbeta = sconst + C1s * C1s; const float* sbias = sbeta + C1s;
+    const float* sbias = sconst;
     uint32_t j = 0;
     for (int item = unit0; item < P.total_items; item += nunits, ++j) {
       const TcItem it = tc_decode_item<CG>(P, item, rank);
@@ -730,10 +750,10 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
       if (tr) tr[5] = clock64();
       const uint32_t trow = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(ew * 32) << 16);
       if (P.epi == TC_EPI_TWO_LAYER && nk > 0) {
-        if (P.C1 == 12) { if (P.has_res) tc_epi_two_layer<12, true>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias, eh, EH);
-                          else tc_epi_two_layer<12, false>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias, eh, EH); }
-        else            { if (P.has_res) tc_epi_two_layer<24, true>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias, eh, EH);
-                          else tc_epi_two_layer<24, false>(P, bd, it, trow, it.b, my, mx, cell_ok, sgamma, sbeta, sbias, eh, EH); }
+        if (P.C1 == 12) { if (P.has_res) tc_epi_two_layer<12, true>(P, bd, it, trow, it.b, my, mx, cell_ok, eh, EH);
+                          else tc_epi_two_layer<12, false>(P, bd, it, trow, it.b, my, mx, cell_ok, eh, EH); }
+        else            { if (P.has_res) tc_epi_two_layer<24, true>(P, bd, it, trow, it.b, my, mx, cell_ok, eh, EH);
+                          else tc_epi_two_layer<24, false>(P, bd, it, trow, it.b, my, mx, cell_ok, eh, EH); }
       } else {
         if (P.vec16 && nk > 0) {
           // 32-column chunks (one tcgen05.ld.x32 each), the quarter's warps take alternate chunks; the load of the
@@ -1145,6 +1165,7 @@ struct TcConvOut {
   // two-layer fusion: f32 receives t = act(base) (+ res), [B,hout,wout,C1]
   bool two_layer = false; int C1 = 0; bool has_res = false; int tl_act = SNTC_ACT_NONE; bool tl_inverse = true;
   const float* gamma = nullptr; int gamma_stride = 0; const float* beta = nullptr;
+  const float* h_gamma = nullptr; const float* h_beta = nullptr;   // host copies ([C1][C1], [C1]) -> kernel parameters
   // GDN stages (see TcParams): pooled planes out / norm-pool GEMM epilogue
   int plane_xform = A_NONE; int gdn_mode = G_NONE; const float* gx = nullptr;
 };
@@ -1183,14 +1204,25 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   const int mtiles = P.tiles_x * P.tiles_y * B;
   const int groups = (mtiles + t.cg - 1) / t.cg;
   P.mtiles = mtiles;
+  // item order: m-tile-group major for the two-layer layer (its per-pixel IGDN epilogue is as long as the MMAs of a light
+  // band: alternating bands keeps both busy, 0.226 -> 0.217 ms), band major elsewhere (hyper layer 0: 0.057 -> 0.052 ms);
+  // SNTC_TC_ORDER = 0 / 1 forces band / group major everywhere
+  static const int order_env = tc_env_int("SNTC_TC_ORDER", -1);
+  const int order_mode = order_env >= 0 ? order_env : (o.two_layer ? 1 : 0);
   int item = 0;
-  for (auto& bd : t.bands) { bd.item_begin = item; item += groups * bd.ntiles; }
+  if (order_mode) {
+    for (auto& bd : t.bands) { bd.item_begin = item; item += bd.ntiles; }
+    P.ipg = item;
+    item *= groups;
+  } else {
+    for (auto& bd : t.bands) { bd.item_begin = item; item += groups * bd.ntiles; }
+  }
   // the band table depends on the batch geometry only through item_begin: refresh it when that changes
   cudaError_t e = cudaSuccess;
-  if (t.uploaded_mtiles != mtiles) {
+  if (t.uploaded_mtiles != mtiles * 2 + order_mode) {
     e = cudaMemcpyAsync(t.d_bands, t.bands.data(), sizeof(TcBandDev) * t.nbands, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) { *err = std::string("band table upload: ") + cudaGetErrorString(e); return TC_ERROR; }
-    t.uploaded_mtiles = mtiles;
+    t.uploaded_mtiles = mtiles * 2 + order_mode;
   }
   P.bands = t.d_bands; P.nbands = t.nbands; P.total_items = item;
   P.kblocks = t.kblocks; P.last_kmma = t.last_kmma;
@@ -1202,6 +1234,12 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   P.q = o.q; P.q_kind = o.q_kind; P.Cy = o.Cy; P.max_index = o.max_index; P.trunc = o.trunc ? 1 : 0; P.y_hat = o.y_hat; P.idx = o.idx;
   P.C1 = o.C1; P.has_res = o.has_res ? 1 : 0; P.tl_act = o.tl_act; P.tl_inverse = o.tl_inverse ? 1 : 0;
   P.gamma = o.gamma; P.gamma_stride = o.gamma_stride; P.beta = o.beta;
+  if (o.two_layer) {
+    if (o.C1 > 24 || c.cout > 48 || (int)c.h_bias.size() < c.cout) { *err = "two-layer epilogue: hidden width > 24"; return TC_ERROR; }
+    for (int i = 0; i < o.C1 * o.C1; ++i) P.tl_gamma[i] = o.h_gamma ? o.h_gamma[i] : 0.f;
+    for (int i = 0; i < o.C1; ++i) P.tl_beta[i] = o.h_beta ? o.h_beta[i] : 0.f;
+    for (int i = 0; i < c.cout; ++i) P.tl_bias[i] = c.h_bias[i];
+  }
   P.rate_slots = o.rate_slots; P.rate_slot_img = o.rate_slot_img; P.rc = o.rc;
   P.plane_xform = o.plane_xform; P.gdn_mode = o.gdn_mode; P.gx = o.gx;
   {

@@ -80,6 +80,7 @@ struct ConvLayer {
   size_t w_floats = 0;
   float* d_w = nullptr;      // packed band matrices
   float* d_bias = nullptr;   // [cout] (zeros when !has_bias)
+  std::vector<float> h_bias; // host copy
   // rgb-cell packing for final layers with tiny Cout: [k*k][cin_pad][4]
   float* d_w_rgb = nullptr;
   std::vector<float> h_w_tail;   // [k*k][cin][3] + bias[3]: by-value kernel parameter of the constant-bank tail kernel
@@ -92,6 +93,7 @@ struct GdnLayer {
   int C = 0; int kind = GDN_NONE; bool inverse = true;
   std::string beta, gamma;
   float* d_beta = nullptr; float* d_gamma = nullptr;  // gamma [in][out] (padded to Npad columns)
+  std::vector<float> h_beta, h_gamma;                 // host copies ([C], [C][C]) of small layers (kernel parameters)
   int Npad = 0;
 };
 
