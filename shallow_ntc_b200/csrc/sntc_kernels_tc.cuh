@@ -577,6 +577,92 @@ __device__ __forceinline__ void tc_epi_two_layer(const TcParams& P, const TcBand
   }
 }
 
+// Wide hidden layers (C1 = 48): the same per-pixel stage with the accumulator columns fetched in 16-column chunks -- base
+// columns first, residual columns after the IGDN, so at most x[C1] + t[C1] + one chunk are live -- and gamma / beta in
+// shared memory (float4 broadcast loads).  Measured on B200 (8 x 1200x1200): 1.21 ms, LSU-bound (a warp-wide LDS.128
+// returns 512 B however few distinct addresses it has, i.e. one LSU cycle per FFMA); the constant-bank form of the narrow
+// variants is slower here (1.90 ms): 9.2 KB of gamma thrash the constant cache.  Still 2.1x faster than the unfused
+// conv + fp32 IGDN kernel it replaces (0.55 + 2.03 ms).
+// tcgen05.ld is warp-collective: every lane runs the whole pixel, only the stores are predicated.
+template <int C1, bool RES>
+__device__ __forceinline__ void tc_epi_two_layer_wide(const TcParams& P, const TcBandRegs& bd, const TcItem& it, const float* sbias, const float* sgamma,
+                                                      const float* sbeta, uint32_t trow, int b, int my, int mx, bool cell_ok, int pp0, int pstep) {
+  static_assert(C1 % 16 == 0, "16-column TMEM chunks");
+  constexpr int PW = RES ? 2 * C1 : C1;
+  const int npx = it.nrows / PW;
+  for (int pp = pp0; pp < npx; pp += pstep) {
+    const uint32_t tcol = trow + (uint32_t)(pp * PW);
+    float x[C1], t[C1];
+#pragma unroll
+    for (int c = 0; c < C1; c += 16) {
+      uint32_t r[16];
+      tcx::tmem_ld8_nowait(tcol + (uint32_t)c, r);
+      tcx::tmem_ld8_nowait(tcol + (uint32_t)c + 8, r + 8);
+      tcx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[c + i] = fmaf(__uint_as_float(r[i]), P.inv_scale, sbias[c + i]);
+    }
+    if (P.tl_act == SNTC_ACT_IGDN1 || P.tl_act == SNTC_ACT_GDN1) {
+#pragma unroll
+      for (int j = 0; j < C1; j += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(sbeta + j);
+        t[j] = bb.x; t[j + 1] = bb.y; t[j + 2] = bb.z; t[j + 3] = bb.w;
+      }
+#pragma unroll
+      for (int i = 0; i < C1; ++i) {
+        const float a = fabsf(x[i]);
+#pragma unroll
+        for (int j = 0; j < C1; j += 4) {
+          const float4 g = *reinterpret_cast<const float4*>(sgamma + i * C1 + j);
+          t[j] = fmaf(a, g.x, t[j]); t[j + 1] = fmaf(a, g.y, t[j + 1]); t[j + 2] = fmaf(a, g.z, t[j + 2]); t[j + 3] = fmaf(a, g.w, t[j + 3]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < C1; ++j) t[j] = P.tl_inverse ? x[j] * t[j] : x[j] / t[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < C1; ++j) t[j] = apply_act(x[j], P.tl_act);
+    }
+    if (RES) {
+#pragma unroll
+      for (int c = 0; c < C1; c += 16) {
+        uint32_t r[16];
+        tcx::tmem_ld8_nowait(tcol + (uint32_t)(C1 + c), r);
+        tcx::tmem_ld8_nowait(tcol + (uint32_t)(C1 + c) + 8, r + 8);
+        tcx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t[c + i] += fmaf(__uint_as_float(r[i]), P.inv_scale, sbias[C1 + c + i]);
+      }
+    }
+    const int ph = (it.n0 + pp * PW) / PW;
+    const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p + bd.oshift, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p + bd.oshift;
+    if (!cell_ok || oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) continue;
+    const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
+    if (P.out_f32) {
+      float* dst = P.out_f32 + pix * C1;
+#pragma unroll
+      for (int j = 0; j < C1; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
+    }
+    if (P.out_hi) {   // octet-planar fp16 hi/lo planes for the tensor-core tail: [B][hout][C1/8][wout][8]
+      const size_t poff = (((size_t)b * P.hout + oy) * (C1 / 8) * P.wout + ox) * 8;
+      const size_t kq_stride = (size_t)P.wout * 8;
+#pragma unroll
+      for (int g = 0; g < C1 / 8; ++g) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half h0, l0, h1, l1;
+          split_f16(t[8 * g + 2 * i], h0, l0); split_f16(t[8 * g + 2 * i + 1], h1, l1);
+          h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        *reinterpret_cast<uint4*>(P.out_hi + poff + (size_t)g * kq_stride) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(P.out_lo + poff + (size_t)g * kq_stride) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Persistent layer kernel: every CTA (CG = 1) or CTA pair (CG = 2, one cluster = two SMs of a TPC) loops over
 // the layer's work items (band, m-tile group, n-tile); the smem ring and the two TMEM accumulators run across
@@ -621,6 +707,11 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
   if (warp >= 4) {   // epilogue constants -> shared memory: bias [cout]
     const int t = threadIdx.x - 128, nb = P.cout, nt = 32 * TC_EPI_WARPS;
     for (int i = t; i < nb; i += nt) sconst[i] = P.bias[i];
+    if (P.epi == TC_EPI_TWO_LAYER && P.C1 > 24 && P.gamma) {   // wide two-layer epilogue: gamma [C1][C1] | beta [C1] after the bias
+      float* sg = sconst + ((nb + 3) & ~3);
+      for (int i = t; i < P.C1 * P.C1; i += nt) sg[i] = P.gamma[(i / P.C1) * P.gamma_stride + (i % P.C1)];
+      for (int i = t; i < P.C1; i += nt) sg[P.C1 * P.C1 + i] = P.beta[i];
+    }
   }
   tcx::tc_fence_before();
   if (CG == 2) tcx::cluster_sync_all(); else __syncthreads();
@@ -750,6 +841,11 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
       if (tr) tr[5] = clock64();
       const uint32_t trow = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(ew * 32) << 16);
       if (P.epi == TC_EPI_TWO_LAYER && nk > 0) {
+        if (P.C1 == 48) {
+          const float* sg = sconst + ((P.cout + 3) & ~3);
+          if (P.has_res) tc_epi_two_layer_wide<48, true>(P, bd, it, sbias, sg, sg + 48 * 48, trow, it.b, my, mx, cell_ok, eh, EH);
+          else tc_epi_two_layer_wide<48, false>(P, bd, it, sbias, sg, sg + 48 * 48, trow, it.b, my, mx, cell_ok, eh, EH);
+        } else
         if (P.C1 == 12) { if (P.has_res) tc_epi_two_layer<12, true>(P, bd, it, trow, it.b, my, mx, cell_ok, eh, EH);
                           else tc_epi_two_layer<12, false>(P, bd, it, trow, it.b, my, mx, cell_ok, eh, EH); }
         else            { if (P.has_res) tc_epi_two_layer<24, true>(P, bd, it, trow, it.b, my, mx, cell_ok, eh, EH);
@@ -1075,7 +1171,7 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
   t.nbands = (int)t.bands.size();
   if (t.bn_max > TC_ACC_COLS) { *err = "n-tile wider than a TMEM accumulator"; return false; }
   int stage_bytes = 2 * TC_BM * 128 + 2 * (t.bn_max / t.cg) * 128;
-  const int reserve = 2048 + (c.cout + 700) * 4;   // alignment slack + barriers + epilogue constants (gamma | beta | bias)
+  const int reserve = 2048 + (c.cout + (pixel_cols >= 48 ? 48 * 48 + 48 + 8 : 700)) * 4;   // alignment slack + barriers + epilogue constants (bias | gamma | beta)
   t.stages = std::min(8, (227 * 1024 - reserve) / stage_bytes);
   if (t.stages < 2) { *err = "not enough shared memory for a 2-stage pipeline"; return false; }
   if (cudaMalloc((void**)&t.d_bands, sizeof(TcBandDev) * std::max(1, t.nbands)) != cudaSuccess) { *err = "cudaMalloc (band table) failed"; return false; }
@@ -1101,8 +1197,8 @@ inline bool tc_finalize(TcDriver& drv, TcModelState& st, Transform* hyper, Trans
       for (size_t oi = 0; oi + 1 < t->ops.size(); ++oi) {
         if ((t->ops[oi].type == OP_CONVT) && t->ops[oi].conv == (int)i) {
           const Op& nx = t->ops[oi + 1];
-          if (nx.type == OP_ACT_RES && (c.cout == 24 || c.cout == 48)) pixel_cols = c.cout;
-          if (nx.type == OP_GDN && t->gdns[nx.gdn].kind == GDN_1 && (c.cout == 12 || c.cout == 24) && (t->kind == SNTC_T_TWO_LAYER)) pixel_cols = c.cout;
+          if (nx.type == OP_ACT_RES && (c.cout == 24 || c.cout == 48 || c.cout == 96)) pixel_cols = c.cout;
+          if (nx.type == OP_GDN && t->gdns[nx.gdn].kind == GDN_1 && (c.cout == 12 || c.cout == 24 || c.cout == 48) && (t->kind == SNTC_T_TWO_LAYER)) pixel_cols = c.cout;
         }
       }
       if (!tc_pack_conv(drv, c, hw, out[i], pixel_cols, owned, err)) return false;
@@ -1131,10 +1227,13 @@ inline bool tc_finalize(TcDriver& drv, TcModelState& st, Transform* hyper, Trans
       tg.ok = tg.tc.ok;
     }
   }
-  if (syn && tc_env_int("SNTC_TC_TAIL", 0)) {
-    // Tail of a two-layer synthesis on the tensor cores (sntc_kernels_tail_tc.cuh).  OFF by default: measured on B200 it
-    // ties with the CUDA-core tail (0.17 vs 0.18 ms per 24-image step) because every M=128 x K=16 MMA costs ~95 clk of
-    // A-operand delivery however small N is, and it slows the layer-1 epilogue (octet-planar fp16 stores, +0.03 ms).
+  const int tail_env = tc_env_int("SNTC_TC_TAIL", -1);   // -1 = auto: hidden widths the warp-MMA tail does not take (C1 > 16)
+  if (syn && tail_env != 0) {
+    // Tail of a two-layer synthesis on the tensor cores (sntc_kernels_tail_tc.cuh).  Default (auto): hidden widths > 16,
+    // where the warp-MMA tail (sntc_kernels_tail_mma.cuh) does not apply -- C1 = 24: 0.60 -> 0.22 ms per 8 x 1200x1200 step
+    // against the FFMA tail.  At C1 = 12 it loses to the warp-MMA tail (0.19 vs 0.13 ms): every M=128 x K=16 MMA costs
+    // ~95 clk of A-operand delivery however small N is, and the octet-planar fp16 stores slow the layer-1 epilogue.
+    // SNTC_TC_TAIL=1 / 0 forces it on / off.
     st.syn_tail.resize(syn->convs.size());
     for (size_t oi = 2; oi < syn->ops.size(); ++oi) {
       const Op& op = syn->ops[oi];
@@ -1143,6 +1242,7 @@ inline bool tc_finalize(TcDriver& drv, TcModelState& st, Transform* hyper, Trans
       if (prev >= (int)st.syn.size() || !st.syn[prev].ok || !st.syn[prev].fused_two_layer) continue;
       const ConvLayer& c = syn->convs[op.conv];
       if (!tail_tc_supported(c)) continue;
+      if (tail_env < 0 && c.cin <= 16) continue;   // tail_mma_supported(): measured faster there (0.10 vs 0.17 ms per 24-image step)
       if (!tail_tc_pack(c, hw, st.syn_tail[op.conv], owned, err)) return false;
     }
   }
@@ -1235,10 +1335,14 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   P.C1 = o.C1; P.has_res = o.has_res ? 1 : 0; P.tl_act = o.tl_act; P.tl_inverse = o.tl_inverse ? 1 : 0;
   P.gamma = o.gamma; P.gamma_stride = o.gamma_stride; P.beta = o.beta;
   if (o.two_layer) {
-    if (o.C1 > 24 || c.cout > 48 || (int)c.h_bias.size() < c.cout) { *err = "two-layer epilogue: hidden width > 24"; return TC_ERROR; }
-    for (int i = 0; i < o.C1 * o.C1; ++i) P.tl_gamma[i] = o.h_gamma ? o.h_gamma[i] : 0.f;
-    for (int i = 0; i < o.C1; ++i) P.tl_beta[i] = o.h_beta ? o.h_beta[i] : 0.f;
-    for (int i = 0; i < c.cout; ++i) P.tl_bias[i] = c.h_bias[i];
+    if ((o.C1 != 12 && o.C1 != 24 && o.C1 != 48) || (int)c.h_bias.size() < c.cout) { *err = "two-layer epilogue: hidden width must be 12, 24 or 48"; return TC_ERROR; }
+    if (o.C1 <= 24) {   // narrow variants: constants as kernel parameters (the wide one stages gamma / beta in shared memory)
+      for (int i = 0; i < o.C1 * o.C1; ++i) P.tl_gamma[i] = o.h_gamma ? o.h_gamma[i] : 0.f;
+      for (int i = 0; i < o.C1; ++i) P.tl_beta[i] = o.h_beta ? o.h_beta[i] : 0.f;
+      for (int i = 0; i < c.cout; ++i) P.tl_bias[i] = c.h_bias[i];
+    } else if ((o.tl_act == SNTC_ACT_IGDN1 || o.tl_act == SNTC_ACT_GDN1) && (!o.gamma || !o.beta)) {
+      *err = "two-layer epilogue: GDN parameters missing"; return TC_ERROR;
+    }
   }
   P.rate_slots = o.rate_slots; P.rate_slot_img = o.rate_slot_img; P.rc = o.rc;
   P.plane_xform = o.plane_xform; P.gdn_mode = o.gdn_mode; P.gx = o.gx;

@@ -180,8 +180,8 @@ def test_streaming_pipeline_matches_direct_decode(gpu_ctx, q_dtype):
 
 @pytest.mark.parametrize("name,B,H,W", [("two_layer_syn", 2, 128, 192), ("two_layer_syn2", 1, 100, 150), ("two_layer_syn2:24", 1, 128, 128)])
 def test_tensor_core_tail_kernel_matches_oracle(gpu_ctx, monkeypatch, name, B, H, W):
-  """The experimental tcgen05 tail (SNTC_TC_TAIL=1: halo-reuse A patch, un-swizzled descriptors, [w_hi | w_lo] in N;
-  off by default) meets the same gates as the CUDA-core tail, and is really the kernel that ran."""
+  """The tcgen05 tail (halo-reuse A patch, un-swizzled descriptors, [w_hi | w_lo] in N; automatic for C1 > 16, forced
+  here with SNTC_TC_TAIL=1 for C1 = 12 too) meets the same gates as the other tails (SNTC_TC_TAIL=0: FFMA / warp-MMA)."""
   monkeypatch.setenv("SNTC_TC_TAIL", "1")
   model, wts, z, q = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
   ref = oracle_decode(model, wts, z, q, H, W)
@@ -212,6 +212,31 @@ def test_warp_mma_tail_kernel(gpu_ctx, monkeypatch, name, B, H, W):
   assert np.abs(ffma["float"] - got["float"]).max() < 2e-6
   d = np.abs(ffma["image"].astype(int) - got["image"].astype(int))
   assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize("name,B,H,W,label", [("two_layer_syn2:48", 2, 97, 149, "synthesis.conv1+activation"),
+                                              ("two_layer_syn:48", 1, 128, 192, "synthesis.base_conv+activation"),
+                                              ("two_layer_syn:24", 2, 100, 150, "synthesis.base_conv+activation"),
+                                              ("two_layer_syn2:24", 1, 97, 149, "synthesis.conv1+activation")])
+def test_wide_hidden_layers_take_the_fused_tensor_core_path(gpu_ctx, name, B, H, W, label):
+  """two_layer_syn2's sweep widths (mshyper/configs/two_layer_syn2.py:87-89: hidden_channels 24, 48) and the residual
+  variant at those widths: IGDN1 (+ residual) runs in the layer-1 GEMM epilogue (C1 = 48: gamma / beta in shared
+  memory) and the tail conv on tcgen05 (automatic for C1 > 16) -- checked against the oracle with crop + ragged tiles,
+  and against the fp32 CUDA-core path; the layer profile proves the fused kernels are the ones that ran."""
+  model, wts, z, q = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
+  ref = oracle_decode(model, wts, z, q, H, W)
+  model._ensure_native()
+  model.profile_layers(True)
+  got = model.decompress(z, q, (H, W), return_float=True, return_yhat=True)
+  model.profile_layers(False)
+  labels = set(model.layer_profile())
+  assert label in labels and not any("activation+res" in l or l.endswith(".activation") for l in labels), labels
+  print(name, check_against_oracle(got, ref, precision="tc"))
+  base, _, _, _ = make_case(name, B, H, W, "stress", "fp32", gpu_ctx)
+  f32 = base.decompress(z, q, (H, W), return_float=True)
+  assert np.abs(f32["float"] - got["float"]).max() < 1e-4
+  fast = model.decompress(z, q, (H, W))                     # uint8-only outputs: same bytes
+  assert np.array_equal(fast["image"], got["image"])
 
 
 # --------------------------------------------------------------------------------------------------
