@@ -137,6 +137,11 @@ def cpu_reference_run(config, n_images, steps, warmup):
 
 
 def main():
+  # Libraries (NCCL's version banner, ...) write to fd 1: keep the real stdout for the ONE JSON line, send the rest to stderr
+  sys.stdout.flush()
+  json_fd = os.dup(1)
+  os.dup2(2, 1)
+  json_out = os.fdopen(json_fd, "w")
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
   ap.add_argument("--steps", type=int, default=200)
@@ -147,6 +152,7 @@ def main():
   ap.add_argument("--precision", default=os.environ.get("SNTC_PRECISION", "auto"))
   ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through (working set > L2)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--e2e-depth", type=int, default=2, help="device buffer sets of the streaming pipeline (copy/compute overlap); measured 2 / 3 / 4: 8.52 / 8.14 / 8.07 Gpx/s")
   ap.add_argument("--height", type=int, default=512, help="image height (side runs of the other BASELINE configs; the headline is 512x768)")
   ap.add_argument("--width", type=int, default=768)
   args = ap.parse_args()
@@ -169,12 +175,14 @@ def main():
                                   sample=f"{n_img} of the {args.batch} images per step, oracle tier T1 (numpy float32 GEMM-form, BLAS threads = all cores); "
                                          "TF-2.10 itself is not installable offline"),
                 e2e=dict(value=v, unit="Mpx/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
     return 0
 
   dist, rank, world, local = dist_init(args.gpus)
   from shallow_ntc_b200 import build_config, synthetic, Context
   ctx = Context(local)
+  from shallow_ntc_b200 import parallel as _par
+  numa = _par.bind_host_to_gpu(ctx) if world > 1 else dict(bound=False)   # pinned buffers + enqueue thread next to the GPU
   B = args.batch
   peaks = load_peaks()
 
@@ -255,7 +263,7 @@ def main():
   def run_e2e(q_dtype):
     pin = [(ctx.pinned_like(z) if hyper else None, ctx.pinned_like(q.astype(q_dtype))) for z, q in sets[:2]]
     outs = [dict(image=ctx.pinned_empty((B, H, W, 3), np.uint8), idx=ctx.pinned_empty(ys, np.uint8) if hyper else None) for _ in range(2)]
-    pipe = DecodePipeline(model, B, (H, W), q_dtype=q_dtype, depth=2)
+    pipe = DecodePipeline(model, B, (H, W), q_dtype=q_dtype, depth=args.e2e_depth)
     for i in range(3):
       pipe.submit(pin[i % 2][0], pin[i % 2][1], outs[i % 2]["image"], outs[i % 2]["idx"])
     pipe.drain()
@@ -268,6 +276,36 @@ def main():
     pipe.drain()
     return (f0.elapsed_ms(f1), int((pin[0][0].nbytes if hyper else 0) + pin[0][1].nbytes),
             int(outs[0]["image"].nbytes + (outs[0]["idx"].nbytes if hyper else 0)), outs)
+
+  def link_probe(n=10):
+    """Host<->device copy rate of THIS box with all ranks copying at once: the same pinned buffers as the e2e steps, H2D and
+    D2H concurrently on two streams.  It is the roofline of the e2e number (PCIe / host memory, not the GPU)."""
+    from shallow_ntc_b200.pipeline import _Stream
+    import ctypes as C
+    from shallow_ntc_b200._lib import lib, check
+    z, q = sets[0]
+    src = ctx.pinned_like(q)
+    dsrc = ctx.empty(q.shape, q.dtype)
+    dst = ctx.pinned_empty((B, H, W, 3), np.uint8)
+    ddst = ctx.empty((B, H, W, 3), np.uint8)
+    s_in, s_out = _Stream(ctx), _Stream(ctx)
+    res = {}
+    for mode in ("h2d", "d2h", "both"):
+      barrier()
+      a0, a1, b0, b1 = ctx.event(), ctx.event(), ctx.event(), ctx.event()
+      a0.record(s_in.handle); b0.record(s_out.handle)
+      for _ in range(n):
+        if mode != "d2h":
+          check(lib.sntc_memcpy_h2d(ctx.handle, dsrc.ptr, src.ctypes.data_as(C.c_void_p), src.nbytes, s_in.handle))
+        if mode != "h2d":
+          check(lib.sntc_memcpy_d2h(ctx.handle, dst.ctypes.data_as(C.c_void_p), ddst.ptr, dst.nbytes, s_out.handle))
+      a1.record(s_in.handle); b1.record(s_out.handle)
+      s_in.sync(); s_out.sync()
+      if mode != "d2h":
+        res[mode + "_up_gbs"] = n * src.nbytes / (a0.elapsed_ms(a1) * 1e-3) / 1e9
+      if mode != "h2d":
+        res[mode + "_down_gbs"] = n * dst.nbytes / (b0.elapsed_ms(b1) * 1e-3) / 1e9
+    return res
 
   ms_e2e, h2d, d2h, out_hosts = run_e2e(np.float32)
   ms_e2e_i8, h2d_i8, _, _ = run_e2e(np.int8)
@@ -290,8 +328,12 @@ def main():
   g1.record()
   ctx.sync()
   ms_rd = g0.elapsed_ms(g1) / n_rd
+  link = link_probe()
+  link_keys = sorted(link)
+  link_sum = np.array([link[k] for k in link_keys])
   if dist is not None:
     from shallow_ntc_b200 import parallel
+    link_sum = parallel.reduce_metric_sums(dist, link_sum, device=f"cuda:{local}")   # aggregate GB/s over ranks
     ms, ms_e2e, ms_e2e_i8 = (float(v) for v in parallel.max_over_ranks(dist, [ms, ms_e2e, ms_e2e_i8], device=f"cuda:{local}"))
     qsum = parallel.reduce_metric_sums(dist, qsum, device=f"cuda:{local}")     # NCCL: the only collective
 
@@ -324,15 +366,20 @@ def main():
                             ms_per_step_with_rate_term=ms_rd, host_enqueue_ms_per_step=round(host_ms, 4)),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=e2e, unit="Mpx/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
-                         api="DecodePipeline.submit (float32 symbols, pinned host buffers, depth 2)",
-                         int8_symbols=dict(value=px_step * args.steps / (ms_e2e_i8 * 1e-3) / 1e6, h2d_bytes_per_step=h2d_i8)),
+                         api=f"DecodePipeline.submit (float32 symbols, pinned host buffers, depth {args.e2e_depth})", host_numa_binding=numa,
+                         int8_symbols=dict(value=px_step * args.steps / (ms_e2e_i8 * 1e-3) / 1e6, h2d_bytes_per_step=h2d_i8),
+                         host_link=dict({k: round(float(v), 1) for k, v in zip(link_keys, link_sum)},
+                                        note="aggregate pinned-copy GB/s over all ranks copying at once (q symbols up, image down; "
+                                             "'both' = the two directions concurrently): the e2e roofline of this box",
+                                        link_bound_mpx=float(px_step / max(world * h2d / (link_sum[link_keys.index("both_up_gbs")] * 1e9),
+                                                                           world * d2h / (link_sum[link_keys.index("both_down_gbs")] * 1e9)) / 1e6))),
                 roofline=roof)
     if world == 1 and not args.no_cpu_baseline:
       n_img = 2
       v, sec = cpu_reference_run(args.config, n_img, 3, 1)
       line["cpu_baseline"] = dict(value=v, unit="Mpx/s", cores=cores, kind="port",
                                   sample=f"{n_img} of the {B} images x 3 steps, oracle tier T1 (numpy float32 GEMM-form + col2im), {sec:.2f} s/step")
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
   if dist is not None:
     dist.barrier()
     dist.destroy_process_group()

@@ -149,6 +149,9 @@ int sntc_destroy(sntc_ctx* ctx);
 int sntc_sync(sntc_ctx* ctx);                       /* cudaStreamSynchronize of the context stream + sticky error check */
 void* sntc_stream(sntc_ctx* ctx);                   /* the context's cudaStream_t (used when `stream` args are NULL) */
 int sntc_device_name(sntc_ctx* ctx, char* buf, size_t n);
+/* "domain:bus:device.function" of the context's GPU (cudaDeviceGetPCIBusId): lets the host side pin its feeding thread and
+ * its page-locked staging buffers to the GPU's NUMA node (multi-GPU boxes: shallow_ntc_b200.parallel.bind_host_to_gpu). */
+int sntc_device_pci_bus_id(sntc_ctx* ctx, char* buf, size_t n);
 
 /* ---- model ----
  * Replaces Model._init_transforms (mshyper/models.py:111-131): transform_builder.build(cls, **kwargs)

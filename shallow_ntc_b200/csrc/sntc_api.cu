@@ -141,6 +141,12 @@ extern "C" int sntc_device_name(sntc_ctx* ctx, char* buf, size_t n) {
   return SNTC_OK;
 }
 
+extern "C" int sntc_device_pci_bus_id(sntc_ctx* ctx, char* buf, size_t n) {
+  if (!ctx || !buf || n < 13) return fail(SNTC_E_INVALID, "sntc_device_pci_bus_id: bad argument (buffer must hold 13 bytes)");
+  CU_TRY(cudaDeviceGetPCIBusId(buf, (int)n, ctx->device));
+  return SNTC_OK;
+}
+
 extern "C" uint64_t sntc_launch_count(sntc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ------------------------------------------------------------------------------------------------

@@ -50,6 +50,12 @@ class Context:
     return buf.value.decode()
 
   @property
+  def pci_bus_id(self) -> str:
+    buf = C.create_string_buffer(32)
+    check(lib.sntc_device_pci_bus_id(self.handle, buf, 32))
+    return buf.value.decode()
+
+  @property
   def launch_count(self) -> int:
     return int(lib.sntc_launch_count(self.handle))
 
