@@ -197,6 +197,13 @@ int sntc_decode_rd(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q
                    sntc_tensor* out_u8, sntc_tensor* out_idx, sntc_tensor* out_yhat, sntc_tensor* out_f32,
                    const sntc_tensor* original_u8, sntc_image_metrics* metrics, sntc_image_rate* rate, void* stream);
 
+/* MS-SSIM per image of two uint8 batches [B,H,W,C] (host or device), on the device: the validation metric of
+ * frame_loss_given_latent_rvs -- tf.image.ssim_multiscale(image, reconstruction, max_val=255.) on the uint8 images, or
+ * tf.image.ssim when both sides are < 160 px (mshyper/models.py:321-332, factorized/models.py:145-156).
+ * msssim[B] (host memory) is valid on return (the call synchronises `stream`); msssim_db = -10 log10(1 - msssim) (:330).
+ * SNTC_E_INVALID when the smallest of the 5 scales is below the 11x11 window (TensorFlow asserts there too). */
+int sntc_image_msssim(sntc_ctx* ctx, const sntc_tensor* a_u8, const sntc_tensor* b_u8, double* msssim, void* stream);
+
 /* ---- two-phase decode ----
  * A real decoder cannot have q_y before it knows the scale-table rows: the range decoder needs idx to pick the CDF
  * of every symbol (tfc LocationScaleIndexedEntropyModel.decompress(strings, indexes, loc)).  Phase 1 runs

@@ -36,6 +36,12 @@ A6  ``LocationScaleIndexedEntropyModel._normalize_indexes`` clamps the float
     ``int32(round_half_even(.))`` (``index_rounding='rint'``; 'trunc' selectable).
 A7  ``ContinuousBatchedEntropyModel.quantize``: round(x - off) + off.
 A8  ``tf.nn.leaky_relu`` alpha = 0.2; Keras "relu" = max(x, 0).
+A9  ``tf.image.ssim`` / ``tf.image.ssim_multiscale`` (TF 2.10 ``image_ops_impl.py``) on uint8 inputs with
+    ``max_val=255.``: images and max_val go through ``convert_image_dtype(., float32)`` (x / 255, max_val 1);
+    11x11 Gaussian window (sigma 1.5, normalised by a softmax = outer product of the normalised 1-D window),
+    VALID depthwise filtering, k1 = .01, k2 = .03; 5 scales with weights (.0448, .2856, .3001, .2363, .1333),
+    2x2 VALID average pooling between scales after SYMMETRIC end-padding of odd sizes; relu on every factor,
+    weighted geometric mean over scales, arithmetic mean over channels.
 
 Two tiers share one code path, selected by ``dtype``:
 T0  float64, per-tap scatter definition  -> the truth used for parity.
@@ -334,6 +340,73 @@ def mse_psnr(a_u8, b_u8, max_val=255.0):
   with np.errstate(divide="ignore"):
     psnrs = -10.0 * (np.log(mses) - 2.0 * math.log(max_val)) / math.log(10.0)
   return mses, psnrs
+
+
+MSSSIM_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)   # tf.image: _MSSSIM_WEIGHTS
+
+
+def _ssim_window(size=11, sigma=1.5):
+  """tf.image _fspecial_gauss: softmax over the 2-D log-weights == outer product of this normalised 1-D window."""
+  c = np.arange(size, dtype=np.float64) - (size - 1) / 2.0
+  g = np.exp(-0.5 * c * c / (sigma * sigma))
+  return g / g.sum()
+
+
+def _valid_filter(x, g):
+  """Separable VALID filtering of [B,H,W,C] over H and W."""
+  k = g.size
+  H, W = x.shape[1], x.shape[2]
+  t = sum(g[i] * x[:, i:H - k + 1 + i] for i in range(k))
+  return sum(g[i] * t[:, :, i:W - k + 1 + i] for i in range(k))
+
+
+def _ssim_per_channel(x, y, max_val=1.0, k1=0.01, k2=0.03):
+  """tf.image _ssim_per_channel + _ssim_helper (compensation = 1): (mean of luminance*cs, mean of cs) per (image, channel)."""
+  g = _ssim_window()
+  c1, c2 = (k1 * max_val) ** 2, (k2 * max_val) ** 2
+  m0, m1 = _valid_filter(x, g), _valid_filter(y, g)
+  num0 = m0 * m1 * 2.0
+  den0 = m0 * m0 + m1 * m1
+  lum = (num0 + c1) / (den0 + c1)
+  num1 = _valid_filter(x * y, g) * 2.0
+  den1 = _valid_filter(x * x + y * y, g)
+  cs = (num1 - num0 + c2) / (den1 - den0 + c2)
+  return (lum * cs).mean(axis=(1, 2)), cs.mean(axis=(1, 2))
+
+
+def _pool2(x):
+  """ssim_multiscale's downscaling: SYMMETRIC pad of one row / column at the END of odd dimensions, then 2x2 VALID mean."""
+  if x.shape[1] % 2:
+    x = np.concatenate([x, x[:, -1:]], axis=1)
+  if x.shape[2] % 2:
+    x = np.concatenate([x, x[:, :, -1:]], axis=2)
+  return 0.25 * (x[:, 0::2, 0::2] + x[:, 0::2, 1::2] + x[:, 1::2, 0::2] + x[:, 1::2, 1::2])
+
+
+def msssim(a_u8, b_u8):
+  """The validation-mode MS-SSIM of the reference (mshyper/models.py:321-332, factorized/models.py:145-156) for uint8
+  images [B,H,W,C]: tf.image.ssim when both sides are < 160 px, tf.image.ssim_multiscale(max_val=255.) otherwise.
+  Returns (msssim [B], msssim_db [B])."""
+  x = np.asarray(a_u8, dtype=np.float64) / 255.0
+  y = np.asarray(b_u8, dtype=np.float64) / 255.0
+  H, W = x.shape[1], x.shape[2]
+  if H < 160 and W < 160:
+    val = _ssim_per_channel(x, y)[0].mean(axis=-1)
+  else:
+    mcs = []
+    for k in range(len(MSSSIM_WEIGHTS)):
+      if k > 0:
+        x, y = _pool2(x), _pool2(y)
+      if x.shape[1] < 11 or x.shape[2] < 11:
+        raise ValueError("ssim_multiscale: image too small for 5 scales of an 11x11 window")
+      ssim_pc, cs = _ssim_per_channel(x, y)
+      mcs.append(np.maximum(cs, 0.0))
+    mcs.pop()
+    fac = np.stack(mcs + [np.maximum(ssim_pc, 0.0)], axis=-1)            # [B, C, 5]
+    val = np.prod(fac ** np.asarray(MSSSIM_WEIGHTS), axis=-1).mean(axis=-1)
+  with np.errstate(divide="ignore"):
+    db = -10.0 * np.log(1.0 - val) / math.log(10.0)
+  return val, db
 
 
 def noisy_normal_bits(q, i_c):

@@ -16,6 +16,7 @@
 #include "sntc_kernels_tc.cuh"
 #include "sntc_kernels_tail_tc.cuh"
 #include "sntc_kernels_tail_mma.cuh"
+#include "sntc_kernels_msssim.cuh"
 #include "sntc_coder.hpp"
 
 using namespace sntc;
@@ -57,6 +58,7 @@ struct sntc_ctx {
   uint64_t launches = 0;
   cudaDeviceProp prop{};
   TcDriver tc;   // cuTensorMapEncodeTiled entry point etc.
+  DevBuf ms_ws;  // scratch of sntc_image_msssim
 };
 
 struct ProfRec { std::string label; cudaEvent_t a = nullptr, b = nullptr; double macs = 0; };
@@ -121,6 +123,7 @@ extern "C" int sntc_destroy(sntc_ctx* ctx) {
   if (!ctx) return SNTC_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  ctx->ms_ws.release();
   delete ctx;
   return SNTC_OK;
 }
@@ -1453,6 +1456,36 @@ extern "C" int sntc_coder_decode(sntc_coder* k, int kind, const uint8_t* bytes, 
 }
 
 extern "C" void sntc_coder_free(void* p) { free(p); }
+
+// ------------------------------------------------------------------------------------------------
+// MS-SSIM of two uint8 image batches (validation metric of the evaluate loop)
+extern "C" int sntc_image_msssim(sntc_ctx* ctx, const sntc_tensor* a_u8, const sntc_tensor* b_u8, double* msssim, void* stream) {
+  if (!ctx) return fail(SNTC_E_INVALID, "sntc_image_msssim: ctx is NULL");
+  if (!msssim) return fail(SNTC_E_INVALID, "sntc_image_msssim: output pointer is NULL");
+  TRY(check_tensor(a_u8, "a_u8", SNTC_DL_UINT, 8, 4));
+  TRY(check_tensor(b_u8, "b_u8", SNTC_DL_UINT, 8, 4));
+  for (int i = 0; i < 4; ++i)
+    if (a_u8->shape[i] != b_u8->shape[i]) return fail(SNTC_E_INVALID, "sntc_image_msssim: the two image batches differ in shape");
+  const int B = (int)a_u8->shape[0], H = (int)a_u8->shape[1], W = (int)a_u8->shape[2], C = (int)a_u8->shape[3];
+  if (B == 0) return SNTC_OK;
+  if (C <= 0 || C > 65535 || B > 65535) return fail(SNTC_E_INVALID, "sntc_image_msssim: batch / channel count out of range");
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick_stream(ctx, stream);
+  const size_t n = (size_t)B * H * W * C, n_al = (n + 255) / 256 * 256;
+  const bool stage_a = !on_device(a_u8), stage_b = !on_device(b_u8);
+  TRY(ctx->ms_ws.ensure(msssim_ws_bytes(B, H, W, C) + 2 * n_al));
+  uint8_t* base = (uint8_t*)ctx->ms_ws.p;
+  const uint8_t* da = (const uint8_t*)tdata(a_u8); const uint8_t* db = (const uint8_t*)tdata(b_u8);
+  if (stage_a) { CU_TRY(cudaMemcpyAsync(base, da, n, cudaMemcpyHostToDevice, s)); da = base; }
+  if (stage_b) { CU_TRY(cudaMemcpyAsync(base + n_al, db, n, cudaMemcpyHostToDevice, s)); db = base + n_al; }
+  std::vector<double> stats((size_t)B * MS_SCALES * C * 2, 0.0);
+  std::string err;
+  const int rc = msssim_run(da, db, B, H, W, C, base + 2 * n_al, stats.data(), s, &ctx->launches, &err);
+  if (rc == 1) return fail(SNTC_E_INVALID, err);
+  if (rc != 0) return fail(SNTC_E_CUDA, err);
+  msssim_combine(stats.data(), B, C, msssim_single_scale(H, W), msssim);
+  return SNTC_OK;
+}
 
 extern "C" int sntc_last_stage_times_ms(sntc_model* m, float out[4]) {
   if (!m || !out) return fail(SNTC_E_INVALID, "sntc_last_stage_times_ms: bad argument");

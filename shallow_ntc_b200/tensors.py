@@ -59,6 +59,19 @@ class Context:
   def launch_count(self) -> int:
     return int(lib.sntc_launch_count(self.handle))
 
+  def msssim(self, a_u8, b_u8):
+    """Per-image MS-SSIM of two uint8 batches [B,H,W,C] (numpy, DeviceArray, DLPack ...) computed on the device the way
+    the reference's validation branch does (mshyper/models.py:321-332: tf.image.ssim_multiscale(max_val=255.), or
+    tf.image.ssim when both sides are < 160 px).  Returns (msssim [B], msssim_db [B]) as float64 numpy arrays."""
+    a, b = as_tensor(a_u8, self.device), as_tensor(b_u8, self.device)
+    B = int(a.shape[0])
+    out = (C.c_double * max(B, 1))()
+    check(lib.sntc_image_msssim(self.handle, a.byref(), b.byref(), out, None))
+    val = np.array(out[:B], dtype=np.float64)
+    with np.errstate(divide="ignore"):
+      db = -10.0 * np.log(1.0 - val) / np.log(10.0)        # :330
+    return val, db
+
   # --- memory ---
   def empty(self, shape, dtype) -> "DeviceArray":
     return DeviceArray(self, shape, dtype)

@@ -304,7 +304,55 @@ def test_evaluate_loop_records_match_oracle(gpu_ctx, tmp_path):
     assert abs(r["psnr"] - ref_psnr[i]) < PSNR_TOL
     assert abs(r["bpp"] / ((ref["bits_y"][i] + ref["bits_z"][i]) / (H * W)) - 1) < 3e-3
     assert abs(r["rd_loss"] - (r["bpp"] + 0.08 * r["mse"])) < 1e-12
+  # msssim of the record: single-scale branch at 64 x 128 (< 160 px), against the oracle on the GPU's own uint8 images
+  got_img = model.decompress(z, q, (H, W))["image"]
+  ref_ms, ref_db = __import__("oracle.ntc_oracle", fromlist=["x"]).msssim(orig, got_img)
+  assert all(abs(r["msssim"] - ref_ms[i]) < 2e-6 and abs(r["msssim_db"] - ref_db[i]) < 1e-3 for i, r in enumerate(recs))
   single = list(model.evaluate(z, q, orig, batch_size=1))
   assert all(abs(a["bpp"] - b["bpp"]) < 1e-12 * max(1.0, a["bpp"]) and a["mse"] == b["mse"] for a, b in zip(recs, single))
   path = eval_lib.dump_json(recs, tmp_path / "results.json")
   assert len(json.load(open(path))) == 5
+
+
+# --------------------------------------------------------------------------------------------------
+# MS-SSIM (the validation metric of the evaluate loop, mshyper/models.py:321-332)
+
+def test_msssim_kernel_matches_oracle_and_golden(gpu_ctx):
+  """sntc_image_msssim (fp32 separable window out of shared memory, deterministic double partial sums) against the float64
+  oracle and the torch-generated fixture: multi-scale with odd sizes, single-scale branch, host and device inputs, identical
+  images, bit-identical repeat, and the loud failure for sizes TensorFlow rejects."""
+  import os
+  from oracle import ntc_oracle as O
+  from shallow_ntc_b200 import SntcError
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "msssim_torch.npz"))
+  for name in ("multi_odd", "small", "multi_even"):
+    a, b = np.ascontiguousarray(g[name + "_a"]), np.ascontiguousarray(g[name + "_b"])
+    val, db = gpu_ctx.msssim(a, b)
+    ref, ref_db = O.msssim(a, b)
+    assert np.abs(val - g[name + "_val"]).max() < 2e-6 and np.abs(val - ref).max() < 2e-6, (name, val, ref)
+    assert np.abs(db - ref_db).max() < 1e-2
+    dev, _ = gpu_ctx.msssim(gpu_ctx.to_device(a), gpu_ctx.to_device(b))
+    assert np.array_equal(dev, val)
+  a = np.ascontiguousarray(g["multi_even_a"])
+  assert np.abs(gpu_ctx.msssim(a, a)[0] - 1.0).max() < 1e-6
+  with pytest.raises(SntcError):
+    gpu_ctx.msssim(np.zeros((1, 100, 200, 3), np.uint8), np.zeros((1, 100, 200, 3), np.uint8))
+  with pytest.raises(SntcError):
+    gpu_ctx.msssim(np.zeros((1, 64, 64, 3), np.uint8), np.zeros((1, 64, 65, 3), np.uint8))
+  assert gpu_ctx.msssim(np.zeros((0, 64, 64, 3), np.uint8), np.zeros((0, 64, 64, 3), np.uint8))[0].shape == (0,)
+
+
+def test_msssim_full_size_batch(gpu_ctx):
+  """BASELINE config 2 shape (24 x 512x768): decoded images against a noisy original; oracle on 2 of the 24 images,
+  batch independence (a slice gives the same numbers) on the rest."""
+  from oracle import ntc_oracle as O
+  B, H, W = 24, 512, 768
+  model, wts, z, q = make_case("two_layer_syn", B, H, W, "stress", "tc", gpu_ctx)
+  img = model.decompress(z, q, (H, W))["image"]
+  orig = synthetic.make_original(img)
+  val, _ = gpu_ctx.msssim(orig, img)
+  ref, _ = O.msssim(orig[[0, 23]], img[[0, 23]])
+  assert np.abs(val[[0, 23]] - ref).max() < 2e-6, (val[[0, 23]], ref)
+  part, _ = gpu_ctx.msssim(np.ascontiguousarray(orig[5:9]), np.ascontiguousarray(img[5:9]))
+  assert np.array_equal(part, val[5:9])
+  assert np.all((val > 0) & (val < 1))

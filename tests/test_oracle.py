@@ -210,3 +210,20 @@ def test_rate_bits_shapes_and_additivity():
   assert out["bits_y"].shape == (3,) and out["bits_z"].shape == (3,)
   one = O.mshyper_decode(wts, "TwoLayerResSynthesis", z[1:2], q[1:2], 64, 64, dict(channels=(12, 3), strides=(8, 2), kernel_sizes=(13, 5)))
   assert np.allclose(one["bits_y"], out["bits_y"][1:2], rtol=1e-12) and np.allclose(one["bits_z"], out["bits_z"][1:2], rtol=1e-12)
+
+
+def test_msssim_oracle_matches_the_torch_statement_of_tf_image_ssim_multiscale():
+  """A9: oracle.msssim (separable 1-D window, numpy) against an independent torch statement of tf.image.ssim /
+  ssim_multiscale (full 2-D softmax window as a grouped conv, replicate-pad + avg_pool2d), tests/golden/make_golden_msssim.py:
+  odd sizes (end padding at three scales), the single-scale branch (< 160 px), identical images -> 1, and the size rule."""
+  from shallow_ntc_b200.eval_lib import msssim_defined
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "msssim_torch.npz"))
+  for name in ("multi_odd", "small", "multi_even"):
+    val, db = O.msssim(g[name + "_a"], g[name + "_b"])
+    assert np.abs(val - g[name + "_val"]).max() < 1e-12, name
+    assert np.allclose(db, -10 * np.log10(1 - val))
+  a = g["multi_even_a"]
+  assert np.allclose(O.msssim(a, a)[0], 1.0)
+  assert msssim_defined(512, 768) and msssim_defined(96, 120) and msssim_defined(161, 176) and not msssim_defined(100, 200) and not msssim_defined(8, 100)
+  with pytest.raises(ValueError):
+    O.msssim(np.zeros((1, 100, 200, 3), np.uint8), np.zeros((1, 100, 200, 3), np.uint8))
