@@ -152,6 +152,7 @@ def main():
   ap.add_argument("--precision", default=os.environ.get("SNTC_PRECISION", "auto"))
   ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through (working set > L2)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-io-stage", action="store_true", help="skip the separately timed host range-decode sample")
   ap.add_argument("--e2e-depth", type=int, default=2, help="device buffer sets of the streaming pipeline (copy/compute overlap); measured 2 / 3 / 4: 8.52 / 8.14 / 8.07 Gpx/s")
   ap.add_argument("--height", type=int, default=512, help="image height (side runs of the other BASELINE configs; the headline is 512x768)")
   ap.add_argument("--width", type=int, default=768)
@@ -374,6 +375,31 @@ def main():
                                         link_bound_mpx=float(px_step / max(world * h2d / (link_sum[link_keys.index("both_up_gbs")] * 1e9),
                                                                            world * d2h / (link_sum[link_keys.index("both_down_gbs")] * 1e9)) / 1e6))),
                 roofline=roof)
+    if world == 1 and hyper and not args.no_io_stage:
+      # The I/O stage either side of the hot path (north_star: "range decoding ... stays in the host coder ... timed
+      # separately"): container bytes -> symbols on ONE host thread, on a 2-image sample of the same workload, with the GPU
+      # phases of the two-phase decode (hyper-synthesis -> idx, then dequantise + synthesis) timed beside it.
+      try:
+        from shallow_ntc_b200 import EntropyCoder, codec
+        wts_io = synthetic.make_weights(model.variable_shapes(), "stress", synthesis_cls=model._transform_config["synthesis"]["cls"])
+        coder = EntropyCoder(prior_weights=wts_io)
+        n_io = min(B, 8)
+        z_io, q_io = sets[0][0][:n_io], sets[0][1][:n_io]
+        blob = codec.compress(model, coder, z_io, q_io, (H, W))
+        tim1, timN = {}, {}
+        nthr = min(n_io, cores or 1)
+        codec.decompress(model, coder, blob)
+        codec.decompress(model, coder, blob, timing=tim1)
+        codec.decompress(model, coder, blob, timing=timN, threads=nthr)
+        nsym = int(z_io.size + q_io.size)
+        line["io_stage"] = dict(range_decode_mpx_s=n_io * H * W / timN["range_decode_s"] / 1e6, range_decode_msym_s=nsym / timN["range_decode_s"] / 1e6,
+                                host_threads=nthr, one_thread_mpx_s=n_io * H * W / tim1["range_decode_s"] / 1e6,
+                                gpu_two_phase_s=timN["gpu_s"], range_decode_s=timN["range_decode_s"],
+                                bits_per_px=8.0 * len(blob) / (n_io * H * W),
+                                sample=f"{n_io} images ({nsym} symbols, {len(blob)} container bytes), codec.decompress with timing, one image per "
+                                       "host thread; not part of `value` / `e2e` (the hot path starts from decoded symbols)")
+      except Exception as e:   # the I/O stage must never take the headline line down
+        line["io_stage"] = dict(error=f"{type(e).__name__}: {e}")
     if world == 1 and not args.no_cpu_baseline:
       n_img = 2
       v, sec = cpu_reference_run(args.config, n_img, 3, 1)

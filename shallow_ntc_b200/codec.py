@@ -123,17 +123,27 @@ def compress(model, coder, z_hat, q_y, image_hw):
   return pack(strings, z_hat.shape[0], H, W, z_hat.shape, q_y.shape)
 
 
-def decompress(model, coder, blob, timing=None, **kw):
+def _map(fn, items, threads):
+  """Images are independent strings: decode them on `threads` host threads (the coder calls release the GIL)."""
+  if threads <= 1 or len(items) <= 1:
+    return [fn(it) for it in items]
+  from concurrent.futures import ThreadPoolExecutor
+  with ThreadPoolExecutor(max_workers=min(threads, len(items))) as ex:
+    return list(ex.map(fn, items))
+
+
+def decompress(model, coder, blob, timing=None, threads=1, **kw):
   """Container bytes -> decompress() dict (``image`` uint8 [B,H,W,3], ...): range-decode z (host) -> hyper-synthesis
   (GPU) -> idx -> range-decode q (host) -> dequantise + synthesis (GPU).  ``timing``: dict that receives the seconds
-  spent in the host coder (``range_decode_s``) and in the GPU calls (``gpu_s``), reported separately (north_star)."""
+  spent in the host coder (``range_decode_s``) and in the GPU calls (``gpu_s``), reported separately (north_star).
+  ``threads``: host threads of the range decoder (one image per task; the tables are read-only)."""
   strings, (B, H, W), zs, ys = unpack(blob)
   t0 = time.perf_counter()
-  z = np.stack([coder.decode_z(sz, zs[1:]) for sz, _ in strings]).astype(np.float32)
+  z = np.stack(_map(lambda st: coder.decode_z(st[0], zs[1:]), strings, threads)).astype(np.float32)
   t1 = time.perf_counter()
   idx = model.decode_hyper(z)
   t2 = time.perf_counter()
-  q = np.stack([coder.decode_y(sy, idx[b]) for b, (_, sy) in enumerate(strings)])
+  q = np.stack(_map(lambda bs: coder.decode_y(bs[1][1], idx[bs[0]]), list(enumerate(strings)), threads))
   q = q.astype(np.int8) if np.abs(q).max(initial=0) <= 127 else q.astype(np.int16)
   t3 = time.perf_counter()
   out = model.decode_latents(q, (H, W), **kw)

@@ -89,6 +89,18 @@ def test_ragged_empty_and_corrupt_input(coder_and_weights):
 
 
 # --------------------------------------------------------------------------------------------------
+def test_threaded_decode_equals_serial(coder_and_weights):
+  """codec.decompress(threads=N) decodes one image per host thread against shared read-only tables: same symbols."""
+  k, _ = coder_and_weights
+  rng = np.random.default_rng(3)
+  idx = rng.integers(0, 64, (6, 8, 8, 320)).astype(np.uint8)
+  q = np.rint(rng.normal(size=idx.shape) * O.scale_fn(idx.astype(np.float64))).astype(np.int32)
+  strings = [k.encode_y(q[b], idx[b]) for b in range(6)]
+  serial = codec._map(lambda bs: k.decode_y(bs[1], idx[bs[0]]), list(enumerate(strings)), 1)
+  threaded = codec._map(lambda bs: k.decode_y(bs[1], idx[bs[0]]), list(enumerate(strings)), 6)
+  assert all(np.array_equal(a, b) and np.array_equal(a, q[i]) for i, (a, b) in enumerate(zip(serial, threaded)))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
 @pytest.mark.parametrize("q_dtype", [np.float32, np.int8])
@@ -134,5 +146,5 @@ def test_compress_decompress_round_trip(gpu_ctx):
   for b in range(B):
     assert abs(8 * len(strings[b][1]) / est["bits_y"][b] - 1) < 0.03, (8 * len(strings[b][1]), est["bits_y"][b])
     assert abs(8 * len(strings[b][0]) / est["bits_z"][b] - 1) < 0.05, (8 * len(strings[b][0]), est["bits_z"][b])
-  back = codec.decompress(model, coder, blob)
+  back = codec.decompress(model, coder, blob, threads=2)
   assert np.array_equal(back["q_y"], qm)

@@ -136,6 +136,19 @@ def test_full_size_config2_properties(gpu_ctx, precision):
   assert np.array_equal(m["image"], got["image"])
 
 
+def test_large_batch_equals_its_shards(gpu_ctx):
+  """Four bench-sized shards in ONE call (96 x 512x768: 3.6 GB of activations in flight, > 2^31 bytes of t) give exactly
+  the bytes of the four 24-image calls -- index arithmetic, work-item scheduling and the persistent kernels' tile loops
+  do not depend on the batch a tile belongs to (weak scaling moves shards between GPUs, never changes them)."""
+  B, H, W = 96, 512, 768
+  model, wts, z, q = make_case("two_layer_syn", B, H, W, "stress", "tc", gpu_ctx)
+  q8 = q.astype(np.int8)
+  full = model.decompress(z, q8, (H, W))
+  for s in range(4):
+    part = model.decompress(z[24 * s:24 * s + 24], q8[24 * s:24 * s + 24], (H, W))
+    assert np.array_equal(part["image"], full["image"][24 * s:24 * s + 24]) and np.array_equal(part["idx"], full["idx"][24 * s:24 * s + 24])
+
+
 @pytest.mark.parametrize("name,B,H,W", [("two_layer_syn", 2, 128, 192), ("jpegl", 1, 64, 128)])
 def test_tc_path_matches_fp32_path(gpu_ctx, name, B, H, W):
   """The two GPU implementations agree with each other far inside the tolerance."""
