@@ -823,7 +823,7 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
           o.hyper_final = true; o.q = hf->q; o.q_kind = hf->q_kind; o.Cy = hf->Cy; o.max_index = hf->max_index; o.trunc = hf->trunc;
           o.y_hat = hf->y_hat; o.idx = hf->idx;
           if (hf->want_rate) {   // bits_y partials: one slot per (work item, CTA, epilogue warp)
-            const size_t ns = tc_rate_slots(tcv, B, ch, cw);
+            const size_t ns = tc_rate_slots(tcv, B, ch, cw, ctx->tc.num_sms);
             TRY(m->d_rate_slots.ensure(ns * 8));
             TRY(m->d_rate_img.ensure(ns * 4));
             CU_TRY(cudaMemsetAsync(m->d_rate_img.p, 0xFF, ns * 4, s));

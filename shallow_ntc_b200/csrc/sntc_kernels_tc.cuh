@@ -991,7 +991,22 @@ struct TcConv {
   TcBandDev* d_bands = nullptr;
   int nbands = 0;
   int uploaded_mtiles = -1;                                // geometry the device band table was built for
+  // Second tiling of the same packed weights with narrow n-tiles (<= 64 columns), for batches whose wide tiling has
+  // fewer work items than half the persistent units (a single 768x512 image gives the 3x3 hyper head 18 items for 74
+  // CTA pairs): more, shorter items -> the layer's latency drops with the serial K loop of one item.
+  struct Tiling { std::vector<TcBandDev> bands; TcBandDev* d_bands = nullptr; int nbands = 0, bn_max = 16, stages = 2, uploaded_mtiles = -1; } narrow;
 };
+
+// Work items of the wide tiling for `mtiles` m-tiles; the narrow tiling is used when they leave half the units idle.
+inline bool tc_use_narrow(const TcConv& t, int mtiles, int num_sms) {
+  static const int env = [] { const char* e = getenv("SNTC_TC_NARROW"); return e ? atoi(e) : -1; }();   // 0 / 1 force, default auto
+  if (t.narrow.nbands == 0 || env == 0) return false;
+  if (env == 1) return true;
+  const int groups = (mtiles + t.cg - 1) / t.cg;
+  long items = 0;
+  for (auto& bd : t.bands) items += (long)groups * bd.ntiles;
+  return 2 * items <= num_sms / t.cg;
+}
 
 struct TcDevBuf {
   void* p = nullptr; size_t cap = 0;
@@ -1056,8 +1071,8 @@ inline int tc_cta_group() {
 }
 // Fewest n-tiles of at most bn_max columns, then the narrowest (balanced) tile that achieves it; tiles are
 // multiples of `unit`.  The last tile of a band only issues MMAs for its own columns.
-inline int tc_choose_bn(int N, int unit) {
-  int cap = (tc_bn_max() / unit) * unit;
+inline int tc_choose_bn(int N, int unit, int bn_cap) {
+  int cap = (bn_cap / unit) * unit;
   if (cap < unit) cap = unit;
   int tiles = (N + cap - 1) / cap;
   int bn = ((N + tiles - 1) / tiles + unit - 1) / unit * unit;
@@ -1146,36 +1161,44 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
   if (cudaMemcpy(t.d_hi, hi.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(t.d_lo, lo.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
     *err = "cudaMemcpy (tc weights) failed"; return false;
   }
-  t.bands.clear(); t.items_per_mtile.clear();
-  t.bn_max = 16;
-  for (size_t oi = 0; oi < order.size(); ++oi) {
-    size_t bi = order[oi];
-    const Band& b = c.bands[bi];
-    if (b.N == 0) continue;
-    TcBandDev d;
-    memset(&d, 0, sizeof(d));
-    d.phy0 = b.phy0; d.nphx = b.nphx; d.phx0 = b.phx0; d.Ty = b.Ty; d.Tx = b.Tx;
-    // band index -> (yi, xi) in row-major order of (by, bx)
-    d.mloy = c.by[bi / c.bx.size()].mlo; d.mlox = c.bx[bi % c.bx.size()].mlo;
-    d.N = b.N;
-    d.oshift = c.merged ? c.s * c.dlo + c.p : 0;
-    if (b.N <= tc_bn_max()) d.BN = (b.N + base_unit - 1) / base_unit * base_unit;   // single tile: no pixel-alignment constraint
-    else d.BN = tc_choose_bn(b.N, unit);
-    d.ntiles = (b.N + d.BN - 1) / d.BN;
-    t.bn_max = std::max(t.bn_max, d.BN);
-    uint64_t kcols = (uint64_t)std::max(1, b.Ty * b.Tx) * t.ktot_pad;
-    if (!tc_make_map_2d(drv, &d.mapBhi, t.d_hi + row0_of[bi] * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)(d.BN / t.cg), err)) return false;
-    if (!tc_make_map_2d(drv, &d.mapBlo, t.d_lo + row0_of[bi] * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)(d.BN / t.cg), err)) return false;
-    t.bands.push_back(d);
-  }
-  t.nbands = (int)t.bands.size();
-  if (t.bn_max > TC_ACC_COLS) { *err = "n-tile wider than a TMEM accumulator"; return false; }
-  int stage_bytes = 2 * TC_BM * 128 + 2 * (t.bn_max / t.cg) * 128;
-  const int reserve = 2048 + (c.cout + (pixel_cols >= 48 ? 48 * 48 + 48 + 8 : 700)) * 4;   // alignment slack + barriers + epilogue constants (bias | gamma | beta)
-  t.stages = std::min(8, (227 * 1024 - reserve) / stage_bytes);
-  if (t.stages < 2) { *err = "not enough shared memory for a 2-stage pipeline"; return false; }
-  if (cudaMalloc((void**)&t.d_bands, sizeof(TcBandDev) * std::max(1, t.nbands)) != cudaSuccess) { *err = "cudaMalloc (band table) failed"; return false; }
-  owned.push_back(t.d_bands);
+  t.items_per_mtile.clear();
+  // one band table (n-tiling + W tensor maps) per tile-width cap over the same packed weights
+  auto build_tiling = [&](int bn_cap, std::vector<TcBandDev>& bands, int& nbands, int& bn_max, int& stages, TcBandDev*& d_bands) -> bool {
+    bands.clear();
+    bn_max = 16;
+    for (size_t oi = 0; oi < order.size(); ++oi) {
+      size_t bi = order[oi];
+      const Band& b = c.bands[bi];
+      if (b.N == 0) continue;
+      TcBandDev d;
+      memset(&d, 0, sizeof(d));
+      d.phy0 = b.phy0; d.nphx = b.nphx; d.phx0 = b.phx0; d.Ty = b.Ty; d.Tx = b.Tx;
+      // band index -> (yi, xi) in row-major order of (by, bx)
+      d.mloy = c.by[bi / c.bx.size()].mlo; d.mlox = c.bx[bi % c.bx.size()].mlo;
+      d.N = b.N;
+      d.oshift = c.merged ? c.s * c.dlo + c.p : 0;
+      if (b.N <= bn_cap) d.BN = (b.N + base_unit - 1) / base_unit * base_unit;   // single tile: no pixel-alignment constraint
+      else d.BN = tc_choose_bn(b.N, unit, bn_cap);
+      d.ntiles = (b.N + d.BN - 1) / d.BN;
+      bn_max = std::max(bn_max, d.BN);
+      uint64_t kcols = (uint64_t)std::max(1, b.Ty * b.Tx) * t.ktot_pad;
+      if (!tc_make_map_2d(drv, &d.mapBhi, t.d_hi + row0_of[bi] * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)(d.BN / t.cg), err)) return false;
+      if (!tc_make_map_2d(drv, &d.mapBlo, t.d_lo + row0_of[bi] * kmax, kcols, (uint64_t)b.N, kmax, TC_BK, (uint32_t)(d.BN / t.cg), err)) return false;
+      bands.push_back(d);
+    }
+    nbands = (int)bands.size();
+    if (bn_max > TC_ACC_COLS) { *err = "n-tile wider than a TMEM accumulator"; return false; }
+    int stage_bytes = 2 * TC_BM * 128 + 2 * (bn_max / t.cg) * 128;
+    const int reserve = 2048 + (c.cout + (pixel_cols >= 48 ? 48 * 48 + 48 + 8 : 700)) * 4;   // alignment slack + barriers + epilogue constants (bias | gamma | beta)
+    stages = std::min(8, (227 * 1024 - reserve) / stage_bytes);
+    if (stages < 2) { *err = "not enough shared memory for a 2-stage pipeline"; return false; }
+    if (cudaMalloc((void**)&d_bands, sizeof(TcBandDev) * std::max(1, nbands)) != cudaSuccess) { *err = "cudaMalloc (band table) failed"; return false; }
+    owned.push_back(d_bands);
+    return true;
+  };
+  if (!build_tiling(tc_bn_max(), t.bands, t.nbands, t.bn_max, t.stages, t.d_bands)) return false;
+  const int narrow_cap = std::max(64 / unit * unit, unit);
+  if (narrow_cap < t.bn_max && !build_tiling(narrow_cap, t.narrow.bands, t.narrow.nbands, t.narrow.bn_max, t.narrow.stages, t.narrow.d_bands)) return false;
   t.ok = t.nbands > 0;
   return true;
 }
@@ -1280,13 +1303,13 @@ inline void tc_choose_patch(int h, int w, int* TH, int* TW) {
 }
 
 // Number of bits_y partial slots the hyper-final epilogue of this layer writes for a [B,h,w] input.
-inline size_t tc_rate_slots(const TcConv& t, int B, int h, int w) {
+inline size_t tc_rate_slots(const TcConv& t, int B, int h, int w, int num_sms) {
   int TH, TW;
   tc_choose_patch(h, w, &TH, &TW);
   const int mtiles = ((h + TH - 1) / TH) * ((w + TW - 1) / TW) * B;
   const int groups = (mtiles + t.cg - 1) / t.cg;
   size_t items = 0;
-  for (auto& bd : t.bands) items += (size_t)groups * bd.ntiles;
+  for (auto& bd : (tc_use_narrow(t, mtiles, num_sms) ? t.narrow.bands : t.bands)) items += (size_t)groups * bd.ntiles;
   return items * t.cg * TC_EPI_WARPS;
 }
 
@@ -1309,24 +1332,30 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   // SNTC_TC_ORDER = 0 / 1 forces band / group major everywhere
   static const int order_env = tc_env_int("SNTC_TC_ORDER", -1);
   const int order_mode = order_env >= 0 ? order_env : (o.two_layer ? 1 : 0);
+  // tiling: wide n-tiles, or the narrow ones when the batch is too small to give every unit a wide item
+  const bool narrow = tc_use_narrow(t, mtiles, drv.num_sms);
+  std::vector<TcBandDev>& bands = narrow ? t.narrow.bands : t.bands;
+  TcBandDev* const d_bands = narrow ? t.narrow.d_bands : t.d_bands;
+  const int nbands = narrow ? t.narrow.nbands : t.nbands, bn_max = narrow ? t.narrow.bn_max : t.bn_max, stages = narrow ? t.narrow.stages : t.stages;
+  int& uploaded_mtiles = narrow ? t.narrow.uploaded_mtiles : t.uploaded_mtiles;
   int item = 0;
   if (order_mode) {
-    for (auto& bd : t.bands) { bd.item_begin = item; item += bd.ntiles; }
+    for (auto& bd : bands) { bd.item_begin = item; item += bd.ntiles; }
     P.ipg = item;
     item *= groups;
   } else {
-    for (auto& bd : t.bands) { bd.item_begin = item; item += groups * bd.ntiles; }
+    for (auto& bd : bands) { bd.item_begin = item; item += groups * bd.ntiles; }
   }
   // the band table depends on the batch geometry only through item_begin: refresh it when that changes
   cudaError_t e = cudaSuccess;
-  if (t.uploaded_mtiles != mtiles * 2 + order_mode) {
-    e = cudaMemcpyAsync(t.d_bands, t.bands.data(), sizeof(TcBandDev) * t.nbands, cudaMemcpyHostToDevice, s);
+  if (uploaded_mtiles != mtiles * 2 + order_mode) {
+    e = cudaMemcpyAsync(d_bands, bands.data(), sizeof(TcBandDev) * nbands, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) { *err = std::string("band table upload: ") + cudaGetErrorString(e); return TC_ERROR; }
-    t.uploaded_mtiles = mtiles * 2 + order_mode;
+    uploaded_mtiles = mtiles * 2 + order_mode;
   }
-  P.bands = t.d_bands; P.nbands = t.nbands; P.total_items = item;
+  P.bands = d_bands; P.nbands = nbands; P.total_items = item;
   P.kblocks = t.kblocks; P.last_kmma = t.last_kmma;
-  P.cout = c.cout; P.bn_max = t.bn_max; P.stages = t.stages;
+  P.cout = c.cout; P.bn_max = bn_max; P.stages = stages;
   P.inv_scale = 1.f / t.scale; P.bias = c.d_bias; P.act = c.act;
   P.hout = h * c.s; P.wout = w * c.s;
   P.epi = o.hyper_final ? TC_EPI_HYPER_FINAL : (o.two_layer ? TC_EPI_TWO_LAYER : TC_EPI_PLAIN);
@@ -1352,7 +1381,7 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
     ok = ok && al(o.hi) && al(o.lo) && al(o.f32) && al(o.q) && al(o.y_hat) && al(o.idx) && al(o.gx);
     // n-tiles must start on a 16-column boundary and the mma width is a multiple of 32 only when BN is: chunks are 32 wide,
     // the last one may be half-used
-    for (auto& bd : t.bands) ok = ok && bd.BN % 16 == 0;
+    for (auto& bd : bands) ok = ok && bd.BN % 16 == 0;
     P.vec16 = ok ? 1 : 0;
   }
   if ((o.plane_xform != A_NONE || o.gdn_mode != G_NONE) && !P.vec16) {
@@ -1361,7 +1390,7 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   if (o.rate_slots && (!P.vec16 || (size_t)P.total_items * t.cg * TC_EPI_WARPS > o.rate_slot_cap)) {
     *err = "rate term: needs Cy % 16 == 0, 32-byte aligned tensors and a large enough slot buffer"; return TC_ERROR;
   }
-  size_t smem = (size_t)t.stages * (2 * TC_BM * 128 + 2 * (t.bn_max / t.cg) * 128) + 1024 + 64 * 8 + (size_t)((o.two_layer ? o.C1 * o.C1 + o.C1 : 0) + c.cout + 8) * 4;
+  size_t smem = (size_t)stages * (2 * TC_BM * 128 + 2 * (bn_max / t.cg) * 128) + 1024 + 64 * 8 + (size_t)((o.two_layer ? o.C1 * o.C1 + o.C1 : 0) + c.cout + 8) * 4;
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns
   if (smem > 227 * 1024) { *err = "shared memory budget exceeded"; return TC_ERROR; }
   int units = std::min(drv.num_sms / t.cg, P.total_items);
@@ -1403,7 +1432,7 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
     cudaStreamSynchronize(s);
     cudaMemcpy(h.data(), d_trace, trace_n * 8, cudaMemcpyDeviceToHost);
     cudaFree(d_trace);
-    fprintf(stderr, "[tc-trace] layer cin=%d cout=%d k=%d s=%d items=%d units=%d cg=%d stages=%d bn_max=%d\n", c.cin, c.cout, c.k, c.s, P.total_items, units, t.cg, t.stages, t.bn_max);
+    fprintf(stderr, "[tc-trace] layer cin=%d cout=%d k=%d s=%d items=%d units=%d cg=%d stages=%d bn_max=%d\n", c.cin, c.cout, c.k, c.s, P.total_items, units, t.cg, stages, bn_max);
     for (int u : {0, units / 2, units - 1}) {
       const long long* b = h.data() + (size_t)u * TC_TRACE_ITEMS * 8;
       long long t0 = b[0];
