@@ -136,6 +136,27 @@ def test_full_size_config2_properties(gpu_ctx, precision):
   assert np.array_equal(m["image"], got["image"])
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 128, 192), (1, 97, 149), (3, 100, 150), (1, 512, 768)])
+def test_jpegl_byte_run_epilogue_writes_the_scalar_paths_bytes(gpu_ctx, monkeypatch, B, H, W):
+  """JPEG-like synthesis on the tensor cores: when the uint8 image is the only destination the epilogue writes byte runs
+  (32-bit stores re-aligned with funnel shifts, tc_epi_rgb_chunk); asking for the float image too takes the scalar
+  epilogue.  Same bytes for crops to odd sizes (runs cut at W*3 not a multiple of 4, rows cut at H), for use_offset-free
+  and ragged tiles, and with the run path disabled (SNTC_TC_RGB_RUNS=0)."""
+  model, wts, z, q = make_case("jpegl", B, H, W, "stress", "tc", gpu_ctx)
+  scalar = model.decompress(z, q, (H, W), return_float=True, return_yhat=True)
+  if H * W <= 128 * 192:
+    print(check_against_oracle(scalar, oracle_decode(model, wts, z, q, H, W), precision="tc"))
+  # device-resident canvas pre-filled with a sentinel (in place, no staging): every byte must be written, none outside
+  canvas = gpu_ctx.to_device(np.full((B + 1, H, W, 3), 0xA5, np.uint8))
+  out_img = gpu_ctx.to_device(np.full((B, H, W, 3), 0xA5, np.uint8))
+  fast = model.decompress(gpu_ctx.to_device(z), gpu_ctx.to_device(q), (H, W), out=dict(image=out_img))
+  assert np.array_equal(fast["image"].to_host(), scalar["image"])
+  del canvas
+  monkeypatch.setenv("SNTC_TC_RGB_RUNS", "0")
+  base, _, _, _ = make_case("jpegl", B, H, W, "stress", "tc", gpu_ctx)
+  assert np.array_equal(base.decompress(z, q, (H, W))["image"], scalar["image"])
+
+
 def test_large_batch_equals_its_shards(gpu_ctx):
   """Four bench-sized shards in ONE call (96 x 512x768: 3.6 GB of activations in flight, > 2^31 bytes of t) give exactly
   the bytes of the four 24-image calls -- index arithmetic, work-item scheduling and the persistent kernels' tile loops
