@@ -310,6 +310,7 @@ def main():
 
   ms_e2e, h2d, d2h, out_hosts = run_e2e(np.float32)
   ms_e2e_i8, h2d_i8, _, _ = run_e2e(np.int8)
+  ms_e2e_i16, h2d_i16, _, _ = run_e2e(np.int16)     # what codec.decompress hands over when a symbol exceeds int8
   out_host = out_hosts[(args.steps - 1) % 2]
 
   # final quality sum over ranks (the only collective; NCCL all-reduce of 3 doubles)
@@ -335,7 +336,7 @@ def main():
   if dist is not None:
     from shallow_ntc_b200 import parallel
     link_sum = parallel.reduce_metric_sums(dist, link_sum, device=f"cuda:{local}")   # aggregate GB/s over ranks
-    ms, ms_e2e, ms_e2e_i8 = (float(v) for v in parallel.max_over_ranks(dist, [ms, ms_e2e, ms_e2e_i8], device=f"cuda:{local}"))
+    ms, ms_e2e, ms_e2e_i8, ms_e2e_i16 = (float(v) for v in parallel.max_over_ranks(dist, [ms, ms_e2e, ms_e2e_i8, ms_e2e_i16], device=f"cuda:{local}"))
     qsum = parallel.reduce_metric_sums(dist, qsum, device=f"cuda:{local}")     # NCCL: the only collective
 
   if rank == 0:
@@ -369,6 +370,7 @@ def main():
                 e2e=dict(value=e2e, unit="Mpx/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
                          api=f"DecodePipeline.submit (float32 symbols, pinned host buffers, depth {args.e2e_depth})", host_numa_binding=numa,
                          int8_symbols=dict(value=px_step * args.steps / (ms_e2e_i8 * 1e-3) / 1e6, h2d_bytes_per_step=h2d_i8),
+                         int16_symbols=dict(value=px_step * args.steps / (ms_e2e_i16 * 1e-3) / 1e6, h2d_bytes_per_step=h2d_i16),
                          host_link=dict({k: round(float(v), 1) for k, v in zip(link_keys, link_sum)},
                                         note="aggregate pinned-copy GB/s over all ranks copying at once (q symbols up, image down; "
                                              "'both' = the two directions concurrently): the e2e roofline of this box",
