@@ -745,6 +745,7 @@ struct HyperFuse {
   float* y_hat = nullptr; uint8_t* idx = nullptr;
   bool no_planes = false;   // phase 1 of the two-phase decode: only fp32 mu + idx leave the epilogue
   bool want_rate = false; RateConst rc{}; double* rate_slots = nullptr; int* rate_slot_img = nullptr; size_t rate_nslots = 0;
+  float* sigma_out = nullptr;   // out (want_rate, default): raw sigma for rate_y_flat_kernel; SNTC_RATE_FUSED=1 sums in the epilogue instead
   bool done = false; const __half* yh_hi = nullptr; const __half* yh_lo = nullptr;   // out: planes of y_hat
 };
 
@@ -822,7 +823,11 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         if (last && hf) {
           o.hyper_final = true; o.q = hf->q; o.q_kind = hf->q_kind; o.Cy = hf->Cy; o.max_index = hf->max_index; o.trunc = hf->trunc;
           o.y_hat = hf->y_hat; o.idx = hf->idx;
-          if (hf->want_rate) {   // bits_y partials: one slot per (work item, CTA, epilogue warp)
+          static const bool rate_fused = tc_env_int("SNTC_RATE_FUSED", 0) != 0;
+          if (hf->want_rate && !rate_fused) {   // raw sigma leaves the epilogue (fp32), the bits are summed by rate_y_flat_kernel
+            TRY(m->d_hs.ensure((size_t)B * ch * c.s * cw * c.s * hf->Cy * 4));
+            o.sigma_out = (float*)m->d_hs.p; hf->sigma_out = o.sigma_out;
+          } else if (hf->want_rate) {   // bits_y partials: one slot per (work item, CTA, epilogue warp)
             const size_t ns = tc_rate_slots(tcv, B, ch, cw, ctx->tc.num_sms);
             TRY(m->d_rate_slots.ensure(ns * 8));
             TRY(m->d_rate_img.ensure(ns * 4));
@@ -1127,7 +1132,16 @@ static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tenso
       TRY(run_transform(m, m->hyper, true, c0, B, hz, wz, nullptr, &hf, s));
       fused = hf.done;
       if (fused) { ycur.f32 = hf.y_hat; ycur.hi = hf.yh_hi; ycur.lo = hf.yh_lo; }
-      if (fused && rate) {
+      if (fused && rate && hf.sigma_out) {
+        const size_t per = (size_t)hy * wy * Cy;
+        const int bpi = (int)std::min<size_t>((per / 4 + 256 * 4 - 1) / (256 * 4), 512);
+        TRY(m->d_rate_slots.ensure((size_t)B * bpi * 8));
+        ProfScope ps(m, s, "rate.bits_y", 0);
+        rate_y_flat_kernel<<<dim3(bpi, B), 256, 0, s>>>(hf.sigma_out, d_q, q_kind, per, rc, (double*)m->d_rate_slots.p);
+        rate_reduce_kernel<<<B, 256, 0, s>>>((const double*)m->d_rate_slots.p, nullptr, 0, bpi, (double*)m->d_rate.p, 2);
+        ctx->launches += 2;
+        CU_TRY(cudaGetLastError());
+      } else if (fused && rate) {
         rate_reduce_kernel<<<B, 256, 0, s>>>(hf.rate_slots, hf.rate_slot_img, (int)hf.rate_nslots, 0, (double*)m->d_rate.p, 2);
         ctx->launches++;
         CU_TRY(cudaGetLastError());

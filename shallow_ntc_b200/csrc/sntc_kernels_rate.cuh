@@ -110,6 +110,37 @@ __global__ void __launch_bounds__(256) rate_y_kernel(const float* __restrict__ h
   if (threadIdx.x == 0) slots[(size_t)b * gridDim.x + blockIdx.x] = tot;
 }
 
+// Tensor-core path: the hyper-head epilogue leaves raw sigma [B, n_per_image] (fp32) next to idx, and the bits are summed
+// here by a full-occupancy elementwise kernel (2048 threads per SM) instead of by the 8 epilogue warps of the GEMM, where
+// the two erfc + log per element made the epilogue longer than the MMAs (hyper-synthesis layer 2: 0.36 -> 0.63 ms).
+// 4 elements per thread and iteration, 16-byte loads; n_per_image % 4 == 0; grid (blocks_per_image, B), block 256.
+__global__ void __launch_bounds__(256) rate_y_flat_kernel(const float* __restrict__ sigma, const void* __restrict__ q, int q_kind, size_t n_per_image,
+                                                          RateConst rc, double* __restrict__ slots) {
+  __shared__ double sh[256];
+  const int b = blockIdx.y;
+  const size_t n4 = n_per_image / 4, base4 = (size_t)b * n4;
+  float acc = 0.f;
+  double tot_acc = 0.0;
+  int cnt = 0;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    const float4 sg = __ldg(reinterpret_cast<const float4*>(sigma) + base4 + i);
+    float4 qv;
+    if (q_kind == 0) qv = __ldg(reinterpret_cast<const float4*>(q) + base4 + i);
+    else if (q_kind == 1) {
+      const uint2 r = __ldg(reinterpret_cast<const uint2*>(q) + base4 + i);
+      qv = make_float4((float)(int16_t)(r.x & 0xFFFFu), (float)(int16_t)(r.x >> 16), (float)(int16_t)(r.y & 0xFFFFu), (float)(int16_t)(r.y >> 16));
+    } else {
+      const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(q) + base4 + i);
+      qv = make_float4((float)(int8_t)(r & 0xFFu), (float)(int8_t)((r >> 8) & 0xFFu), (float)(int8_t)((r >> 16) & 0xFFu), (float)(int8_t)(r >> 24));
+    }
+    acc += noisy_normal_bits(qv.x, sg.x, rc) + noisy_normal_bits(qv.y, sg.y, rc) + noisy_normal_bits(qv.z, sg.z, rc) + noisy_normal_bits(qv.w, sg.w, rc);
+    if (++cnt == 16) { tot_acc += (double)acc; acc = 0.f; cnt = 0; }   // short fp32 runs, double across them
+  }
+  tot_acc += (double)acc;
+  const double tot = block_sum_256(tot_acc, sh);
+  if (threadIdx.x == 0) slots[(size_t)b * gridDim.x + blockIdx.x] = tot;
+}
+
 // z_hat [B, n_per_image = hz*wz*Cz]; grid (blocks_per_image, B)
 __global__ void __launch_bounds__(256) rate_z_kernel(const float* __restrict__ z, size_t n_per_image, int Cz, const float* __restrict__ prior,
                                                      double* __restrict__ slots) {

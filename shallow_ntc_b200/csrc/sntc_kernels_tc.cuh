@@ -75,6 +75,7 @@ struct TcParams {
   // TC_EPI_TWO_LAYER: columns of one output pixel = base[0,C1) (|| res[C1,2C1)); out_f32 = t [B,hout,wout,C1]
   int C1, has_res, tl_act, tl_inverse; const float* gamma; int gamma_stride; const float* beta;
   double* rate_slots; int* rate_slot_img; RateConst rc;   // TC_EPI_HYPER_FINAL: per-(item, CTA, epilogue warp) partial bits_y
+  float* sigma_out;   // TC_EPI_HYPER_FINAL: raw sigma [B,hout,wout,Cy] for the stand-alone rate kernel (nullable)
   // TC_EPI_PLAIN extras for the GDN stages of the deep decoders (transforms.py:8-63, tfc.GDN):
   //   plane_xform: the fp16 planes receive f(x) (A_ABS / A_SQUARE = the GDN pooling input) while out_f32 receives x;
   //   gdn_mode: this GEMM *is* the GDN norm pool (1x1, gamma): out = gx * norm | gx / norm, norm = acc + beta (or its sqrt)
@@ -433,6 +434,7 @@ __device__ __forceinline__ float tc_epi_vec16(const TcParams& P, const float* sb
                ((uint32_t)scale_index(v[4 * i + 2], P.max_index, P.trunc) << 16) | ((uint32_t)scale_index(v[4 * i + 3], P.max_index, P.trunc) << 24);
       *reinterpret_cast<uint4*>(P.idx + pix * P.Cy + (co - P.Cy)) = make_uint4(o[0], o[1], o[2], o[3]);
     }
+    if (co >= P.Cy && P.sigma_out) store16_f32(P.sigma_out + pix * P.Cy + (co - P.Cy), v);
     float bits = 0.f;
     if (co >= P.Cy && P.rate_slots) {   // rate term a7: bits of q under NoisyNormal(scale = SCALE_FN(i_c))   :278-279
       float qv[16];
@@ -1364,6 +1366,7 @@ struct TcConvOut {
   bool hyper_final = false; const void* q = nullptr; int q_kind = 0; int Cy = 0; float max_index = 63.f; bool trunc = false;
   float* y_hat = nullptr; uint8_t* idx = nullptr;
   double* rate_slots = nullptr; int* rate_slot_img = nullptr; RateConst rc{}; size_t rate_slot_cap = 0;   // bits_y partials (nullable)
+  float* sigma_out = nullptr;                                                                              // raw sigma for rate_y_flat_kernel (nullable)
   // two-layer fusion: f32 receives t = act(base) (+ res), [B,hout,wout,C1]
   bool two_layer = false; int C1 = 0; bool has_res = false; int tl_act = SNTC_ACT_NONE; bool tl_inverse = true;
   const float* gamma = nullptr; int gamma_stride = 0; const float* beta = nullptr;
@@ -1452,12 +1455,12 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
       *err = "two-layer epilogue: GDN parameters missing"; return TC_ERROR;
     }
   }
-  P.rate_slots = o.rate_slots; P.rate_slot_img = o.rate_slot_img; P.rc = o.rc;
+  P.rate_slots = o.rate_slots; P.rate_slot_img = o.rate_slot_img; P.rc = o.rc; P.sigma_out = o.sigma_out;
   P.plane_xform = o.plane_xform; P.gdn_mode = o.gdn_mode; P.gx = o.gx;
   {
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
     bool ok = c.cout % 16 == 0 && (!o.hyper_final || o.Cy % 16 == 0) && !o.two_layer && !o.u8 && !o.crop;
-    ok = ok && al(o.hi) && al(o.lo) && al(o.f32) && al(o.q) && al(o.y_hat) && al(o.idx) && al(o.gx);
+    ok = ok && al(o.hi) && al(o.lo) && al(o.f32) && al(o.q) && al(o.y_hat) && al(o.idx) && al(o.gx) && al(o.sigma_out);
     // n-tiles must start on a 16-column boundary and the mma width is a multiple of 32 only when BN is: chunks are 32 wide,
     // the last one may be half-used
     for (auto& bd : bands) ok = ok && bd.BN % 16 == 0;
@@ -1467,6 +1470,7 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   if ((o.plane_xform != A_NONE || o.gdn_mode != G_NONE) && !P.vec16) {
     *err = "GDN stage on the tensor cores: needs C % 16 == 0 and 32-byte aligned tensors"; return TC_ERROR;
   }
+  if (o.sigma_out && !P.vec16) { *err = "rate term: needs Cy % 16 == 0 and 32-byte aligned tensors"; return TC_ERROR; }
   if (o.rate_slots && (!P.vec16 || (size_t)P.total_items * t.cg * TC_EPI_WARPS > o.rate_slot_cap)) {
     *err = "rate term: needs Cy % 16 == 0, 32-byte aligned tensors and a large enough slot buffer"; return TC_ERROR;
   }
