@@ -157,6 +157,25 @@ def test_jpegl_byte_run_epilogue_writes_the_scalar_paths_bytes(gpu_ctx, monkeypa
   assert np.array_equal(base.decompress(z, q, (H, W))["image"], scalar["image"])
 
 
+@pytest.mark.parametrize("name", ["two_layer_syn", "jpegl", "two_layer_syn2:48"])
+def test_extreme_image_sizes(gpu_ctx, name):
+  """Smallest and awkward geometries (a single pixel, one latent cell, sizes just off the 64-px padding grid, a large
+  image whose sides are not multiples of anything): the tensor-core path agrees with the fp32 CUDA-core path (each pinned
+  to the oracle on the other shapes), its uint8-only fast path writes the same bytes, and rows are never off by more
+  than one.  tools/edge_check.py runs the longer list (up to 2048 x 2048)."""
+  tc, _, _, _ = make_case(name, 1, 64, 64, "stress", "tc", gpu_ctx)
+  ff, _, _, _ = make_case(name, 1, 64, 64, "stress", "fp32", gpu_ctx)
+  for B, H, W in ((1, 1, 1), (1, 16, 16), (3, 63, 65), (2, 257, 511), (1, 1201, 999)):
+    zs, ys = tc.latent_shapes(B, H, W)
+    z, q = synthetic.make_latents(zs, ys)
+    a = tc.decompress(z, q, (H, W), return_float=True)
+    b = ff.decompress(z, q, (H, W), return_float=True)
+    assert np.abs(a["float"] - b["float"]).max() < 1e-4, (B, H, W)
+    assert np.abs(a["image"].astype(int) - b["image"].astype(int)).max() <= 1
+    assert np.abs(a["idx"].astype(int) - b["idx"].astype(int)).max() <= 1 and (a["idx"] != b["idx"]).mean() < 2e-2
+    assert np.array_equal(tc.decompress(z, q, (H, W))["image"], a["image"])
+
+
 def test_large_batch_equals_its_shards(gpu_ctx):
   """Four bench-sized shards in ONE call (96 x 512x768: 3.6 GB of activations in flight, > 2^31 bytes of t) give exactly
   the bytes of the four 24-image calls -- index arithmetic, work-item scheduling and the persistent kernels' tile loops
