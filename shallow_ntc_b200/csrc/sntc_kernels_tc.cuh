@@ -371,11 +371,13 @@ __device__ __forceinline__ void tc_epi_vec8(const TcParams& P, const float* sbia
 __device__ __forceinline__ void store16_planes(__half* hi, __half* lo, size_t off, const float* v) {
   uint32_t h[8], l[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    __half h0, l0, h1, l1;
-    split_f16(v[2 * i], h0, l0); split_f16(v[2 * i + 1], h1, l1);
-    h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  for (int i = 0; i < 8; ++i) {   // split_f16 on pairs: packed conversions (one F2FP per two values each way), same roundings
+    const float c0 = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), c1 = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
+    const __half2 hh = __floats2half2_rn(c0, c1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(c0 - hf.x, c1 - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   tcx::stg256(hi + off, h);
   tcx::stg256(lo + off, l);
@@ -406,6 +408,61 @@ __device__ __forceinline__ void load_q16(const void* q, int kind, size_t e, floa
     }
   }
 }
+// The band fields the epilogue needs, copied to registers once per work item: the band table lives in global
+// memory and the epilogue's own stores would otherwise force a reload (possible aliasing) per column group.
+struct TcBandRegs { int N, nphx, phy0, phx0, oshift; };
+
+// GDN norm pool (1x1 GEMM over gamma), 16 columns of one pixel: out = x * norm | x / norm, norm = acc + beta or its root, with
+// the mode a COMPILE-TIME constant.  The generic tc_epi_vec16 tests act / gdn_mode / plane_xform per element (~40
+// instructions per element); with only 8 epilogue warps per SM that made the stage issue-latency bound (mbt2018 igdn_2:
+// 0.24 IPC per scheduler, 10 % tensor pipe, 29 % of HBM: profiles/r01_ncu_full_mbt2018_gdn2_layer3.txt).
+template <int GM>
+__device__ __forceinline__ void tc_epi_gdn16(const TcParams& P, const float* sbias, size_t off, int co, const uint32_t* raw) {
+  float x[16], v[16];
+  tcx::ldg256_nc(P.gx + off, reinterpret_cast<uint32_t*>(x));
+  tcx::ldg256_nc(P.gx + off + 8, reinterpret_cast<uint32_t*>(x) + 8);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 bb = *reinterpret_cast<const float4*>(sbias + co + 4 * g);
+    v[4 * g] = fmaf(__uint_as_float(raw[4 * g]), P.inv_scale, bb.x); v[4 * g + 1] = fmaf(__uint_as_float(raw[4 * g + 1]), P.inv_scale, bb.y);
+    v[4 * g + 2] = fmaf(__uint_as_float(raw[4 * g + 2]), P.inv_scale, bb.z); v[4 * g + 3] = fmaf(__uint_as_float(raw[4 * g + 3]), P.inv_scale, bb.w);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    // sqrt.approx / div.approx (<= 2 ulp): two orders of magnitude below the split-fp16 accumulation error of this path
+    float nrm = v[i];
+    if (GM == G_MUL_SQRT || GM == G_DIV_SQRT) asm("sqrt.approx.f32 %0, %1;" : "=f"(nrm) : "f"(fmaxf(v[i], 0.f)));
+    v[i] = (GM == G_MUL || GM == G_MUL_SQRT) ? x[i] * nrm : __fdividef(x[i], nrm);
+  }
+  if (P.out_f32) store16_f32(P.out_f32 + off, v);
+  if (P.out_hi) store16_planes(P.out_hi, P.out_lo, off, v);
+}
+
+// All chunks of one work item of a GDN stage (act = none, no plane transform: checked by the caller).
+template <int GM>
+__device__ __forceinline__ void tc_epi_gdn_item(const TcParams& P, const TcBandRegs& bd, const TcItem& it, const float* sbias, uint32_t trow,
+                                                int my, int mx, bool cell_ok, int eh, int EH) {
+  uint32_t raw[32], nxt[32];
+  int c = 32 * eh;
+  if (c < it.mma_n) tcx::tmem_ld32_nowait(trow + (uint32_t)c, nxt);
+  for (; c < it.mma_n; c += 32 * EH) {
+    tcx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) raw[i] = nxt[i];
+    if (c + 32 * EH < it.mma_n) tcx::tmem_ld32_nowait(trow + (uint32_t)(c + 32 * EH), nxt);
+    if (!cell_ok) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = it.n0 + c + 16 * h;
+      if (n >= bd.N) break;
+      const int ph = n / P.cout, co = n - ph * P.cout;
+      const int oy = P.s * my + bd.phy0 + ph / bd.nphx - P.p + bd.oshift, ox = P.s * mx + bd.phx0 + ph % bd.nphx - P.p + bd.oshift;
+      if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) continue;
+      tc_epi_gdn16<GM>(P, sbias, (((size_t)it.b * P.hout + oy) * P.wout + ox) * P.cout + co, co, raw + 16 * h);
+    }
+  }
+}
+
 __device__ __forceinline__ float tc_epi_vec16(const TcParams& P, const float* sbias, int b, int oy, int ox, int co, const uint32_t* raw) {
   if (oy < 0 || oy >= P.hout || ox < 0 || ox >= P.wout) return 0.f;
   const size_t pix = ((size_t)b * P.hout + oy) * P.wout + ox;
@@ -471,9 +528,6 @@ __device__ __forceinline__ float tc_epi_vec16(const TcParams& P, const float* sb
   return 0.f;
 }
 
-// The band fields the epilogue needs, copied to registers once per work item: the band table lives in global
-// memory and the epilogue's own stores would otherwise force a reload (possible aliasing) per column group.
-struct TcBandRegs { int N, nphx, phy0, phx0, oshift; };
 
 // generic scalar epilogue (final layers with cout = 3, ...)
 __device__ __forceinline__ void tc_epi_scalar8(const TcParams& P, const TcBandRegs& bd, const float* sbias, int b, int my, int mx, int n, const float* v) {
@@ -920,7 +974,14 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
         else            { if (P.has_res) tc_epi_two_layer<24, true>(P, bd, it, trow, it.b, my, mx, cell_ok, eh, EH);
                           else tc_epi_two_layer<24, false>(P, bd, it, trow, it.b, my, mx, cell_ok, eh, EH); }
       } else {
-        if (P.vec16 && nk > 0) {
+        if (P.vec16 && nk > 0 && P.gdn_mode != G_NONE && P.act == SNTC_ACT_NONE && P.plane_xform == A_NONE) {
+          switch (P.gdn_mode) {   // mode-specialised GDN epilogue
+            case G_MUL: tc_epi_gdn_item<G_MUL>(P, bd, it, sbias, trow, my, mx, cell_ok, eh, EH); break;
+            case G_DIV: tc_epi_gdn_item<G_DIV>(P, bd, it, sbias, trow, my, mx, cell_ok, eh, EH); break;
+            case G_MUL_SQRT: tc_epi_gdn_item<G_MUL_SQRT>(P, bd, it, sbias, trow, my, mx, cell_ok, eh, EH); break;
+            default: tc_epi_gdn_item<G_DIV_SQRT>(P, bd, it, sbias, trow, my, mx, cell_ok, eh, EH); break;
+          }
+        } else if (P.vec16 && nk > 0) {
           // 32-column chunks (one tcgen05.ld.x32 each), the quarter's warps take alternate chunks; the load of the
           // next chunk is in flight while this one is processed
           int co = it.n0 % P.cout, ph = it.n0 / P.cout, c_at = 0;
