@@ -321,7 +321,10 @@ def main():
   qsum = np.array([met["psnr"].sum(), met["mse"].sum(), met["bits_y"].sum() if hyper else 0.0, met["bits_z"].sum() if hyper else 0.0,
                    float(len(met["psnr"]))])
   # cost of asking for the rate term as well (bits_y in the hyper-head epilogue + bits_z kernel), device-resident
-  n_rd = max(3, args.steps // 8)
+  n_rd = max(20, args.steps // 4)
+  for i in range(3):   # untimed: the first call with the rate term sizes its scratch buffers (cudaMalloc)
+    model.decompress(dev[i % args.rotate][0], dev[i % args.rotate][1], (H, W), out=out_dev, return_bits=hyper, sync=False)
+  ctx.sync()
   g0, g1 = ctx.event(), ctx.event()
   g0.record()
   for i in range(n_rd):
