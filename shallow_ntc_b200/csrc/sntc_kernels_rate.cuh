@@ -21,7 +21,7 @@ struct RateConst { float max_index, log_scale_min, scale_factor; };   // mshyper
 // exp(-a'^2) never underflows because it stays in the log domain (|q| = 127 at sigma = 0.11: a' = 813, bits = 9.5e5), which
 // is what tfc's UniformNoiseAdapter achieves with log survival functions; and there is no erfc / log-sf pair per edge, no
 // expm1 / log1p and no divergent tail branch: ~150 instructions per element instead of ~500 (rate kernel 0.21 -> 0.08 ms per
-// 24-image step).  q = 0 (a < 0) is P = erf(b').  Against the float64 oracle (log_ndtr form) on 2 M random (q, i_c):
+// 24-image step).  q = 0 (a < 0) is P = erf(b').  Against the float64 log_ndtr form on 2 M random (q, i_c):
 // max relative error 4.5e-5 per element, 1.7e-7 on the sum.
 __device__ __forceinline__ float noisy_normal_bits(float q, float raw_sigma, const RateConst& rc) {
   const float i_c = fminf(fmaxf(expf(raw_sigma), 0.f), rc.max_index);
