@@ -91,3 +91,32 @@ def test_cuda_array_interface_objects_are_device_tensors():
     __cuda_array_interface__ = dict(shape=(1, 2, 2, 4), typestr="<f4", data=(0x7f0000000000, False), version=3, strides=None)
   t = as_tensor(Fake(), device_id=3)
   assert t.t.device_type == _lib.DL_CUDA and t.t.device_id == 3 and t.t.data == 0x7f0000000000
+
+
+def test_bind_host_to_gpu_uses_the_gpus_numa_cpus(tmp_path, monkeypatch):
+  """parallel.bind_host_to_gpu: CPU list of the GPU's PCI device from sysfs -> sched_setaffinity; a box without NUMA
+  information (numa_node = -1, the 8-GPU VM of this round) or without sysfs is left alone and nothing raises."""
+  import os
+  from shallow_ntc_b200 import parallel
+
+  class Ctx:
+    pci_bus_id = "0000:1B:00.0"
+
+  assert sorted(parallel._parse_cpulist("0-3,8,10-11\n")) == [0, 1, 2, 3, 8, 10, 11]
+  dev = tmp_path / "0000:1b:00.0"
+  dev.mkdir()
+  allowed = sorted(os.sched_getaffinity(0))
+  calls = []
+  monkeypatch.setattr(os, "sched_setaffinity", lambda pid, cpus: calls.append(set(cpus)))
+  # no NUMA information
+  (dev / "numa_node").write_text("-1\n"); (dev / "local_cpulist").write_text(f"{allowed[0]}\n")
+  info = parallel.bind_host_to_gpu(Ctx(), sysfs=str(tmp_path))
+  assert info["bound"] is False and info["numa_node"] == -1 and not calls
+  # NUMA node with a strict subset of the allowed CPUs -> bound to it
+  if len(allowed) > 1:
+    (dev / "numa_node").write_text("1\n"); (dev / "local_cpulist").write_text(f"{allowed[0]}\n")
+    info = parallel.bind_host_to_gpu(Ctx(), sysfs=str(tmp_path))
+    assert info["bound"] is True and calls == [{allowed[0]}]
+  # missing sysfs entry: reported, not raised
+  info = parallel.bind_host_to_gpu(Ctx(), sysfs=str(tmp_path / "nope"))
+  assert info["bound"] is False and "error" in info
