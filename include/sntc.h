@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SNTC_VERSION 101
+#define SNTC_VERSION 102
 
 /* status codes */
 #define SNTC_OK 0
@@ -77,7 +77,13 @@ enum sntc_activation {
   SNTC_ACT_RELU = 1,
   SNTC_ACT_LEAKY_RELU = 2, /* tf.nn.leaky_relu, alpha 0.2 */
   SNTC_ACT_IGDN1 = 3,      /* GDN1(inverse=True)  */
-  SNTC_ACT_GDN1 = 4        /* GDN1()              */
+  SNTC_ACT_GDN1 = 4,       /* GDN1()              */
+  /* MBT2018Synthesis only (common/transforms.py:170 builds tfc.GDN(inverse=True) with the library defaults):
+   * tensorflow-compression 2.x defaults are alpha_parameter=1, epsilon_parameter=1, i.e. the SAME function as
+   * GDN1(inverse=True): y = x * (beta + |x| @ gamma) -- that is what activation = 0 selects for that class.
+   * SNTC_ACT_IGDN_CLASSIC asks for the original (alpha=2, epsilon=.5) form y = x * sqrt(beta + x^2 @ gamma)
+   * instead, for checkpoints trained with tfc.GDN(alpha_parameter=2, epsilon_parameter=.5). */
+  SNTC_ACT_IGDN_CLASSIC = 5
 };
 
 /* Constructor kwargs of one transform class (same meaning as the Python kwargs). */
@@ -98,6 +104,10 @@ typedef struct sntc_transform_desc {
 /* precision of the contraction kernels */
 #define SNTC_PRECISION_FP32 0      /* CUDA-core FFMA, fp32 throughout */
 #define SNTC_PRECISION_TC_F16X3 1  /* tcgen05 split-fp16 3-pass, fp32 accumulate in TMEM (fp32-class accuracy) */
+/* Opt-in, NOT the parity mode: hyper-synthesis as in TC_F16X3 (mu, idx, y_hat and the rate are bit-identical to it); the
+ * synthesis layers drop the a_hi * w_lo cross term (2 MMA passes, tail included).  Reconstruction error grows from ~1e-5 to
+ * ~1e-4 (inside the 1e-3 tolerance) and a few percent of the uint8 samples move by one LSB. */
+#define SNTC_PRECISION_TC_F16X3_SYN2 2
 
 /* prior of the hyper-latent z (mshyper/models.py:135): tfc.NoisyDeepFactorized(batch_shape=(Cz,)), num_filters (3,3,3).
  * With SNTC_PRIOR_DEEP_FACTORIZED the model expects the raw tfc variables prior.matrix_{0..3} [Cz,f_out,f_in],
@@ -105,7 +115,11 @@ typedef struct sntc_transform_desc {
 #define SNTC_PRIOR_NONE 0
 #define SNTC_PRIOR_DEEP_FACTORIZED 1
 
-/* index rounding rule of the scale table row */
+/* Rule that turns the clamped float index i_c = clamp(exp(raw_sigma), 0, S-1) into the scale-table row a range coder
+ * uses.  tensorflow-compression 2.10 does this in ContinuousIndexedEntropyModel._flatten_indexes with
+ * tf.cast(indexes, tf.int32), i.e. TRUNCATION (= floor, i_c >= 0): SNTC_INDEX_TRUNC is what the host side
+ * (shallow_ntc_b200.models.Model) selects by default.  SNTC_INDEX_RINT (round half to even) is kept for coders that
+ * round.  The eval-path rate term (bits_y) uses the continuous i_c under either rule. */
 #define SNTC_INDEX_RINT 0
 #define SNTC_INDEX_TRUNC 1
 
@@ -245,6 +259,20 @@ int sntc_profile_get(sntc_model* m, int i, const char** label, float* total_ms, 
 
 /* Number of kernels this library has launched on the context since creation (bench "gpu_launches"). */
 uint64_t sntc_launch_count(sntc_ctx* ctx);
+/* The same, by kernel family, so that a caller (and the parity tests) can tell WHICH path served a model created with
+ * SNTC_PRECISION_TC_F16X3 -- layers that are not TMA-addressable (input channels < 64 or not a multiple of 8, e.g.
+ * JPEGLikeSynthesis(use_offset=True)) run on the FFMA band GEMM and show up under SNTC_LAUNCH_BAND_F32:
+ *   out[SNTC_LAUNCH_TOTAL] all kernels | [SNTC_LAUNCH_BAND_TC] tcgen05 band GEMM | [SNTC_LAUNCH_BAND_F32] FFMA band GEMM
+ *   | [SNTC_LAUNCH_TAIL_MMA] warp-MMA two-layer tail | [SNTC_LAUNCH_TAIL_TC] tcgen05 two-layer tail
+ *   | [SNTC_LAUNCH_FINAL_F32] CUDA-core final conv kernels (FFMA tail / rgb cell kernel). */
+#define SNTC_LAUNCH_TOTAL 0
+#define SNTC_LAUNCH_BAND_TC 1
+#define SNTC_LAUNCH_BAND_F32 2
+#define SNTC_LAUNCH_TAIL_MMA 3
+#define SNTC_LAUNCH_TAIL_TC 4
+#define SNTC_LAUNCH_FINAL_F32 5
+#define SNTC_LAUNCH_KINDS 6
+int sntc_launch_counts(sntc_ctx* ctx, uint64_t out[SNTC_LAUNCH_KINDS]);
 
 /* ---- device / pinned memory helpers for hosts without a CUDA array library ---- */
 int sntc_malloc(sntc_ctx* ctx, size_t bytes, void** out);

@@ -28,12 +28,22 @@ A2  tfc ``SignalConv2D(corr=False, strides_up=s, padding="same_zeros")``: same
     scatter form with p = (k-1)//2 (odd k), kernel layout [kh, kw, Cin, Cout].
 A3  ``tf.round`` is round-half-to-even.
 A4  ``tf.saturate_cast(x, uint8)`` clamps to [0, 255] then converts.
-A5  ``tfc.GDN(inverse=True)`` (alpha=2, epsilon=.5): x * sqrt(beta + x^2 @ gamma);
-    ``GDN1`` (``common/transforms.py:8-63``): x * (beta + |x| @ gamma) when inverse,
-    x / (...) otherwise; gamma indexed [in, out].
+A5  ``GDN1`` (``common/transforms.py:8-63``): x * (beta + |x| @ gamma) when inverse,
+    x / (...) otherwise; gamma indexed [in, out].  ``tfc.GDN(inverse=True)`` with the
+    library defaults (``MBT2018Synthesis``, ``common/transforms.py:170``): in
+    tensorflow-compression 2.x the defaults are alpha_parameter=1, epsilon_parameter=1
+    (gdn.py: "GDN1", Johnston et al. 2019) -- the SAME function as GDN1; the reference's
+    own ``GDN1`` class passes exactly those two values to ``tfc.GDN.__init__`` and calls
+    itself "a copy of tfc.GDN that only implements the GDN1 activation".  The original
+    form (alpha=2, epsilon=.5): x * sqrt(beta + x^2 @ gamma) is ``gdn_form='classic'``.
 A6  ``LocationScaleIndexedEntropyModel._normalize_indexes`` clamps the float
-    index to [0, num_scales-1]; the table row used by a range coder is
-    ``int32(round_half_even(.))`` (``index_rounding='rint'``; 'trunc' selectable).
+    index to [0, num_scales-1]; the table row a range coder uses comes from
+    ``ContinuousIndexedEntropyModel._flatten_indexes``: ``tf.cast(indexes, tf.int32)``,
+    i.e. truncation (``index_rounding='trunc'``, the default here and in the product;
+    'rint' = round-half-even stays selectable).  As recalled from tfc 2.10's
+    ``entropy_models/continuous_indexed.py``; not verifiable offline.
+A10 The rate term applies no likelihood lower bound (tfc 2.x entropy models dropped the
+    ``likelihood_bound`` of tfc 1.x; ``mshyper/models.py:246-251`` passes none).
 A7  ``ContinuousBatchedEntropyModel.quantize``: round(x - off) + off.
 A8  ``tf.nn.leaky_relu`` alpha = 0.2; Keras "relu" = max(x, 0).
 A9  ``tf.image.ssim`` / ``tf.image.ssim_multiscale`` (TF 2.10 ``image_ops_impl.py``) on uint8 inputs with
@@ -155,7 +165,7 @@ def gdn1(x, beta, gamma, inverse: bool):
 
 
 def gdn_classic(x, beta, gamma, inverse: bool):
-  """tfc.GDN defaults (alpha=2, epsilon=.5): norm = sqrt(beta + x^2 @ gamma)."""
+  """tfc.GDN(alpha_parameter=2, epsilon_parameter=.5), the original GDN: norm = sqrt(beta + x^2 @ gamma)."""
   dt = x.dtype
   norm = np.sqrt(np.square(x) @ np.asarray(gamma, dtype=dt) + np.asarray(beta, dtype=dt))
   return x * norm if inverse else x / norm
@@ -230,13 +240,15 @@ def two_layer_res_synthesis(wts, y_hat, strides=(8, 2), activation_type="igdn", 
   return keras_conv2d_transpose(base + res, wts[f"{prefix}.out_conv.kernel"], wts[f"{prefix}.out_conv.bias"], strides[1], dtype, gemm_form)
 
 
-def mbt2018_synthesis(wts, y_hat, n_layers=4, dtype=np.float64, gemm_form=False, prefix="synthesis"):
-  """common/transforms.py:158-175: n_layers x SignalConv2D 5x5 up2, classic IGDN after all but the last."""
+def mbt2018_synthesis(wts, y_hat, n_layers=4, dtype=np.float64, gemm_form=False, prefix="synthesis", gdn_form="gdn1"):
+  """common/transforms.py:158-175: n_layers x SignalConv2D 5x5 up2, tfc.GDN(inverse=True) after all but the last
+  (A5: the tfc 2.x defaults make it IGDN1; gdn_form='classic' = the alpha=2 / epsilon=.5 form)."""
   x = y_hat
+  act = gdn1 if gdn_form == "gdn1" else gdn_classic
   for i in range(n_layers):
     x = tfc_signal_conv2d_up(x, wts[f"{prefix}.layer_{i}.kernel"], wts[f"{prefix}.layer_{i}.bias"], 2, dtype, gemm_form)
     if i + 1 < n_layers:
-      x = gdn_classic(x, wts[f"{prefix}.igdn_{i}.beta"], wts[f"{prefix}.igdn_{i}.gamma"], inverse=True)
+      x = act(x, wts[f"{prefix}.igdn_{i}.beta"], wts[f"{prefix}.igdn_{i}.gamma"], inverse=True)
   return x
 
 
@@ -267,7 +279,7 @@ _SYNTHESIS = {
     w, y, kw.get("strides", (8, 2)), kw.get("activation_type", "igdn"), dt, g),
   "TwoLayerResSynthesis": lambda w, y, kw, dt, g: two_layer_res_synthesis(
     w, y, kw.get("strides", (8, 2)), kw.get("activation_type", "igdn"), dt, g),
-  "MBT2018Synthesis": lambda w, y, kw, dt, g: mbt2018_synthesis(w, y, kw.get("n_layers", 4), dt, g),
+  "MBT2018Synthesis": lambda w, y, kw, dt, g: mbt2018_synthesis(w, y, kw.get("n_layers", 4), dt, g, gdn_form=kw.get("gdn_form", "gdn1")),
   "BLS2017Synthesis": lambda w, y, kw, dt, g: bls2017_synthesis(w, y, dt, g),
   "CNNSynthesis": lambda w, y, kw, dt, g: cnn_synthesis(w, y, kw.get("activation_type", "leaky_relu"), dt, g),
 }
@@ -290,7 +302,7 @@ def hyper_synthesis_by_name(cls, wts, z_hat, kwargs=None, dtype=np.float64, gemm
 # --------------------------------------------------------------------------
 # entropy-model glue and pixel epilogue
 
-def scale_indexes(raw_sigma, index_rounding="rint"):
+def scale_indexes(raw_sigma, index_rounding="trunc"):
   """mshyper/models.py:274-276 + tfc index handling (A6).
 
   Returns (i_c float64 clamped continuous index, idx uint8 table row, dist = distance
@@ -478,7 +490,7 @@ def rate_bits(wts, raw_sigma, q_y, z_hat=None, prefix="prior"):
 
 def mshyper_decode(wts, synthesis_cls, z_hat, q_y, H, W, synthesis_kwargs=None,
                    hyper_cls="HyperSynthesis", hyper_kwargs=None, original_u8=None,
-                   dtype=np.float64, gemm_form=False, index_rounding="rint"):
+                   dtype=np.float64, gemm_form=False, index_rounding="trunc"):
   """mshyper/models.py:269-317 (training=False), from decoded symbols.
 
   z_hat: [B, Hp/64, Wp/64, Cz] integer-valued; q_y = round(y - mu): [B, Hp/16, Wp/16, Cy]."""

@@ -18,8 +18,9 @@ T_NONE = 0
 T_HYPER_SYNTHESIS, T_JPEG_LIKE_HYPER, T_HYPER_SMALL = 1, 2, 3
 T_JPEG_LIKE_SYNTHESIS, T_TWO_LAYER, T_TWO_LAYER_RES, T_MBT2018, T_BLS2017, T_CNN = 10, 11, 12, 13, 14, 15
 # enum sntc_activation
-ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_IGDN1, ACT_GDN1 = 0, 1, 2, 3, 4
-PRECISION_FP32, PRECISION_TC_F16X3 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_IGDN1, ACT_GDN1, ACT_IGDN_CLASSIC = 0, 1, 2, 3, 4, 5
+PRECISION_FP32, PRECISION_TC_F16X3, PRECISION_TC_F16X3_SYN2 = 0, 1, 2
+LAUNCH_KINDS = ("total", "band_tc", "band_f32", "tail_mma", "tail_tc", "final_f32")   # SNTC_LAUNCH_*
 INDEX_RINT, INDEX_TRUNC = 0, 1
 PRIOR_NONE, PRIOR_DEEP_FACTORIZED = 0, 1
 
@@ -94,6 +95,7 @@ _PROTOS = {
   "sntc_profile_count": (C.c_int, [_P]),
   "sntc_profile_get": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
   "sntc_launch_count": (C.c_uint64, [_P]),
+  "sntc_launch_counts": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
   "sntc_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
   "sntc_free": (C.c_int, [_P, _P]),
   "sntc_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),

@@ -23,6 +23,8 @@ using namespace sntc;
 
 static thread_local std::string g_err;
 
+static inline bool is_tc(int precision) { return precision == SNTC_PRECISION_TC_F16X3 || precision == SNTC_PRECISION_TC_F16X3_SYN2; }
+
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 #define CU_TRY(expr)                                                                              \
@@ -56,6 +58,7 @@ struct sntc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   uint64_t launches = 0;
+  uint64_t kinds[SNTC_LAUNCH_KINDS] = {0, 0, 0, 0, 0, 0};   // by kernel family (sntc_launch_counts); [0] unused (= launches)
   cudaDeviceProp prop{};
   TcDriver tc;   // cuTensorMapEncodeTiled entry point etc.
   DevBuf ms_ws;  // scratch of sntc_image_msssim
@@ -84,6 +87,7 @@ struct sntc_model {
   DevBuf d_rate_slots, d_rate_img, d_rate_zslots, d_rate;   // rate term: partial slots, slot->image map, per-image [bits_y, bits_z]
   float* d_prior = nullptr;             // NoisyDeepFactorized parameters [Cz][DF_STRIDE] (softplus / tanh applied)
   double* h_rate = nullptr; int h_rate_cap = 0;   // pinned
+  DevBuf d_flag;                        // split_planes_kernel's "lo plane is non-zero" flag (one unsigned)
   DevBuf d_mu;                          // two-phase decode: mu of the last sntc_decode_hyper [B,hy,wy,Cy] f32
   int ph_B = 0, ph_hy = 0, ph_wy = 0;   // geometry of that call (0 = none pending)
   TcModelState tc;                      // tensor-core plan state (tensor maps, fp16 planes)
@@ -151,6 +155,12 @@ extern "C" int sntc_device_pci_bus_id(sntc_ctx* ctx, char* buf, size_t n) {
 }
 
 extern "C" uint64_t sntc_launch_count(sntc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int sntc_launch_counts(sntc_ctx* ctx, uint64_t out[SNTC_LAUNCH_KINDS]) {
+  if (!ctx || !out) return fail(SNTC_E_INVALID, "sntc_launch_counts: bad argument");
+  for (int i = 0; i < SNTC_LAUNCH_KINDS; ++i) out[i] = ctx->kinds[i];
+  out[SNTC_LAUNCH_TOTAL] = ctx->launches;
+  return SNTC_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // memory / event helpers
@@ -264,7 +274,7 @@ static void mark_final_op(Transform& t, int precision) {
   if (c.cout <= 3 && maxN < 64 && (c.s == 1 || c.s == 2 || c.s == 4)) {
     // tensor-core precision and a TMA-addressable input (deep decoders: 192 / 256 channels): all s*s output residues of a
     // cell become ONE band (N = s*s*cout) of the tcgen05 band GEMM; SNTC_TC_FINAL=0 keeps the CUDA-core cell kernel
-    if (precision == SNTC_PRECISION_TC_F16X3 && tc_conv_supported(c) && c.s > 1 && tc_env_int("SNTC_TC_FINAL", 1)) finish_conv_merged(c);
+    if (is_tc(precision) && tc_conv_supported(c) && c.s > 1 && tc_env_int("SNTC_TC_FINAL", 1)) finish_conv_merged(c);
     else last.type = OP_CONVT_RGB;
   }
 }
@@ -274,7 +284,7 @@ extern "C" int sntc_model_create(sntc_ctx* ctx, const sntc_model_desc* desc, snt
   *out = nullptr;
   if (desc->struct_size != (int32_t)sizeof(sntc_model_desc))
     return fail(SNTC_E_INVALID, "sntc_model_create: desc.struct_size mismatch (ABI)");
-  if (desc->precision != SNTC_PRECISION_FP32 && desc->precision != SNTC_PRECISION_TC_F16X3)
+  if (desc->precision != SNTC_PRECISION_FP32 && !is_tc(desc->precision))
     return fail(SNTC_E_INVALID, "sntc_model_create: unknown precision");
   auto m = std::make_unique<sntc_model>();
   m->ctx = ctx;
@@ -330,7 +340,7 @@ extern "C" int sntc_model_destroy(sntc_model* m) {
   cudaStreamSynchronize(m->ctx->stream);
   for (void* p : m->owned) cudaFree(p);
   for (DevBuf* b : {&m->ws_a, &m->ws_b, &m->ws_c, &m->st_z, &m->st_q, &m->st_u8, &m->st_idx, &m->st_yhat, &m->st_f32,
-                    &m->st_orig, &m->d_hs, &m->d_yhat, &m->d_ssd, &m->d_rate_slots, &m->d_rate_img, &m->d_rate_zslots, &m->d_rate, &m->d_mu})
+                    &m->st_orig, &m->d_hs, &m->d_yhat, &m->d_ssd, &m->d_rate_slots, &m->d_rate_img, &m->d_rate_zslots, &m->d_rate, &m->d_mu, &m->d_flag})
     b->release();
   m->tc.release();
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
@@ -422,7 +432,7 @@ extern "C" int sntc_model_finalize(sntc_model* m) {
       }
     }
   }
-  if (m->desc.precision == SNTC_PRECISION_TC_F16X3) {
+  if (is_tc(m->desc.precision)) {
     std::string err;
     if (!tc_finalize(m->ctx->tc, m->tc, m->has_hyper ? &m->hyper : nullptr, m->has_syn ? &m->syn : nullptr, m->hw, m->owned, &err))
       return fail(SNTC_E_CUDA, "sntc_model_finalize (tensor-core path): " + err);
@@ -616,7 +626,7 @@ static int launch_band_gemm(sntc_ctx* ctx, const BandGemmParams& P, cudaStream_t
     dim3 grid((M + 63) / 64, (P.N + 31) / 32);
     band_gemm_f32_kernel<64, 32, 16, 4, 4><<<grid, 128, 0, s>>>(P);
   }
-  ctx->launches++;
+  ctx->launches++; ctx->kinds[SNTC_LAUNCH_BAND_F32]++;
   CU_TRY(cudaGetLastError());
   return SNTC_OK;
 }
@@ -659,7 +669,7 @@ static int launch_tail(sntc_ctx* ctx, const ConvLayer& c, const float* in, int B
   }
   dim3 grid((Q.wout + 63) / 64, (Q.hout + RY * TR - 1) / (RY * TR), B);
   tail_s2_kernel<K, PD, C1, TR><<<grid, 32 * TR, smem, s>>>(Q);
-  ctx->launches++;
+  ctx->launches++; ctx->kinds[SNTC_LAUNCH_FINAL_F32]++;
   CU_TRY(cudaGetLastError());
   return SNTC_OK;
 }
@@ -680,7 +690,7 @@ static int run_rgb_f32(sntc_ctx* ctx, const ConvLayer& c, const float* in, int B
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr; cfg.numAttrs = tc_pdl() ? 1 : 0;
       CU_TRY(cudaLaunchKernelEx(&cfg, tail_s2_const_kernel<5, 1, 12, 4>, Q, Wt));
-      ctx->launches++;
+      ctx->launches++; ctx->kinds[SNTC_LAUNCH_FINAL_F32]++;
       CU_TRY(cudaGetLastError());
       return SNTC_OK;
     }
@@ -705,6 +715,21 @@ static int run_rgb_f32(sntc_ctx* ctx, const ConvLayer& c, const float* in, int B
   else if (c.s == 2) convt_rgb_cell_kernel<2><<<grid, 128, smem, s>>>(P);
   else if (c.s == 4) convt_rgb_cell_kernel<4><<<grid, 128, smem, s>>>(P);
   else return fail(SNTC_E_UNSUPPORTED, "rgb cell kernel: stride must be 1, 2 or 4");
+  ctx->launches++; ctx->kinds[SNTC_LAUNCH_FINAL_F32]++;
+  CU_TRY(cudaGetLastError());
+  return SNTC_OK;
+}
+
+// act_res_kernel keeps gamma [C][C] | beta [C] | a 128-pixel x tile in dynamic shared memory: above 48 KB (C = 64: 49 920 B)
+// the launch needs the opt-in attribute
+static int launch_act_res(sntc_ctx* ctx, const ActResParams& P, cudaStream_t s) {
+  const size_t smem = ((size_t)P.C * P.C + P.C + 128 * (P.C + 1)) * 4;
+  static size_t attr_bytes = 48 * 1024;
+  if (smem > attr_bytes) {
+    CU_TRY(cudaFuncSetAttribute(act_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes = smem;
+  }
+  act_res_kernel<<<(unsigned)((P.npix + 127) / 128), 128, smem, s>>>(P);
   ctx->launches++;
   CU_TRY(cudaGetLastError());
   return SNTC_OK;
@@ -717,11 +742,7 @@ static int run_gdn_f32(sntc_ctx* ctx, const GdnLayer& g, const float* in, size_t
     P.act = g.inverse ? SNTC_ACT_IGDN1 : SNTC_ACT_GDN1; P.has_res = 0;
     P.beta = g.d_beta; P.gamma = g.d_gamma; P.gamma_stride = g.Npad; P.inverse = g.inverse;
     if (g.kind != GDN_1) return fail(SNTC_E_UNSUPPORTED, "classic GDN with C <= 64 is not on any decode path");
-    size_t smem = ((size_t)g.C * g.C + g.C + 128 * (g.C + 1)) * 4;
-    act_res_kernel<<<(unsigned)((npix + 127) / 128), 128, smem, s>>>(P);
-    ctx->launches++;
-    CU_TRY(cudaGetLastError());
-    return SNTC_OK;
+    return launch_act_res(ctx, P, s);
   }
   // norm = beta + f(x) @ gamma as a 1x1 band GEMM; epilogue multiplies / divides x
   BandGemmParams P{};
@@ -750,7 +771,7 @@ struct HyperFuse {
 };
 
 static bool op_on_tc(sntc_model* m, Transform& t, bool is_hyper, size_t i) {
-  if (m->desc.precision != SNTC_PRECISION_TC_F16X3) return false;
+  if (!is_tc(m->desc.precision)) return false;
   const Op& op = t.ops[i];
   if (op.type != OP_CONVT) return false;
   const std::vector<TcConv>& tc = is_hyper ? m->tc.hyper : m->tc.syn;
@@ -758,7 +779,7 @@ static bool op_on_tc(sntc_model* m, Transform& t, bool is_hyper, size_t i) {
 }
 
 static bool gdn_on_tc(sntc_model* m, Transform& t, bool is_hyper, size_t i) {
-  if (is_hyper || m->desc.precision != SNTC_PRECISION_TC_F16X3 || i >= t.ops.size()) return false;
+  if (is_hyper || !is_tc(m->desc.precision) || i >= t.ops.size()) return false;
   const Op& op = t.ops[i];
   return op.type == OP_GDN && op.gdn < (int)m->tc.syn_gdn.size() && m->tc.syn_gdn[op.gdn].ok;
 }
@@ -788,7 +809,7 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
   }
   TRY(m->ws_a.ensure(max_f32));
   TRY(m->ws_b.ensure(max_f32));
-  const bool any_tc = m->desc.precision == SNTC_PRECISION_TC_F16X3;
+  const bool any_tc = is_tc(m->desc.precision);
   if (any_tc)
     for (auto& pb : m->tc.plane)
       if (!pb.ensure(max_pl)) return fail(SNTC_E_CUDA, "cudaMalloc failed for the fp16 activation planes");
@@ -804,21 +825,27 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
       std::string lbl = c.sources[0].kernel.substr(0, c.sources[0].kernel.size() - 7);
       if (op_on_tc(m, t, is_hyper, i)) {
         // ---- tensor-core band GEMM ----
+        bool split_here = false;
         if (!cur.hi) {   // first tensor-core layer of a chain: split the fp32 input into fp16 planes
           if (!cur.f32) return fail(SNTC_E_STATE, "executor: no input for the tensor-core layer");
           __half *hi, *lo;
           next_planes(&hi, &lo);
           size_t n8 = (size_t)B * ch * cw * c.cin / 8;
           ProfScope ps(m, s, lbl + ".split_input", 0);
-          split_planes_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>(cur.f32, hi, lo, n8);
+          TRY(m->d_flag.ensure(4));
+          CU_TRY(cudaMemsetAsync(m->d_flag.p, 0, 4, s));
+          split_planes_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>(cur.f32, hi, lo, n8, (unsigned*)m->d_flag.p);
           ctx->launches++;
           CU_TRY(cudaGetLastError());
           cur.hi = hi; cur.lo = lo;
+          split_here = true;
         }
         TcConv& tcv = (is_hyper ? m->tc.hyper : m->tc.syn)[op.conv];
         TcConvOut o;
         Cur nxt;
         bool skip_next = false;
+        if (split_here) o.alo_flag = (const unsigned*)m->d_flag.p;   // integer-valued input (z_hat): the a_lo pass is skipped
+        if (!is_hyper && m->desc.precision == SNTC_PRECISION_TC_F16X3_SYN2) o.pass_mask = 1u;   // a_lo*w_hi + a_hi*w_hi
         const bool next_tc = !last && op_on_tc(m, t, is_hyper, i + 1);
         if (last && hf) {
           o.hyper_final = true; o.q = hf->q; o.q_kind = hf->q_kind; o.Cy = hf->Cy; o.max_index = hf->max_index; o.trunc = hf->trunc;
@@ -890,6 +917,7 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         ProfScope ps(m, s, skip_next ? lbl + "+activation" : lbl, conv_macs(c, B, ch, cw));
         if (tc_run_conv(ctx->tc, c, tcv, cur.hi, cur.lo, B, ch, cw, o, s, &ctx->launches, &err) != TC_OK)
           return fail(SNTC_E_CUDA, "tensor-core path: " + err);
+        ctx->kinds[SNTC_LAUNCH_BAND_TC]++;
         ch *= c.s; cw *= c.s; cc = c.cout;
         cur = nxt;
         if (skip_next) { cc = o.C1; ++i; }
@@ -904,6 +932,7 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
         if (tail_tc_run(ctx->tc, c, tt, tt.bias, cur.hi, cur.lo, B, ch, cw, to, s, &ctx->launches, &err) != TC_OK)
           return fail(SNTC_E_CUDA, "tensor-core tail: " + err);
+        ctx->kinds[SNTC_LAUNCH_TAIL_TC]++;
         ch *= c.s; cw *= c.s; cc = c.cout;
         cur = Cur{};
         continue;
@@ -914,8 +943,10 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         if (fin) { to.f32 = fin->full; to.u8 = fin->u8; to.crop = fin->crop; to.H = fin->H; to.W = fin->W; }
         std::string err;
         ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
-        if (tail_mma_run(ctx->tc, c, m->tail_mma[op.conv], cur.f32, B, ch, cw, to, tc_pdl(), s, &ctx->launches, &err) != 0)
+        if (tail_mma_run(ctx->tc, c, m->tail_mma[op.conv], cur.f32, B, ch, cw, to, tc_pdl(), s, &ctx->launches, &err,
+                         m->desc.precision != SNTC_PRECISION_TC_F16X3_SYN2) != 0)
           return fail(SNTC_E_CUDA, "warp-MMA tail: " + err);
+        ctx->kinds[SNTC_LAUNCH_TAIL_MMA]++;
         ch *= c.s; cw *= c.s; cc = c.cout;
         cur = Cur{};
         continue;
@@ -959,6 +990,7 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         // a 1x1 "image" row of B*ch*cw pixels would overflow the TMA box arithmetic for large batches: keep [B,ch,cw]
         if (tc_run_conv(ctx->tc, tg.conv, tg.tc, cur.hi, cur.lo, B, ch, cw, o, s, &ctx->launches, &err) != TC_OK)
           return fail(SNTC_E_CUDA, "tensor-core GDN: " + err);
+        ctx->kinds[SNTC_LAUNCH_BAND_TC]++;
         cur = nxt;
         continue;
       }
@@ -975,10 +1007,7 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
       if (op.gdn >= 0) { const GdnLayer& g = t.gdns[op.gdn]; P.beta = g.d_beta; P.gamma = g.d_gamma; P.gamma_stride = g.Npad; P.inverse = g.inverse; }
       if (C > 64) return fail(SNTC_E_UNSUPPORTED, "two-layer hidden width > 64");
       ProfScope ps(m, s, "synthesis.activation+res", (double)P.npix * C * C);
-      size_t smem = ((size_t)C * C + C + 128 * (C + 1)) * 4;
-      act_res_kernel<<<(unsigned)((P.npix + 127) / 128), 128, smem, s>>>(P);
-      ctx->launches++;
-      CU_TRY(cudaGetLastError());
+      TRY(launch_act_res(ctx, P, s));
       cur = Cur{}; cur.f32 = dst; cc = C;
     }
   }
@@ -1118,7 +1147,7 @@ static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tenso
   }
   if (m->has_hyper) {
     bool fused = false;
-    const bool tc = m->desc.precision == SNTC_PRECISION_TC_F16X3;
+    const bool tc = is_tc(m->desc.precision);
     if (tc && op_on_tc(m, m->hyper, true, m->hyper.ops.size() - 1)) {
       // tensor-core path: split/exp/clamp/round and q + mu are the epilogue of the last hyper-synthesis GEMM
       HyperFuse hf;
@@ -1178,7 +1207,9 @@ static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tenso
   } else {
     CU_TRY(cudaEventRecord(m->ev[1], s));
     if (q_kind == 0) {
-      d_yhat = const_cast<void*>(d_q);   // y_hat = q, already float32
+      // y_hat = q, already float32; a caller-owned device out_yhat still has to receive it
+      if (out_yhat && on_device(out_yhat) && d_yhat != d_q) CU_TRY(cudaMemcpyAsync(d_yhat, d_q, n_lat * 4, cudaMemcpyDeviceToDevice, s));
+      d_yhat = const_cast<void*>(d_q);
     } else {
       convert_q_kernel<<<(unsigned)((n_lat / 4 + 255) / 256), 256, 0, s>>>(d_q, q_kind, (float*)d_yhat, n_lat / 4);
       ctx->launches++;
@@ -1269,7 +1300,7 @@ extern "C" int sntc_decode_hyper(sntc_model* m, const sntc_tensor* z_hat, sntc_t
   TRY(stage_out(m, out_idx, n_lat, m->st_idx, &d_idx));
   TRY(m->d_mu.ensure(n_lat * 4));
   bool fused = false;
-  if (m->desc.precision == SNTC_PRECISION_TC_F16X3 && op_on_tc(m, m->hyper, true, m->hyper.ops.size() - 1)) {
+  if (is_tc(m->desc.precision) && op_on_tc(m, m->hyper, true, m->hyper.ops.size() - 1)) {
     HyperFuse hf;
     hf.q = nullptr; hf.q_kind = 3; hf.Cy = Cy; hf.max_index = (float)(m->desc.num_scales - 1);
     hf.trunc = m->desc.index_rounding == SNTC_INDEX_TRUNC;
@@ -1342,8 +1373,9 @@ extern "C" int sntc_decode_latents(sntc_model* m, const sntc_tensor* q_y, int H,
   }
   {
     ProfScope ps(m, s, "dequant_planes", 0);
-    const size_t n8 = n_lat / 8;
-    dequant_planes_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>((const float*)m->d_mu.p, d_q, q_kind, n8, d_yhat, hi, lo);
+    const size_t n8 = (n_lat + 7) / 8;   // n_lat % 4 == 0 (model_create); the last thread may own a 4-element tail
+    if (hi && n_lat % 8 != 0) return fail(SNTC_E_UNSUPPORTED, "sntc_decode_latents: the fp16 planes need a multiple of 8 latent elements");
+    dequant_planes_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>((const float*)m->d_mu.p, d_q, q_kind, n_lat, d_yhat, hi, lo);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
   }

@@ -565,20 +565,22 @@ __global__ void dequant_index_kernel(const DequantParams P) {
 
 // Phase 2 of the two-phase decode: y_hat = q + mu (mshyper/models.py:278) from the mu kept by phase 1; writes fp32
 // and/or the fp16 hi/lo planes the tensor-core synthesis reads.  One thread per 8 elements.
-__global__ void dequant_planes_kernel(const float* __restrict__ mu, const void* __restrict__ q, int kind, size_t n8,
+__global__ void dequant_planes_kernel(const float* __restrict__ mu, const void* __restrict__ q, int kind, size_t n,
                                       float* __restrict__ y_hat, __half* __restrict__ hi, __half* __restrict__ lo) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n8) return;
   const size_t e = i * 8;
-  const float4 m0 = __ldg(reinterpret_cast<const float4*>(mu + e)), m1 = __ldg(reinterpret_cast<const float4*>(mu + e + 4));
-  const float4 q0 = load_q4(q, kind, e), q1 = load_q4(q, kind, e + 4);
+  if (e >= n) return;
+  const bool full = e + 8 <= n;   // n % 4 == 0: the last thread may hold 4 elements only (fp32 output only, see the caller)
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 m0 = __ldg(reinterpret_cast<const float4*>(mu + e)), m1 = full ? __ldg(reinterpret_cast<const float4*>(mu + e + 4)) : z4;
+  const float4 q0 = load_q4(q, kind, e), q1 = full ? load_q4(q, kind, e + 4) : z4;
   const float y[8] = {__fadd_rn(q0.x, m0.x), __fadd_rn(q0.y, m0.y), __fadd_rn(q0.z, m0.z), __fadd_rn(q0.w, m0.w),
                       __fadd_rn(q1.x, m1.x), __fadd_rn(q1.y, m1.y), __fadd_rn(q1.z, m1.z), __fadd_rn(q1.w, m1.w)};
   if (y_hat) {
     *reinterpret_cast<float4*>(y_hat + e) = make_float4(y[0], y[1], y[2], y[3]);
-    *reinterpret_cast<float4*>(y_hat + e + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    if (full) *reinterpret_cast<float4*>(y_hat + e + 4) = make_float4(y[4], y[5], y[6], y[7]);
   }
-  if (hi) {
+  if (hi && full) {
     __align__(16) __half h[8];
     __align__(16) __half l[8];
 #pragma unroll

@@ -76,7 +76,8 @@ __device__ __forceinline__ uint32_t tm_pixel(float x) {
 // Persistent CTAs (3 per SM) loop over the tiles.  The fp32 halo tile of t arrives by ONE TMA tiled load per tile
 // (4-D map (c, x, y, b), box (C1, 66, 10, 1); out-of-image coordinates are zero-filled = the conv padding) into a raw
 // staging buffer; the load of tile n+1 is issued as soon as tile n has been converted, so it overlaps the MMA phase.
-template <int C1, bool FAST>
+// WLO = false drops the t_hi * w_lo cross term (SNTC_PRECISION_TC_F16X3_SYN2: 30 instead of 45 MMAs per row step).
+template <int C1, bool FAST, bool WLO = true>
 __global__ void __launch_bounds__(TM_THREADS, 3) tail_s2_mma_kernel(const __grid_constant__ CUtensorMap mapT, const TailMmaParams Q) {
   static_assert(C1 % 4 == 0 && C1 <= 16, "one K=16 step per tap");
   constexpr int NPX = TM_TYH * TM_TXH;
@@ -195,17 +196,19 @@ __global__ void __launch_bounds__(TM_THREADS, 3) tail_s2_mma_kernel(const __grid
           if (f == 0 || f == 6) {
             tm_mma16816_first(acc[nt][0], a[0], wf[f][0]);        // hi * hi
             tm_mma16816_first(acc[nt][1], a[1], wf[f][0]);        // lo * hi
-            tm_mma16816_first(acx[nt], a[0], wf[f][1]);           // hi * lo
+            if (WLO) tm_mma16816_first(acx[nt], a[0], wf[f][1]);  // hi * lo
           } else {
             tm_mma16816(acc[nt][0], a[0], wf[f][0]);
             tm_mma16816(acc[nt][1], a[1], wf[f][0]);
-            tm_mma16816(acx[nt], a[0], wf[f][1]);
+            if (WLO) tm_mma16816(acx[nt], a[0], wf[f][1]);
           }
         }
+        if (WLO) {
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+          for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[nt][1][e] += acx[nt][e];
+            for (int e = 0; e < 4; ++e) acc[nt][1][e] += acx[nt][e];
+        }
       }
       const int ty = ty0 + i;
       if (ty >= Q.hin) continue;
@@ -321,8 +324,19 @@ inline size_t tail_mma_smem(int C1) {
   return 128 + raw + (size_t)2 * 2 * TM_TYH * TM_TXH * 16 + 16;
 }
 
+template <int C1, bool FAST, bool WLO>
+inline cudaError_t tail_mma_launch(const cudaLaunchConfig_t& cfg, const CUtensorMap& mapT, const TailMmaParams& Q, size_t smem) {
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tail_s2_mma_kernel<C1, FAST, WLO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<C1, FAST, WLO>, mapT, Q);
+}
+
 inline int tail_mma_run(TcDriver& drv, const ConvLayer& c, TailMma& t, const float* in, int B, int h, int w, const TailMmaOut& o, bool pdl,
-                        cudaStream_t s, uint64_t* launches, std::string* err) {
+                        cudaStream_t s, uint64_t* launches, std::string* err, bool w_lo = true) {
   if (!drv.encode) { *err = "cuTensorMapEncodeTiled unavailable"; return 2; }
   TailMmaParams Q{};
   Q.x = in; Q.B = B; Q.hin = h; Q.win = w; Q.wfrag = t.d_wfrag; Q.inv_scale = 1.f / t.scale;
@@ -342,16 +356,15 @@ inline int tail_mma_run(TcDriver& drv, const ConvLayer& c, TailMma& t, const flo
   }
   const size_t smem = tail_mma_smem(c.cin);
   if (!t.attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tail_s2_mma_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_mma_smem(12));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_s2_mma_kernel<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_mma_smem(12));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_s2_mma_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_mma_smem(16));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_s2_mma_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_mma_smem(16));
-    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute (tail): ") + cudaGetErrorString(e); return 2; }
     t.attr_set = true;
     int n = 0;
-    e = c.cin == 12 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tail_s2_mma_kernel<12, true>, TM_THREADS, smem)
-                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tail_s2_mma_kernel<16, true>, TM_THREADS, smem);
+    cudaError_t e = cudaFuncSetAttribute(tail_s2_mma_kernel<12, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_mma_smem(12));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_s2_mma_kernel<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_mma_smem(16));
+    if (e == cudaSuccess)
+      e = c.cin == 12 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tail_s2_mma_kernel<12, true, true>, TM_THREADS, smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tail_s2_mma_kernel<16, true, true>, TM_THREADS, smem);
     t.ctas_per_sm = (e == cudaSuccess && n > 0) ? n : 1;
+    cudaGetLastError();
   }
   const int ntiles = ((w + TM_TX - 1) / TM_TX) * ((h + TM_RW - 1) / TM_RW) * B;
   if (ntiles <= 0) return 0;
@@ -364,8 +377,17 @@ inline int tail_mma_run(TcDriver& drv, const ConvLayer& c, TailMma& t, const flo
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
   const bool fast = o.u8 && !o.f32 && !o.crop && (o.W % 2) == 0;
   cudaError_t e;
-  if (c.cin == 12) e = fast ? cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<12, true>, mapT, Q) : cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<12, false>, mapT, Q);
-  else e = fast ? cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<16, true>, mapT, Q) : cudaLaunchKernelEx(&cfg, tail_s2_mma_kernel<16, false>, mapT, Q);
+  const int variant = (c.cin == 12 ? 0 : 4) + (fast ? 2 : 0) + (w_lo ? 1 : 0);
+  switch (variant) {
+    case 0: e = tail_mma_launch<12, false, false>(cfg, mapT, Q, smem); break;
+    case 1: e = tail_mma_launch<12, false, true>(cfg, mapT, Q, smem); break;
+    case 2: e = tail_mma_launch<12, true, false>(cfg, mapT, Q, smem); break;
+    case 3: e = tail_mma_launch<12, true, true>(cfg, mapT, Q, smem); break;
+    case 4: e = tail_mma_launch<16, false, false>(cfg, mapT, Q, smem); break;
+    case 5: e = tail_mma_launch<16, false, true>(cfg, mapT, Q, smem); break;
+    case 6: e = tail_mma_launch<16, true, false>(cfg, mapT, Q, smem); break;
+    default: e = tail_mma_launch<16, true, true>(cfg, mapT, Q, smem); break;
+  }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("tail_s2_mma_kernel launch: ") + cudaGetErrorString(e); return 2; }
   if (launches) (*launches)++;

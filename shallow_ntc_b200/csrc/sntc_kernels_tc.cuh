@@ -86,6 +86,11 @@ struct TcParams {
   // is a constant-bank operand of its FFMA (no shared-memory loads in the per-pixel IGDN)
   float tl_gamma[24 * 24]; float tl_beta[24]; float tl_bias[48];
   long long* trace;   // debug timeline (SNTC_TC_TRACE=1): [unit][TC_TRACE_ITEMS][8] clock64 stamps, leader CTA only
+  // Which of the two cross terms of the split product are issued (hi*hi always is): bit 0 = a_lo * w_hi, bit 1 = a_hi * w_lo.
+  // 3 = the fp32-class 3-pass product (default).  A plane that is not needed is not loaded either.
+  // alo_flag (nullable, device): written by split_planes_kernel, non-zero iff some element of the A lo plane is non-zero;
+  // when it reads 0 (integer-valued input such as z_hat: exact in fp16) bit 0 is cleared -- the result is bit-identical.
+  unsigned pass_mask; const unsigned* alo_flag;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -842,6 +847,9 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem_base = tcx::smem_u32(smem);
   tcx::pdl_wait();   // everything above only touched weights / our own smem; from here on we read the previous layer's output
+  unsigned pmask = P.pass_mask;
+  if (P.alo_flag != nullptr && *reinterpret_cast<const volatile unsigned*>(P.alo_flag) == 0u) pmask &= ~1u;
+  const bool use_alo = (pmask & 1u) != 0, use_blo = (pmask & 2u) != 0;
 
   if (warp == 0) {
     // ===== TMA producer: the whole warp runs the (uniform) loop, one elected lane issues the copies.
@@ -853,7 +861,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
       const int Ty = bd.Ty, Tx = bd.Tx;
       const int wrows = bd.BN / CG;                                  // W box rows per CTA
       const int wrow0 = it.n0 + rank * (it.mma_n / CG);              // this CTA supplies columns [rank*mma_n/CG, ...)
-      const uint32_t tx_bytes = (uint32_t)CG * (2 * a_bytes + 2 * (uint32_t)wrows * 128);
+      const uint32_t tx_bytes = (uint32_t)CG * ((use_alo ? 2u : 1u) * a_bytes + (use_blo ? 2u : 1u) * (uint32_t)wrows * 128);
       const int cx0 = bd.mlox + it.ix0, cy0 = bd.mloy + it.iy0;
       int kcol = 0;
       const int jt = (item - unit0) / nunits;
@@ -870,15 +878,15 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
                 if (leader) tcx::mbar_expect_tx(&full_bar[st], tx_bytes);
                 const uint32_t fb = tcx::mapa_u32(tcx::smem_u32(&full_bar[st]), 0);   // the leader's full barrier
                 tcx::tma_load_4d_2sm(sa, &mapAhi, fb, cc, cx, cy, it.b);
-                tcx::tma_load_4d_2sm(sa + a_bytes, &mapAlo, fb, cc, cx, cy, it.b);
+                if (use_alo) tcx::tma_load_4d_2sm(sa + a_bytes, &mapAlo, fb, cc, cx, cy, it.b);
                 tcx::tma_load_2d_2sm(sa + 2 * a_bytes, &bd.mapBhi, fb, kcol, wrow0);
-                tcx::tma_load_2d_2sm(sa + 2 * a_bytes + b_slot, &bd.mapBlo, fb, kcol, wrow0);
+                if (use_blo) tcx::tma_load_2d_2sm(sa + 2 * a_bytes + b_slot, &bd.mapBlo, fb, kcol, wrow0);
               } else {
                 tcx::mbar_expect_tx(&full_bar[st], tx_bytes);
                 tcx::tma_load_4d(sa, &mapAhi, &full_bar[st], cc, cx, cy, it.b);
-                tcx::tma_load_4d(sa + a_bytes, &mapAlo, &full_bar[st], cc, cx, cy, it.b);
+                if (use_alo) tcx::tma_load_4d(sa + a_bytes, &mapAlo, &full_bar[st], cc, cx, cy, it.b);
                 tcx::tma_load_2d(sa + 2 * a_bytes, &bd.mapBhi, &full_bar[st], kcol, wrow0);
-                tcx::tma_load_2d(sa + 2 * a_bytes + b_slot, &bd.mapBlo, &full_bar[st], kcol, wrow0);
+                if (use_blo) tcx::tma_load_2d(sa + 2 * a_bytes + b_slot, &bd.mapBlo, &full_bar[st], kcol, wrow0);
               }
             }
             __syncwarp();
@@ -915,7 +923,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
             const int nm = (kb == P.kblocks - 1) ? P.last_kmma : 4;
             if (tcx::elect_one()) {
               // lo*hi and hi*lo first (small terms), hi*hi last
-              if (nm == 4) {
+              if (nm == 4 && pmask == 3u) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_lo + 2 * q, desc_hi), tcx::desc64(b_hi + 2 * q, desc_hi), idesc, q == 0 ? acc : 1u); }
 #pragma unroll
@@ -923,9 +931,10 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
 #pragma unroll
                 for (int q = 0; q < 4; ++q) tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_hi + 2 * q, desc_hi), tcx::desc64(b_hi + 2 * q, desc_hi), idesc, 1u);
               } else {
-                for (int q = 0; q < nm; ++q) { tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_lo + 2 * q, desc_hi), tcx::desc64(b_hi + 2 * q, desc_hi), idesc, q == 0 ? acc : 1u); }
-                for (int q = 0; q < nm; ++q) tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_hi + 2 * q, desc_hi), tcx::desc64(b_lo + 2 * q, desc_hi), idesc, 1u);
-                for (int q = 0; q < nm; ++q) tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_hi + 2 * q, desc_hi), tcx::desc64(b_hi + 2 * q, desc_hi), idesc, 1u);
+                uint32_t a1 = acc;   // accumulate flag of the next MMA: 0 only for the very first MMA of the work item
+                if (use_alo) for (int q = 0; q < nm; ++q) { tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_lo + 2 * q, desc_hi), tcx::desc64(b_hi + 2 * q, desc_hi), idesc, a1); a1 = 1u; }
+                if (use_blo) for (int q = 0; q < nm; ++q) { tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_hi + 2 * q, desc_hi), tcx::desc64(b_lo + 2 * q, desc_hi), idesc, a1); a1 = 1u; }
+                for (int q = 0; q < nm; ++q) { tcx::umma_f16_t<CG>(tacc, tcx::desc64(a_hi + 2 * q, desc_hi), tcx::desc64(b_hi + 2 * q, desc_hi), idesc, a1); a1 = 1u; }
               }
               if (CG == 2) tcx::umma_commit_2sm(&empty_bar[st], 3);   // frees this smem stage in both CTAs
               else tcx::umma_commit(&empty_bar[st]);
@@ -1084,14 +1093,23 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
   if (warp == 2) { if (CG == 2) tcx::tmem_dealloc_2sm(tmem_base, 2 * TC_ACC_COLS); else tcx::tmem_dealloc(tmem_base, 2 * TC_ACC_COLS); }
 }
 
-// f32 NHWC -> fp16 hi/lo planes (input of the first tensor-core layer)
-__global__ void split_planes_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t n8) {
+// f32 NHWC -> fp16 hi/lo planes (input of the first tensor-core layer).  lo_flag (nullable, zeroed by the caller) is set
+// to 1 when any lo element is non-zero: an all-zero lo plane (integer-valued symbols) lets the layer skip its a_lo * w_hi pass.
+__global__ void split_planes_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t n8, unsigned* lo_flag) {
   tcx::pdl_launch_dependents();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n8) return;
-  float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
-  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  store8_planes(hi, lo, i * 8, v);
+  bool nz = false;
+  if (i < n8) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { split_f16(v[k], h[k], l[k]); nz = nz || (__half_as_ushort(l[k]) & 0x7FFFu) != 0; }
+    *reinterpret_cast<uint4*>(hi + i * 8) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + i * 8) = *reinterpret_cast<const uint4*>(l);
+  }
+  if (lo_flag != nullptr && __any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(lo_flag, 1u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1434,6 +1452,7 @@ struct TcConvOut {
   const float* h_gamma = nullptr; const float* h_beta = nullptr;   // host copies ([C1][C1], [C1]) -> kernel parameters
   // GDN stages (see TcParams): pooled planes out / norm-pool GEMM epilogue
   int plane_xform = A_NONE; int gdn_mode = G_NONE; const float* gx = nullptr;
+  unsigned pass_mask = 3u; const unsigned* alo_flag = nullptr;   // see TcParams
 };
 
 inline void tc_choose_patch(int h, int w, int* TH, int* TW) {
@@ -1518,6 +1537,7 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   }
   P.rate_slots = o.rate_slots; P.rate_slot_img = o.rate_slot_img; P.rc = o.rc; P.sigma_out = o.sigma_out;
   P.plane_xform = o.plane_xform; P.gdn_mode = o.gdn_mode; P.gx = o.gx;
+  P.pass_mask = o.pass_mask & 3u; P.alo_flag = o.alo_flag;
   {
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
     bool ok = c.cout % 16 == 0 && (!o.hyper_final || o.Cy % 16 == 0) && !o.two_layer && !o.u8 && !o.crop;

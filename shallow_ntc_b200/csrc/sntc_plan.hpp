@@ -266,7 +266,9 @@ inline Transform build_transform(const sntc_transform_desc& d, const std::string
       for (int i = 0; i < nl; ++i) {
         bool last = i + 1 == nl;
         add_conv(make_conv(prefix, "layer_" + std::to_string(i), 5, 2, cin, last ? Co : C, LAYOUT_TFC_IO, true, SNTC_ACT_NONE));
-        if (!last) add_gdn("igdn_" + std::to_string(i), C, GDN_CLASSIC, true);
+        // tfc.GDN(inverse=True) with the tfc 2.x defaults alpha_parameter = epsilon_parameter = 1 is IGDN1 (see sntc.h,
+        // SNTC_ACT_IGDN_CLASSIC); the (alpha=2, epsilon=.5) form only on request
+        if (!last) add_gdn("igdn_" + std::to_string(i), C, d.activation == SNTC_ACT_IGDN_CLASSIC ? GDN_CLASSIC : GDN_1, true);
         cin = C; up *= 2;
       }
       t.out_channels = Co; t.upsample = up;

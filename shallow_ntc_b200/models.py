@@ -17,11 +17,16 @@ from ._lib import lib, check, ModelDesc, TransformDesc, ImageMetrics, ImageRate
 from .tensors import Context, as_tensor, empty_like_kind, DeviceArray
 from .transforms import class_builder as transform_builder
 
+# Scale-table row rule.  tfc 2.10 ContinuousIndexedEntropyModel._flatten_indexes is tf.cast(indexes, tf.int32):
+# truncation.  'rint' stays selectable for coders that round.  The default is a deliberate choice, recorded in DESIGN.md section 5.
+DEFAULT_INDEX_ROUNDING = "trunc"
+
 # Fixed configs for the ScaleIndexedEntropyModel (mshyper/models.py:27-34).
 NUM_SCALES = 64
 SCALE_MIN = 0.11
 SCALE_MAX = 256.
-_PRECISION = {"fp32": _lib.PRECISION_FP32, "tc": _lib.PRECISION_TC_F16X3, "tc_f16x3": _lib.PRECISION_TC_F16X3}
+_PRECISION = {"fp32": _lib.PRECISION_FP32, "tc": _lib.PRECISION_TC_F16X3, "tc_f16x3": _lib.PRECISION_TC_F16X3,
+              "tc_syn2": _lib.PRECISION_TC_F16X3_SYN2}   # opt-in: 2-pass synthesis layers (see include/sntc.h)
 _ROUNDING = {"rint": _lib.INDEX_RINT, "trunc": _lib.INDEX_TRUNC}
 
 
@@ -48,7 +53,7 @@ class _NativeModel:
 
 
 def _create_model(ctx: Context, hyper: TransformDesc, syn: TransformDesc, weights: dict, precision="fp32",
-                  index_rounding="rint", num_scales=NUM_SCALES, prior=False) -> _NativeModel:
+                  index_rounding=DEFAULT_INDEX_ROUNDING, num_scales=NUM_SCALES, prior=False) -> _NativeModel:
   desc = ModelDesc(struct_size=C.sizeof(ModelDesc), hyper=hyper, synthesis=syn, num_scales=num_scales,
                    index_rounding=_ROUNDING[index_rounding], precision=_PRECISION[precision],
                    prior=_lib.PRIOR_DEEP_FACTORIZED if prior else _lib.PRIOR_NONE)
@@ -84,7 +89,7 @@ class Model:
   factorized-prior model (``factorized/models.py``: no z, no scale indexes, DOWNSAMPLE_FACTOR 16)."""
 
   def __init__(self, transform_config, bottleneck_size=None, hyperprior=True, profile=False, device=0,
-               precision="fp32", index_rounding="rint", ctx: Context | None = None, prior=False, **_ignored_training_kwargs):
+               precision="fp32", index_rounding=DEFAULT_INDEX_ROUNDING, ctx: Context | None = None, prior=False, **_ignored_training_kwargs):
     self._transform_config = transform_config
     self._with_prior = bool(prior) and hyperprior    # self._prior = tfc.NoisyDeepFactorized(...)   mshyper/models.py:135
     self._profile = profile

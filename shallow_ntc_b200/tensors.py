@@ -59,6 +59,14 @@ class Context:
   def launch_count(self) -> int:
     return int(lib.sntc_launch_count(self.handle))
 
+  @property
+  def launch_counts(self) -> dict:
+    """Kernels launched so far by family (sntc_launch_counts): total, band_tc (tcgen05 band GEMM), band_f32 (FFMA band GEMM),
+    tail_mma, tail_tc, final_f32.  Lets a caller see which path served a ``precision='tc'`` model."""
+    out = (C.c_uint64 * len(_lib.LAUNCH_KINDS))()
+    check(lib.sntc_launch_counts(self.handle, out))
+    return {k: int(out[i]) for i, k in enumerate(_lib.LAUNCH_KINDS)}
+
   def msssim(self, a_u8, b_u8):
     """Per-image MS-SSIM of two uint8 batches [B,H,W,C] (numpy, DeviceArray, DLPack ...) computed on the device the way
     the reference's validation branch does (mshyper/models.py:321-332: tf.image.ssim_multiscale(max_val=255.), or

@@ -269,10 +269,16 @@ class TwoLayerResSynthesis(TwoLayerSynthesis):
 
 
 class MBT2018Synthesis(Transform):
-  """common/transforms.py:158-175."""
+  """common/transforms.py:158-175.  Its activations are ``tfc.GDN(inverse=True)`` with the library defaults, which in
+  tensorflow-compression 2.x are alpha_parameter = epsilon_parameter = 1: the same function as ``GDN1(inverse=True)``
+  (x * (beta + |x| @ gamma)).  ``gdn_form="classic"`` (an extension, not a reference kwarg) selects the original
+  x * sqrt(beta + x^2 @ gamma) for weights trained with ``tfc.GDN(alpha_parameter=2, epsilon_parameter=.5)``."""
 
-  def __init__(self, channels_base, n_layers=4, output_channels=3):
+  def __init__(self, channels_base, n_layers=4, output_channels=3, *, gdn_form="gdn1"):
     super().__init__()
+    if gdn_form not in ("gdn1", "classic"):
+      raise ValueError(f"gdn_form={gdn_form!r}")
+    self.gdn_form = gdn_form
     self.channels_base, self.n_layers = int(channels_base), int(n_layers)
     self.output_channels = int(output_channels) if output_channels is not None else int(channels_base)
     self.upsample = 2 ** self.n_layers
@@ -282,7 +288,8 @@ class MBT2018Synthesis(Transform):
     return self.output_channels
 
   def desc(self, in_channels):
-    d = TransformDesc(kind=_lib.T_MBT2018, in_channels=in_channels, n_layers=self.n_layers)
+    d = TransformDesc(kind=_lib.T_MBT2018, in_channels=in_channels, n_layers=self.n_layers,
+                      activation=_lib.ACT_IGDN_CLASSIC if self.gdn_form == "classic" else _lib.ACT_NONE)
     d.channels[0], d.channels[1] = self.channels_base, self.output_channels
     return d
 

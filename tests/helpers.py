@@ -26,8 +26,10 @@ def hyper_kwargs(model):
   return cfg["cls"], {k: v for k, v in cfg.items() if k not in ("cls", "bottleneck_size")}
 
 
-def make_case(name, B, H, W, kind="stress", precision="fp32", ctx=None, first_index=0, index_rounding="rint"):
-  model = build_config(name, precision=precision, ctx=ctx, index_rounding=index_rounding)
+def make_case(name, B, H, W, kind="stress", precision="fp32", ctx=None, first_index=0, index_rounding=None, **model_kw):
+  if index_rounding is not None:
+    model_kw["index_rounding"] = index_rounding
+  model = build_config(name, precision=precision, ctx=ctx, **model_kw)
   cls, _ = syn_kwargs(model)
   wts = synthetic.make_weights(model.variable_shapes(), kind, synthesis_cls=cls)
   model.load_weights(wts)
@@ -36,8 +38,9 @@ def make_case(name, B, H, W, kind="stress", precision="fp32", ctx=None, first_in
   return model, wts, z, q
 
 
-def oracle_decode(model, wts, z, q, H, W, original=None, dtype=np.float64, gemm_form=False, index_rounding="rint"):
+def oracle_decode(model, wts, z, q, H, W, original=None, dtype=np.float64, gemm_form=False, index_rounding=None):
   cls, kw = syn_kwargs(model)
+  index_rounding = index_rounding or model.index_rounding
   if model.hyperprior:
     hcls, hkw = hyper_kwargs(model)
     return O.mshyper_decode(wts, cls, z, q, H, W, kw, hcls, hkw, original, dtype, gemm_form, index_rounding)

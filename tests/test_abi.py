@@ -34,7 +34,8 @@ def test_struct_layouts_match_the_header():
   assert ctypes.sizeof(_lib.ImageMetrics) == 24
   assert ctypes.sizeof(_lib.ImageRate) == 16
   assert _lib.ModelDesc.prior.offset == 4 + 2 * 48 + 12
-  assert _lib.lib.sntc_version() == 101
+  hdr = open(os.path.join(ROOT, "include", "sntc.h")).read()
+  assert _lib.lib.sntc_version() == int(re.search(r"#define SNTC_VERSION (\d+)", hdr).group(1))
 
 
 def test_sass_contains_tcgen05_and_tma():
