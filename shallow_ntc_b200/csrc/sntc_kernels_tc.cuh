@@ -1157,9 +1157,11 @@ struct TcConv {
   struct Tiling { std::vector<TcBandDev> bands; TcBandDev* d_bands = nullptr; int nbands = 0, bn_max = 16, stages = 2, uploaded_mtiles = -1; } narrow;
 };
 
+inline int tc_env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
 // Work items of the wide tiling for `mtiles` m-tiles; the narrow tiling is used when they leave half the units idle.
 inline bool tc_use_narrow(const TcConv& t, int mtiles, int num_sms) {
-  static const int env = [] { const char* e = getenv("SNTC_TC_NARROW"); return e ? atoi(e) : -1; }();   // 0 / 1 force, default auto
+  const int env = tc_env_int("SNTC_TC_NARROW", -1);   // 0 / 1 force, default auto
   if (t.narrow.nbands == 0 || env == 0) return false;
   if (env == 1) return true;
   const int groups = (mtiles + t.cg - 1) / t.cg;
@@ -1211,7 +1213,6 @@ struct TcModelState {
 
 // Widest n-tile (multiple of `unit`, itself a multiple of 16) that keeps >= 3 pipeline stages in 227 KB
 // and wastes the least padded columns; the last tile of a band only issues MMAs for its own columns.
-inline int tc_env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 inline int tc_bn_max() {
   static int v = -1;
   if (v < 0) { v = tc_env_int("SNTC_TC_BN_MAX", 256); if (v < 16 || v > TC_ACC_COLS) v = 256; }
@@ -1224,10 +1225,9 @@ inline bool tc_pdl() {
   if (v < 0) v = tc_env_int("SNTC_TC_PDL", 0) ? 1 : 0;
   return v != 0;
 }
-inline int tc_cta_group() {
-  static int v = -1;
-  if (v < 0) { v = tc_env_int("SNTC_TC_CTA_GROUP", 2); if (v != 1 && v != 2) v = 2; }
-  return v;
+inline int tc_cta_group() {   // read when a model is finalized (not cached: tests build both variants in one process)
+  const int v = tc_env_int("SNTC_TC_CTA_GROUP", 2);
+  return (v != 1 && v != 2) ? 2 : v;
 }
 // Fewest n-tiles of at most bn_max columns, then the narrowest (balanced) tile that achieves it; tiles are
 // multiples of `unit`.  The last tile of a band only issues MMAs for its own columns.

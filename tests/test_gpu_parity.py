@@ -27,10 +27,17 @@ def test_decode_matches_oracle(gpu_ctx, name, B, H, W, kind, precision):
   ref = oracle_decode(model, wts, z, q, H, W)
   orig = synthetic.make_original(ref["recon_u8"])
   ref_mse, ref_psnr = __import__("oracle.ntc_oracle", fromlist=["x"]).mse_psnr(orig, ref["recon_u8"])
+  n0 = gpu_ctx.launch_counts
   got = model.decompress(z, q, (H, W), return_float=True, return_yhat=True, original=orig)
+  n = {k: v - n0[k] for k, v in gpu_ctx.launch_counts.items()}
   rep = check_against_oracle(got, ref, hyper=model.hyperprior, precision=precision)
   assert np.all(np.abs(got["psnr"] - ref_psnr) < PSNR_TOL), (got["psnr"], ref_psnr)
-  print(name, kind, precision, rep)
+  # which kernels served the call: a 'tc' model must not fall back to FFMA silently, an 'fp32' model never touches tcgen05
+  if precision == "tc":
+    assert n["band_tc"] >= 1 and n["band_f32"] == 0 and n["final_f32"] == 0, n
+  else:
+    assert n["band_tc"] == 0 and n["tail_mma"] == 0 and n["tail_tc"] == 0 and n["band_f32"] >= 1, n
+  print(name, kind, precision, rep, n)
 
 
 def test_yhat_is_bit_exact_single_add(gpu_ctx):
