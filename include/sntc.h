@@ -278,6 +278,10 @@ int sntc_launch_counts(sntc_ctx* ctx, uint64_t out[SNTC_LAUNCH_KINDS]);
 int sntc_malloc(sntc_ctx* ctx, size_t bytes, void** out);
 int sntc_free(sntc_ctx* ctx, void* p);
 int sntc_host_alloc(sntc_ctx* ctx, size_t bytes, void** out); /* pinned */
+/* pinned, with flags: SNTC_HOST_WRITE_COMBINED = cudaHostAllocWriteCombined -- for staging buffers the host only WRITES (the
+ * symbols on their way up): not snooped, so the device reads them faster over PCIe; host reads from such memory are very slow. */
+#define SNTC_HOST_WRITE_COMBINED 1
+int sntc_host_alloc_flags(sntc_ctx* ctx, size_t bytes, unsigned flags, void** out);
 int sntc_host_free(sntc_ctx* ctx, void* p);
 int sntc_memcpy_h2d(sntc_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream);
 int sntc_memcpy_d2h(sntc_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream);
@@ -288,6 +292,25 @@ int sntc_stream_create(sntc_ctx* ctx, void** out);
 int sntc_stream_destroy(sntc_ctx* ctx, void* stream);
 int sntc_stream_wait_event(sntc_ctx* ctx, void* stream, void* event); /* stream == NULL: the context stream */
 int sntc_stream_sync(sntc_ctx* ctx, void* stream);
+
+/* ---- multi-GPU: the ONE collective of the path ----
+ * Images are independent units: ranks never exchange data on the decode path.  What the reference does after the loop is an
+ * arithmetic mean of per-image metrics (mshyper/models.py:300-317, common/train_lib.py:64-68); with one process per GPU that is
+ * one all-reduce(sum) of [sum psnr, sum mse, sum bits_y, sum bits_z, n_images] over NCCL (NVLink 5 / NVSwitch; 40 bytes: latency
+ * only).  libsntc resolves NCCL with dlopen("libnccl.so.2") on first use -- no link-time dependency, no PyTorch.
+ *   rank 0: sntc_comm_unique_id(id) -> hand the 128 bytes to every rank (file, socket, MPI, the launcher's store ...)
+ *   all   : sntc_comm_create(ctx, id, rank, world, &comm)            (ncclCommInitRank on the context's device)
+ *   all   : sntc_allreduce_metrics(comm, sums)  /  sntc_comm_allreduce_f64(comm, v, n, op)  (in place, host doubles; returns
+ *           after the result is back in host memory; op SNTC_REDUCE_SUM / SNTC_REDUCE_MAX; n <= 4096) */
+#define SNTC_COMM_ID_BYTES 128
+#define SNTC_REDUCE_SUM 0
+#define SNTC_REDUCE_MAX 1
+typedef struct sntc_comm sntc_comm;
+int sntc_comm_unique_id(void* id128);
+int sntc_comm_create(sntc_ctx* ctx, const void* id128, int rank, int world, sntc_comm** out);
+int sntc_comm_destroy(sntc_comm* comm);
+int sntc_comm_allreduce_f64(sntc_comm* comm, double* values, int n, int op);
+int sntc_allreduce_metrics(sntc_comm* comm, double sums[5]);
 
 /* ---- CUDA-event timers on the launching stream (bench.py) ---- */
 int sntc_event_create(sntc_ctx* ctx, void** out);

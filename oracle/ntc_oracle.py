@@ -309,13 +309,16 @@ def scale_indexes(raw_sigma, index_rounding="trunc"):
   of i_c to the nearest rounding boundary -- used for the tie margin of SURVEY F8)."""
   i_f = np.exp(np.asarray(raw_sigma, dtype=np.float64))
   i_c = np.minimum(np.maximum(i_f, 0.0), NUM_SCALES - 1.0)
+  top = NUM_SCALES - 1.0
   if index_rounding == "rint":
     idx = np.rint(i_c)
-    dist = np.abs(np.abs(i_c - np.floor(i_c)) - 0.5)
+    # boundaries k + .5, k = 0 .. S-2; above the clamp only the last one (S - 1.5) is near
+    dist = np.where(i_f >= top, i_f - (top - 0.5), np.abs(np.abs(i_c - np.floor(i_c)) - 0.5))
   elif index_rounding == "trunc":
     idx = np.floor(i_c)
+    # boundaries are the integers 1 .. S-1: below 1 only 1 is a boundary (exp > 0), above the clamp only S-1
     frac = i_c - np.floor(i_c)
-    dist = np.minimum(frac, 1.0 - frac)
+    dist = np.where(i_f >= top, i_f - top, np.where(i_f < 1.0, 1.0 - i_f, np.minimum(frac, 1.0 - frac)))
   else:
     raise ValueError(index_rounding)
   return i_c, idx.astype(np.uint8), dist

@@ -23,6 +23,8 @@ PRECISION_FP32, PRECISION_TC_F16X3, PRECISION_TC_F16X3_SYN2 = 0, 1, 2
 LAUNCH_KINDS = ("total", "band_tc", "band_f32", "tail_mma", "tail_tc", "final_f32")   # SNTC_LAUNCH_*
 INDEX_RINT, INDEX_TRUNC = 0, 1
 PRIOR_NONE, PRIOR_DEEP_FACTORIZED = 0, 1
+HOST_WRITE_COMBINED = 1
+COMM_ID_BYTES, REDUCE_SUM, REDUCE_MAX = 128, 0, 1
 
 
 class SntcError(RuntimeError):
@@ -99,6 +101,7 @@ _PROTOS = {
   "sntc_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
   "sntc_free": (C.c_int, [_P, _P]),
   "sntc_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+  "sntc_host_alloc_flags": (C.c_int, [_P, C.c_size_t, C.c_uint, C.POINTER(_P)]),
   "sntc_host_free": (C.c_int, [_P, _P]),
   "sntc_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
   "sntc_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
@@ -107,6 +110,11 @@ _PROTOS = {
   "sntc_stream_destroy": (C.c_int, [_P, _P]),
   "sntc_stream_wait_event": (C.c_int, [_P, _P, _P]),
   "sntc_stream_sync": (C.c_int, [_P, _P]),
+  "sntc_comm_unique_id": (C.c_int, [_P]),
+  "sntc_comm_create": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+  "sntc_comm_destroy": (C.c_int, [_P]),
+  "sntc_comm_allreduce_f64": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int, C.c_int]),
+  "sntc_allreduce_metrics": (C.c_int, [_P, C.POINTER(C.c_double)]),
   "sntc_event_create": (C.c_int, [_P, C.POINTER(_P)]),
   "sntc_event_destroy": (C.c_int, [_P, _P]),
   "sntc_event_record": (C.c_int, [_P, _P, _P]),

@@ -1,6 +1,8 @@
 // libsntc.so -- C ABI implementation (see include/sntc.h).  One translation unit: host plan logic
 // (sntc_plan.hpp), fp32 CUDA-core kernels (sntc_kernels_f32.cuh), tcgen05 kernels (sntc_kernels_tc.cuh).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the entry points are resolved with dlsym (no link-time dependency on libnccl)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -180,6 +182,13 @@ extern "C" int sntc_host_alloc(sntc_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return fail(SNTC_E_INVALID, "sntc_host_alloc: bad argument");
   CU_TRY(cudaSetDevice(ctx->device));
   CU_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return SNTC_OK;
+}
+extern "C" int sntc_host_alloc_flags(sntc_ctx* ctx, size_t bytes, unsigned flags, void** out) {
+  if (!ctx || !out) return fail(SNTC_E_INVALID, "sntc_host_alloc_flags: bad argument");
+  if (flags & ~(unsigned)SNTC_HOST_WRITE_COMBINED) return fail(SNTC_E_INVALID, "sntc_host_alloc_flags: unknown flag");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaHostAlloc(out, bytes ? bytes : 1, (flags & SNTC_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
   return SNTC_OK;
 }
 extern "C" int sntc_host_free(sntc_ctx* ctx, void* p) {
@@ -1532,6 +1541,105 @@ extern "C" int sntc_image_msssim(sntc_ctx* ctx, const sntc_tensor* a_u8, const s
   msssim_combine(stats.data(), B, C, msssim_single_scale(H, W), msssim);
   return SNTC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// The one collective of the path: all-reduce of a few host doubles over NCCL (see sntc.h).
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+  bool load() {
+    if (lib) return true;
+    if (!err.empty()) return false;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { const char* e = dlerror(); err = std::string("dlopen(libnccl.so.2) failed: ") + (e ? e : "?"); return false; }
+    auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p && err.empty()) err = std::string("libnccl lacks ") + n; return p; };
+    GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+    if (!err.empty()) { dlclose(lib); lib = nullptr; return false; }
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
+struct sntc_comm {
+  sntc_ctx* ctx = nullptr;
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  double* d_buf = nullptr;   // device scratch
+  double* h_buf = nullptr;   // pinned
+};
+static constexpr int SNTC_COMM_MAX_N = 4096;
+
+#define NCCL_TRY(expr)                                                                                              \
+  do {                                                                                                              \
+    ncclResult_t r__ = (expr);                                                                                      \
+    if (r__ != ncclSuccess) return fail(SNTC_E_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(r__));        \
+  } while (0)
+
+extern "C" int sntc_comm_unique_id(void* id128) {
+  if (!id128) return fail(SNTC_E_INVALID, "sntc_comm_unique_id: id is NULL");
+  if (!g_nccl.load()) return fail(SNTC_E_UNSUPPORTED, "sntc_comm_unique_id: " + g_nccl.err);
+  static_assert(sizeof(ncclUniqueId) == SNTC_COMM_ID_BYTES, "NCCL unique id size");
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return SNTC_OK;
+}
+
+extern "C" int sntc_comm_create(sntc_ctx* ctx, const void* id128, int rank, int world, sntc_comm** out) {
+  if (!ctx || !id128 || !out || world < 1 || rank < 0 || rank >= world) return fail(SNTC_E_INVALID, "sntc_comm_create: bad argument");
+  *out = nullptr;
+  if (!g_nccl.load()) return fail(SNTC_E_UNSUPPORTED, "sntc_comm_create: " + g_nccl.err);
+  CU_TRY(cudaSetDevice(ctx->device));
+  auto c = std::make_unique<sntc_comm>();
+  c->ctx = ctx; c->rank = rank; c->world = world;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NCCL_TRY(g_nccl.CommInitRank(&c->comm, world, id, rank));
+  CU_TRY(cudaMalloc((void**)&c->d_buf, SNTC_COMM_MAX_N * sizeof(double)));
+  CU_TRY(cudaHostAlloc((void**)&c->h_buf, SNTC_COMM_MAX_N * sizeof(double), cudaHostAllocDefault));
+  *out = c.release();
+  return SNTC_OK;
+}
+
+extern "C" int sntc_comm_destroy(sntc_comm* c) {
+  if (!c) return SNTC_OK;
+  cudaSetDevice(c->ctx->device);
+  cudaStreamSynchronize(c->ctx->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->d_buf) cudaFree(c->d_buf);
+  if (c->h_buf) cudaFreeHost(c->h_buf);
+  delete c;
+  return SNTC_OK;
+}
+
+extern "C" int sntc_comm_allreduce_f64(sntc_comm* c, double* values, int n, int op) {
+  if (!c || !values || n < 0 || n > SNTC_COMM_MAX_N) return fail(SNTC_E_INVALID, "sntc_comm_allreduce_f64: bad argument (n <= 4096)");
+  if (op != SNTC_REDUCE_SUM && op != SNTC_REDUCE_MAX) return fail(SNTC_E_INVALID, "sntc_comm_allreduce_f64: unknown op");
+  if (n == 0) return SNTC_OK;
+  CU_TRY(cudaSetDevice(c->ctx->device));
+  cudaStream_t s = c->ctx->stream;
+  memcpy(c->h_buf, values, (size_t)n * sizeof(double));
+  CU_TRY(cudaMemcpyAsync(c->d_buf, c->h_buf, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  NCCL_TRY(g_nccl.AllReduce(c->d_buf, c->d_buf, (size_t)n, ncclFloat64, op == SNTC_REDUCE_SUM ? ncclSum : ncclMax, c->comm, s));
+  CU_TRY(cudaMemcpyAsync(c->h_buf, c->d_buf, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  memcpy(values, c->h_buf, (size_t)n * sizeof(double));
+  return SNTC_OK;
+}
+
+extern "C" int sntc_allreduce_metrics(sntc_comm* c, double sums[5]) { return sntc_comm_allreduce_f64(c, sums, 5, SNTC_REDUCE_SUM); }
 
 extern "C" int sntc_last_stage_times_ms(sntc_model* m, float out[4]) {
   if (!m || !out) return fail(SNTC_E_INVALID, "sntc_last_stage_times_ms: bad argument");

@@ -90,12 +90,13 @@ class Context:
     d.copy_from_host(arr)
     return d
 
-  def pinned_empty(self, shape, dtype) -> np.ndarray:
-    """numpy array backed by page-locked host memory (cudaHostAlloc)."""
+  def pinned_empty(self, shape, dtype, write_combined=False) -> np.ndarray:
+    """numpy array backed by page-locked host memory (cudaHostAlloc).  ``write_combined``: for buffers the host only writes
+    (symbols on their way to the device); reading such an array on the host is very slow."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
     p = C.c_void_p()
-    check(lib.sntc_host_alloc(self.handle, max(n, 1), C.byref(p)))
+    check(lib.sntc_host_alloc_flags(self.handle, max(n, 1), _lib.HOST_WRITE_COMBINED if write_combined else 0, C.byref(p)))
     owner = _PinnedOwner(self, p)
     buf = (C.c_char * max(n, 1)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
@@ -192,6 +193,31 @@ class DeviceArray:
       self.free()
     except Exception:
       pass
+
+
+class DeviceView:
+  """Non-owning dense view of a byte range of a DeviceArray (``base`` keeps the allocation alive): lets several tensors share
+  one allocation, so that one host<->device copy moves all of them (DecodePipeline's packed staging buffers)."""
+
+  def __init__(self, base: DeviceArray, byte_offset: int, shape, dtype):
+    self.base, self.ctx = base, base.ctx
+    self.shape = tuple(int(s) for s in shape)
+    self.dtype = np.dtype(dtype)
+    self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+    if byte_offset < 0 or byte_offset + self.nbytes > base.nbytes:
+      raise ValueError("view exceeds the allocation")
+    self.ptr = C.c_void_p(base.ptr.value + int(byte_offset))
+
+  @property
+  def __cuda_array_interface__(self):
+    return dict(shape=self.shape, typestr=self.dtype.str, data=(self.ptr.value, False), version=3, strides=None)
+
+  def to_host(self, out: np.ndarray | None = None) -> np.ndarray:
+    if out is None:
+      out = np.empty(self.shape, dtype=self.dtype)
+    check(lib.sntc_memcpy_d2h(self.ctx.handle, out.ctypes.data_as(C.c_void_p), self.ptr, self.nbytes, None))
+    self.ctx.sync()
+    return out
 
 
 # --- DLPack capsule parsing (borrowed: we never call the deleter, never rename the capsule) ---

@@ -73,6 +73,6 @@ def test_product_never_imports_the_oracle():
       if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
         txt = open(os.path.join(dirpath, f)).read()
         assert "oracle" not in txt.lower().replace("# oracle", ""), f"{f} mentions the oracle"
-        if f != "parallel.py":   # torch.distributed plumbing for the multi-GPU driver only
-          assert "import torch" not in txt, f
-        assert "import tensorflow" not in txt, f
+        assert "import torch" not in txt, f          # no PyTorch in the product: the collective is NCCL through libsntc
+        if f != "tf_glue.py":                          # the reference-side binding imports TensorFlow lazily, on the reference's side only
+          assert "import tensorflow" not in txt, f

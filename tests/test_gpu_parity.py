@@ -219,23 +219,60 @@ def test_tc_hyper_transform_call(gpu_ctx):
   assert np.abs(hs - ref).max() < 2e-4
 
 
-@pytest.mark.parametrize("q_dtype", [np.float32, np.int8])
-def test_streaming_pipeline_matches_direct_decode(gpu_ctx, q_dtype):
-  """DecodePipeline (H2D / decode / D2H on three streams, double-buffered) returns exactly what the
-  synchronous call returns, for every batch, in order."""
+@pytest.mark.parametrize("q_dtype", [np.float32, np.int16, np.int8])
+@pytest.mark.parametrize("packed", [False, True])
+def test_streaming_pipeline_matches_direct_decode(gpu_ctx, q_dtype, packed):
+  """DecodePipeline (H2D / decode / D2H on three streams, double-buffered) returns exactly what the synchronous call
+  returns, for every batch, in order -- with caller-owned pinned arrays (one copy per array) and with the pipeline's own
+  packed page-locked slots (one copy per direction), with and without the idx download."""
   from shallow_ntc_b200 import DecodePipeline
-  B, H, W = 2, 64, 128
-  model, wts, z, q = make_case("two_layer_syn", B * 5, H, W, "stress", "tc", gpu_ctx)
-  pipe = DecodePipeline(model, B, (H, W), q_dtype=q_dtype, depth=2)
+  B, H, W, N = 2, 64, 128, 5
+  model, wts, z, q = make_case("two_layer_syn", B * N, H, W, "stress", "tc", gpu_ctx)
+  refs = [model.decompress(z[i * B:(i + 1) * B], q[i * B:(i + 1) * B], (H, W)) for i in range(N)]
   zs, ys = model.latent_shapes(B, H, W)
-  outs = [dict(image=gpu_ctx.pinned_empty((B, H, W, 3), np.uint8), idx=gpu_ctx.pinned_empty(ys, np.uint8)) for _ in range(5)]
-  pins = [(gpu_ctx.pinned_like(z[i * B:(i + 1) * B]), gpu_ctx.pinned_like(q[i * B:(i + 1) * B].astype(q_dtype))) for i in range(5)]
-  tickets = [pipe.submit(pz, pq, o["image"], o["idx"]) for (pz, pq), o in zip(pins, outs)]
-  pipe.wait(tickets[-1])
+  for return_idx in (True, False):
+    pipe = DecodePipeline(model, B, (H, W), q_dtype=q_dtype, depth=2, return_idx=return_idx, host_slots=N, write_combined=packed)
+    if packed:
+      slots = [pipe.host_slot(i) for i in range(N)]
+      for i, h in enumerate(slots):
+        h["z"][...] = z[i * B:(i + 1) * B]
+        h["q"][...] = q[i * B:(i + 1) * B].astype(q_dtype)
+        h["image"][...] = 0xA5
+        h["idx"][...] = 0xA5
+      tickets = [pipe.submit(h["z"], h["q"], h["image"], h["idx"]) for h in slots]
+      outs = slots
+    else:
+      outs = [dict(image=gpu_ctx.pinned_empty((B, H, W, 3), np.uint8), idx=gpu_ctx.pinned_empty(ys, np.uint8)) for _ in range(N)]
+      for o in outs:
+        o["idx"][...] = 0xA5
+      pins = [(gpu_ctx.pinned_like(z[i * B:(i + 1) * B]), gpu_ctx.pinned_like(q[i * B:(i + 1) * B].astype(q_dtype))) for i in range(N)]
+      tickets = [pipe.submit(pz, pq, o["image"], o["idx"]) for (pz, pq), o in zip(pins, outs)]
+    pipe.wait(tickets[-1])
+    pipe.drain()
+    for i in range(N):
+      assert np.array_equal(outs[i]["image"], refs[i]["image"]), (i, return_idx)
+      if return_idx:
+        assert np.array_equal(outs[i]["idx"], refs[i]["idx"]), i
+      else:
+        assert np.all(outs[i]["idx"] == 0xA5), "idx must not be downloaded unless asked for"
+    # the rows stay available on the device either way
+    last = pipe.slots[(N - 1) % 2]["idx"].to_host()
+    assert np.array_equal(last, refs[N - 1]["idx"])
+
+
+def test_streaming_pipeline_factorized_model(gpu_ctx):
+  from shallow_ntc_b200 import DecodePipeline
+  B, H, W = 2, 48, 80
+  model, wts, z, q = make_case("bls2017", B * 3, H, W, "stress", "tc", gpu_ctx)
+  pipe = DecodePipeline(model, B, (H, W), q_dtype=np.int8, depth=2)
+  for i in range(3):
+    h = pipe.host_slot(i)
+    h["q"][...] = q[i * B:(i + 1) * B].astype(np.int8)
+    t = pipe.submit(None, h["q"], h["image"])
+    pipe.wait(t)
+    ref = model.decompress(q[i * B:(i + 1) * B], (H, W))
+    assert np.array_equal(h["image"], ref["image"])
   pipe.drain()
-  for i in range(5):
-    ref = model.decompress(z[i * B:(i + 1) * B], q[i * B:(i + 1) * B], (H, W))
-    assert np.array_equal(outs[i]["image"], ref["image"]) and np.array_equal(outs[i]["idx"], ref["idx"])
 
 
 @pytest.mark.parametrize("name,B,H,W", [("two_layer_syn", 2, 128, 192), ("two_layer_syn2", 1, 100, 150), ("two_layer_syn2:24", 1, 128, 128)])

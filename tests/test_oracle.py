@@ -128,11 +128,12 @@ def test_scale_index_rules():
   raw = np.log(np.array([1e-9, 0.49, 0.51, 1.49, 2.51, 62.4, 62.6, 63.5, 1e6]))
   i_c, idx, dist = O.scale_indexes(raw, "rint")
   assert idx.tolist() == [0, 0, 1, 1, 3, 62, 63, 63, 63]         # clamp to [0, 63], round to nearest
-  assert np.allclose(dist[:3], [0.5 - 1e-9, 0.01, 0.01], atol=1e-6) and abs(dist[-1] - 0.5) < 1e-12
+  assert np.allclose(dist[:3], [0.5 - 1e-9, 0.01, 0.01], atol=1e-6) and abs(dist[7] - 1.0) < 1e-9 and dist[-1] > 1e5   # above the clamp: distance to 62.5
   assert np.rint(np.array([0.5, 1.5, 2.5, 62.5])).tolist() == [0, 2, 2, 62]   # A3: ties to even
   _, idx_t, dist_t = O.scale_indexes(raw)                          # the default (A6): tf.cast(indexes, tf.int32) truncates
   assert idx_t.tolist() == [0, 0, 0, 1, 2, 62, 62, 63, 63]
-  assert np.allclose(dist_t[1:5], [0.49, 0.49, 0.49, 0.49], atol=1e-9)   # distance to the nearest integer boundary
+  # distance to the nearest boundary: integers 1 .. 63 (values below 1 and above the clamp have ONE neighbour boundary)
+  assert np.allclose(dist_t[:8], [1.0, 0.51, 0.49, 0.49, 0.49, 0.4, 0.4, 0.5], atol=1e-8) and dist_t[-1] > 1e5
   assert abs(O.scale_fn(0) - 0.11) < 1e-12 and abs(O.scale_fn(63) - 256.0) < 1e-9
 
 
