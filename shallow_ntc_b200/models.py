@@ -282,6 +282,46 @@ class Model:
       out["ssd"] = np.array([m.ssd for m in metrics], dtype=np.uint64)
     return out
 
+  # ---------------------------------------------------------------------------------------------
+  # intra-frame sharding (BASELINE configs[4]): latent-row bands with recomputed halos, see tiling.py
+  def band_plan(self, image_hw, n_bands):
+    from .tiling import plan_bands
+    hyp = self._hyper_synthesis
+    return plan_bands(int(image_hw[0]), self._synthesis.conv_chain(), self._synthesis.upsample,
+                      hyp.conv_chain() if hyp is not None else None, hyp.upsample if hyp is not None else 1, int(n_bands))
+
+  def band_inputs(self, z_hat, q_y, band):
+    """The (contiguous) sub-tensors of host symbol arrays a band decodes: what a rank would be handed by the range decoder."""
+    z = None if z_hat is None else np.ascontiguousarray(z_hat[:, band.z_rows[0]:band.z_rows[1]])
+    return z, np.ascontiguousarray(q_y[:, band.y_rows[0]:band.y_rows[1]])
+
+  def decompress_band(self, z_band, q_band, image_hw, band, **kw):
+    """Decode ONE band from its sub-tensors (``band_inputs``).  Returns the usual dict restricted to the band: ``image``
+    [B, r1-r0, W, 3] (rows ``band.rows`` of the frame), ``idx`` / ``y_hat`` [B, c1-c0, wy, Cy] (latent rows ``band.y_core``).
+    Host or device inputs; the crops are views / device-to-host slices of the sub-decode's outputs."""
+    W = int(image_hw[1])
+    full = self.decompress(z_band, q_band, (band.sub_h, W), **kw)
+    out = dict(full)
+    k0, k1 = band.keep
+    c0, c1 = band.y_core[0] - band.y_rows[0], band.y_core[1] - band.y_rows[0]
+    for key, (a, b) in (("image", (k0, k1)), ("float", (k0, k1)), ("idx", (c0, c1)), ("y_hat", (c0, c1))):
+      if key in out:
+        v = out[key] if isinstance(out[key], np.ndarray) else out[key].to_host()
+        out[key] = v[:, a:b]
+    return out
+
+  def decompress_tiled(self, z_hat, q_y, image_hw, n_bands, **kw):
+    """Whole frames decoded band by band on THIS GPU and stitched: bit-identical to ``decompress`` (the test of the halo
+    derivation).  On N GPUs rank r runs ``decompress_band`` on band r only; no collective is needed to produce the frame
+    (each rank owns its rows)."""
+    bands = self.band_plan(image_hw, n_bands)
+    parts = [self.decompress_band(*self.band_inputs(z_hat, q_y, b), image_hw, b, **kw) for b in bands]
+    out = {}
+    for key in ("image", "float", "idx", "y_hat"):
+      if key in parts[0]:
+        out[key] = np.concatenate([p[key] for p in parts], axis=1)
+    return out
+
   def evaluate(self, z_hat, q_y, originals, image_hw=None, **kw):
     """Model.evaluate (mshyper/models.py:415-433) from decoded symbols: yields one metrics dict per image
     (see eval_lib.evaluate_symbols)."""

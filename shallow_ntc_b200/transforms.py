@@ -52,6 +52,14 @@ def _gdn(prefix, name, c):
   return {f"{prefix}.{name}.beta": (c,), f"{prefix}.{name}.gamma": (c, c)}
 
 
+def _keras_pad(k, s):
+  return max(k - s, 0) // 2          # Conv2DTranspose(padding="SAME"): pad_before of the SAME correlation it is the gradient of
+
+
+def _tfc_pad(k):
+  return (k - 1) // 2                # SignalConv2D(padding="same_zeros")
+
+
 class Transform:
   """Base of the shim classes.  A transform is lazily bound to a hyper-only / synthesis-only libsntc
   model the first time it is called on its own; inside ``models.Model`` the fused decode is used."""
@@ -74,6 +82,11 @@ class Transform:
 
   @property
   def out_channels(self):
+    raise NotImplementedError
+
+  def conv_chain(self):
+    """[(kernel, stride, pad), ...] of the transposed convolutions in forward order: out[o] += in[n] * W[a], o = n*s + a - pad.
+    Pointwise stages do not appear.  Drives the halo computation of the intra-frame band split (tiling.py)."""
     raise NotImplementedError
 
   def count_params(self, in_channels: int | None = None) -> int:
@@ -125,6 +138,9 @@ class HyperSynthesis(Transform):
     self.bottleneck_size = int(bottleneck_size)
     self.activation_type = activation_type
 
+  def conv_chain(self):
+    return [(5, 2, _keras_pad(5, 2)), (5, 2, _keras_pad(5, 2)), (3, 1, _keras_pad(3, 1))]
+
   @property
   def out_channels(self):
     return self.bottleneck_size * 2
@@ -152,6 +168,9 @@ class JPEGLikeHyperSynthesis(Transform):
     super().__init__()
     self.bottleneck_size, self.kernel_size = int(bottleneck_size), int(kernel_size)
 
+  def conv_chain(self):
+    return [(self.kernel_size, 4, _keras_pad(self.kernel_size, 4))]
+
   @property
   def out_channels(self):
     return self.bottleneck_size * 2
@@ -174,6 +193,9 @@ class HyperSynthesisSmall(Transform):
   def __init__(self, bottleneck_size):
     super().__init__()
     self.bottleneck_size = int(bottleneck_size)
+
+  def conv_chain(self):
+    return [(5, 2, _tfc_pad(5)), (3, 1, _tfc_pad(3))]
 
   @property
   def out_channels(self):
@@ -202,6 +224,9 @@ class JPEGLikeSynthesis(Transform):
     self.use_bias, self.use_offset = bool(use_bias), bool(use_offset)
     self.upsample = self.strides
 
+  def conv_chain(self):
+    return [(self.kernel_size, self.strides, _keras_pad(self.kernel_size, self.strides))]
+
   @property
   def out_channels(self):
     return self.output_channels
@@ -225,6 +250,9 @@ class TwoLayerSynthesis(Transform):
     self.channels, self.strides, self.kernel_sizes = tuple(channels), tuple(strides), tuple(kernel_sizes)
     self.activation_type = activation_type
     self.upsample = self.strides[0] * self.strides[1]
+
+  def conv_chain(self):
+    return [(k, s, _keras_pad(k, s)) for k, s in zip(self.kernel_sizes, self.strides)]
 
   @property
   def out_channels(self):
@@ -283,6 +311,9 @@ class MBT2018Synthesis(Transform):
     self.output_channels = int(output_channels) if output_channels is not None else int(channels_base)
     self.upsample = 2 ** self.n_layers
 
+  def conv_chain(self):
+    return [(5, 2, _tfc_pad(5))] * self.n_layers
+
   @property
   def out_channels(self):
     return self.output_channels
@@ -312,6 +343,9 @@ class BLS2017Synthesis(Transform):
     super().__init__()
     self.num_filters = int(num_filters)
 
+  def conv_chain(self):
+    return [(5, 2, _tfc_pad(5)), (5, 2, _tfc_pad(5)), (9, 4, _tfc_pad(9))]
+
   @property
   def out_channels(self):
     return 3
@@ -339,6 +373,9 @@ class CNNSynthesis(Transform):
     super().__init__()
     self.channels_base, self.output_channels = int(channels_base), int(output_channels)
     self.activation_type = activation_type
+
+  def conv_chain(self):
+    return [(5, 2, _keras_pad(5, 2))] * 4
 
   @property
   def out_channels(self):

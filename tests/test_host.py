@@ -6,6 +6,7 @@ import pytest
 
 from shallow_ntc_b200 import class_builder, build_config, CONFIGS, Model, FactorizedModel, as_tensor, _lib
 from shallow_ntc_b200 import transforms as T
+from shallow_ntc_b200 import synthetic
 
 
 def test_registry_has_the_decoder_classes_of_the_reference():
@@ -120,3 +121,45 @@ def test_bind_host_to_gpu_uses_the_gpus_numa_cpus(tmp_path, monkeypatch):
   # missing sysfs entry: reported, not raised
   info = parallel.bind_host_to_gpu(Ctx(), sysfs=str(tmp_path / "nope"))
   assert info["bound"] is False and "error" in info
+
+
+# ---- intra-frame band split (tiling.py): geometry against the oracle ---------------------------------------------------
+def test_input_rows_formula_against_brute_force():
+  """Receptive rows of a conv chain, checked by enumerating o = n*s + a - p directly."""
+  from shallow_ntc_b200.tiling import input_rows
+  for chain in ([(5, 2, 1)], [(5, 2, 2), (9, 4, 4)], [(13, 8, 2), (5, 2, 1)], [(5, 2, 1), (5, 2, 1), (3, 1, 1)], [(18, 16, 1)], [(6, 4, 1)]):
+    for lo, hi in ((0, 0), (5, 9), (64, 127), (17, 17)):
+      rows = set(range(lo, hi + 1))
+      for k, s, p in reversed(chain):
+        rows = {n for o in rows for a in range(k) for n in [(o + p - a) // s] if (o + p - a) % s == 0}
+      assert (min(rows), max(rows)) == input_rows(chain, lo, hi), (chain, lo, hi)
+
+
+@pytest.mark.parametrize("name,H,W,n_bands", [("bls2017", 200, 48, 3), ("two_layer_syn", 320, 64, 2), ("jpegl", 300, 64, 4), ("mbt2018", 192, 64, 3)])
+def test_banded_oracle_decode_equals_whole_frame(name, H, W, n_bands):
+  """The band plan (rows + halo) applied to the ORACLE: decoding each band's sub-tensors and keeping its rows reproduces
+  the whole-frame decode (float64, so equal up to BLAS blocking: 1e-11), image rows and scale-table rows alike."""
+  from oracle import ntc_oracle as O
+  m = build_config(name)
+  cfg = m._transform_config["synthesis"]
+  kw = {k: v for k, v in cfg.items() if k != "cls"}
+  w = synthetic.make_weights(m.variable_shapes(), "stress", synthesis_cls=cfg["cls"])
+  zs, ys = m.latent_shapes(1, H, W)
+  z, q = synthetic.make_latents(zs, ys)
+  dec = (lambda z_, q_, h: O.mshyper_decode(w, cfg["cls"], z_, q_, h, W, kw)) if m.hyperprior else (lambda z_, q_, h: O.factorized_decode(w, cfg["cls"], q_, h, W, kw))
+  whole = dec(z, q, H)
+  bands = m.band_plan((H, W), n_bands)
+  assert bands[0].rows[0] == 0 and bands[-1].rows[1] == H and all(a.rows[1] == b.rows[0] for a, b in zip(bands, bands[1:]))
+  for b in bands:
+    zb, qb = m.band_inputs(z, q, b)
+    part = dec(zb, qb, b.sub_h)
+    assert np.abs(part["recon"][:, b.keep[0]:b.keep[1]] - whole["recon"][:, b.rows[0]:b.rows[1]]).max() < 1e-11
+    if m.hyperprior:
+      c0, c1 = b.y_core[0] - b.y_rows[0], b.y_core[1] - b.y_rows[0]
+      assert np.array_equal(part["idx"][:, c0:c1], whole["idx"][:, b.y_core[0]:b.y_core[1]])
+  # the halo is tight: one row less on either side changes the band's pixels
+  b = bands[1]
+  if not m.hyperprior:
+    qs = np.ascontiguousarray(q[:, b.y_rows[0] + 1:b.y_rows[1]])
+    part = dec(None, qs, b.sub_h - 16)
+    assert np.abs(part["recon"][:, b.keep[0] - 16:b.keep[1] - 16] - whole["recon"][:, b.rows[0]:b.rows[1]]).max() > 1e-6
