@@ -167,6 +167,12 @@ class DeviceArray:
   def __cuda_array_interface__(self):
     return dict(shape=self.shape, typestr=self.dtype.str, data=(self.ptr.value, False), version=3, strides=None)
 
+  def __dlpack__(self, stream=None):
+    return to_dlpack(self)
+
+  def __dlpack_device__(self):
+    return (_lib.DL_CUDA, self.ctx.device)
+
   def copy_from_host(self, arr: np.ndarray, stream=None):
     arr = np.ascontiguousarray(arr, dtype=self.dtype)
     assert arr.shape == self.shape, (arr.shape, self.shape)
@@ -225,10 +231,13 @@ class _DLManagedTensor(C.Structure):
   _fields_ = [("dl_tensor", Tensor), ("manager_ctx", C.c_void_p), ("deleter", C.c_void_p)]
 
 
-C.pythonapi.PyCapsule_IsValid.restype = C.c_int
-C.pythonapi.PyCapsule_IsValid.argtypes = [C.py_object, C.c_char_p]
-C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
-C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+# Private prototypes: ctypes.pythonapi's function objects are process-wide singletons whose argtypes any other package may
+# reassign, so none of them is configured or relied upon here.
+_capsule_is_valid = C.PYFUNCTYPE(C.c_int, C.py_object, C.c_char_p)(("PyCapsule_IsValid", C.pythonapi))
+_capsule_get_pointer = C.PYFUNCTYPE(C.c_void_p, C.py_object, C.c_char_p)(("PyCapsule_GetPointer", C.pythonapi))
+_capsule_get_pointer_raw = C.PYFUNCTYPE(C.c_void_p, C.c_void_p, C.c_char_p)(("PyCapsule_GetPointer", C.pythonapi))
+_capsule_get_name_raw = C.PYFUNCTYPE(C.c_char_p, C.c_void_p)(("PyCapsule_GetName", C.pythonapi))
+_capsule_new = C.PYFUNCTYPE(C.py_object, C.c_void_p, C.c_char_p, C.c_void_p)(("PyCapsule_New", C.pythonapi))
 
 
 class TensorRef:
@@ -285,15 +294,58 @@ def as_tensor(obj, device_id: int = 0) -> TensorRef | None:
     return _from_parts(cai["data"][0], _lib.DL_CUDA, device_id if dev is None else dev, cai["shape"], np.dtype(cai["typestr"]), obj)
   capsule = obj if _is_capsule(obj) else (obj.__dlpack__() if hasattr(obj, "__dlpack__") else None)
   if capsule is not None:
-    if not C.pythonapi.PyCapsule_IsValid(capsule, b"dltensor"):
+    if not _capsule_is_valid(capsule, b"dltensor"):
       raise ValueError("not a live 'dltensor' capsule (already consumed?)")
-    p = C.pythonapi.PyCapsule_GetPointer(capsule, b"dltensor")
+    p = _capsule_get_pointer(capsule, b"dltensor")
     mt = _DLManagedTensor.from_address(p)
     src = mt.dl_tensor
     t = Tensor()
     C.memmove(C.byref(t), C.byref(src), C.sizeof(Tensor))
     return TensorRef(t, (obj, capsule))
   raise TypeError(f"cannot interpret {type(obj)} as a tensor")
+
+
+# --- DLPack export: hand a DeviceArray / DeviceView / numpy array to a consumer (tf.experimental.dlpack.from_dlpack, ...) zero-copy ---
+_DL_DELETER = C.CFUNCTYPE(None, C.c_void_p)
+_DL_CAPSULE_DTOR = C.CFUNCTYPE(None, C.c_void_p)
+_DL_LIVE = {}     # address of the DLManagedTensor -> everything that must outlive the consumer's use of it
+
+
+
+@_DL_DELETER
+def _dl_deleter(managed_ptr):
+  _DL_LIVE.pop(managed_ptr, None)     # drops the owner reference: the buffer may be freed from here on
+
+
+@_DL_CAPSULE_DTOR
+def _dl_capsule_destructor(capsule_ptr):
+  # a capsule that was never consumed still owns the tensor (consumers rename theirs to "used_dltensor")
+  if _capsule_get_name_raw(capsule_ptr) == b"dltensor":
+    _DL_LIVE.pop(_capsule_get_pointer_raw(capsule_ptr, b"dltensor"), None)
+
+
+def to_dlpack(obj):
+  """'dltensor' capsule of a DeviceArray / DeviceView (kDLCUDA) or a C-contiguous numpy array (kDLCPU; page-locked ones as
+  kDLCUDAHost).  The producer object stays alive until the consumer calls the deleter: zero-copy hand-off of decode outputs,
+  e.g. ``tf.experimental.dlpack.from_dlpack(to_dlpack(out["image"]))``."""
+  if isinstance(obj, np.ndarray):
+    if not obj.flags.c_contiguous or obj.dtype not in _DTYPES:
+      raise ValueError("numpy arrays must be C-contiguous float32 / uint8 / int16 / int8")
+    ptr, shape, dtype = obj.ctypes.data, obj.shape, obj.dtype
+    dev_type, dev_id = (_lib.DL_CUDA_HOST if ptr in _PINNED else _lib.DL_CPU), 0
+  elif isinstance(obj, (DeviceArray, DeviceView)):
+    ptr, shape, dtype, dev_type, dev_id = obj.ptr.value, obj.shape, obj.dtype, _lib.DL_CUDA, obj.ctx.device
+  else:
+    raise TypeError(f"cannot export {type(obj)} through DLPack")
+  code, bits = _DTYPES[np.dtype(dtype)]
+  shp = (C.c_int64 * max(len(shape), 1))(*[int(s) for s in shape])
+  mt = _DLManagedTensor()
+  mt.dl_tensor = Tensor(C.c_void_p(ptr), dev_type, dev_id, len(shape), code, bits, 1, shp, None, 0)
+  mt.manager_ctx = None
+  mt.deleter = C.cast(_dl_deleter, C.c_void_p)
+  addr = C.addressof(mt)
+  _DL_LIVE[addr] = (mt, shp, obj)
+  return _capsule_new(addr, b"dltensor", C.cast(_dl_capsule_destructor, C.c_void_p))
 
 
 def empty_like_kind(ctx: Context, like, shape, dtype):

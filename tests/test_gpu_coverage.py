@@ -331,3 +331,17 @@ def test_tiled_decode_equals_whole_frame_bit_for_bit(gpu_ctx, name, B, H, W, n_b
   zb, qb = model.band_inputs(z, q, b)
   dev = model.decompress_band(gpu_ctx.to_device(zb) if zb is not None else None, gpu_ctx.to_device(qb), (H, W), b)
   assert np.array_equal(dev["image"], whole["image"][:, b.rows[0]:b.rows[1]])
+
+
+# --------------------------------------------------------------------------------------------------
+# the ONE collective of the path: NCCL called by libsntc (no PyTorch); single-rank communicator here, N ranks in bench.py
+
+def test_nccl_group_of_one_rank(gpu_ctx, tmp_path):
+  from shallow_ntc_b200 import parallel
+  g = parallel.NcclGroup(gpu_ctx, 0, 1, str(tmp_path / "id"))
+  sums = np.array([31.5, 48.25, 1.0e6, 2.0e3, 24.0])
+  assert np.array_equal(g.allreduce_metrics(sums), sums) and np.array_equal(parallel.reduce_metric_sums(g, sums), sums)
+  v = np.arange(100, dtype=np.float64) - 50.5
+  assert np.array_equal(g.allreduce_sum(v), v) and np.array_equal(parallel.max_over_ranks(g, v), v)
+  g.barrier()
+  g.close()
