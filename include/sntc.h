@@ -181,6 +181,11 @@ int sntc_model_variable(sntc_model* m, int i, const char** name, int64_t shape[4
 int sntc_model_load_weights(sntc_model* m, const char* name, const float* host, const int64_t* shape, int ndim);
 /* Packs and uploads all weights; fails with SNTC_E_STATE naming the first missing variable. */
 int sntc_model_finalize(sntc_model* m);
+/* Small-batch decodes (batch <= 4) whose tensors are all device-resident are replayed as ONE CUDA graph from their third
+ * identical call on (first call eager, second captured): the decode is launch-bound there.  Results are identical; the
+ * per-stage event times (sntc_last_stage_times_ms) exist for eager decodes only.  on = 0 keeps every decode eager (what
+ * Model(profile=True) selects); default on.  Environment: SNTC_GRAPH=0, SNTC_GRAPH_MAX_BATCH. */
+int sntc_model_enable_graphs(sntc_model* m, int on);
 
 /* ---- transform-level calls (the Keras-layer __call__ the model code makes) ----
  * self._hyper_synthesis(z_hat)            mshyper/models.py:273  -> out f32 [B, hy, wy, 2*Cy]

@@ -76,6 +76,7 @@ _PROTOS = {
   "sntc_model_variable": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
   "sntc_model_load_weights": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.c_int]),
   "sntc_model_finalize": (C.c_int, [_P]),
+  "sntc_model_enable_graphs": (C.c_int, [_P, C.c_int]),
   "sntc_hyper_synthesis": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), _P]),
   "sntc_synthesis": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), _P]),
   "sntc_decode": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor),

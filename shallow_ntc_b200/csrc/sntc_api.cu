@@ -66,6 +66,9 @@ struct sntc_ctx {
   DevBuf ms_ws;  // scratch of sntc_image_msssim
 };
 
+struct GraphKey { long long v[6]; const void* p[20]; };
+struct GraphEntry { GraphKey key{}; cudaGraphExec_t exec = nullptr; bool failed = false; uint64_t epoch = 0; uint64_t launches = 0; uint64_t kinds[SNTC_LAUNCH_KINDS] = {0, 0, 0, 0, 0, 0}; };
+
 struct ProfRec { std::string label; cudaEvent_t a = nullptr, b = nullptr; double macs = 0; };
 struct ProfAgg { std::string label; float ms = 0; int n = 0; double macs = 0; };
 
@@ -96,6 +99,8 @@ struct sntc_model {
   std::vector<TailMma> tail_mma;       // parallel to syn.convs: warp-MMA tail of a two-layer synthesis (tc precision only)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
+  bool graphs_on = true;                // sntc_model_enable_graphs
+  std::vector<GraphEntry> graphs;       // CUDA graphs of small-batch decodes, keyed by shapes + pointers (decode_impl)
   unsigned long long* h_ssd = nullptr;  // pinned
   int h_ssd_cap = 0;
 };
@@ -352,12 +357,19 @@ extern "C" int sntc_model_destroy(sntc_model* m) {
                     &m->st_orig, &m->d_hs, &m->d_yhat, &m->d_ssd, &m->d_rate_slots, &m->d_rate_img, &m->d_rate_zslots, &m->d_rate, &m->d_mu, &m->d_flag})
     b->release();
   m->tc.release();
+  for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
   for (auto& r : m->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto& e : m->prof_pool) cudaEventDestroy(e);
   if (m->h_ssd) cudaFreeHost(m->h_ssd);
   if (m->h_rate) cudaFreeHost(m->h_rate);
   delete m;
+  return SNTC_OK;
+}
+
+extern "C" int sntc_model_enable_graphs(sntc_model* m, int on) {
+  if (!m) return fail(SNTC_E_INVALID, "sntc_model_enable_graphs: model is NULL");
+  m->graphs_on = on != 0;
   return SNTC_OK;
 }
 
@@ -697,7 +709,7 @@ static int run_rgb_f32(sntc_ctx* ctx, const ConvLayer& c, const float* in, int B
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr; cfg.numAttrs = tc_pdl() ? 1 : 0;
+      cfg.attrs = attr; cfg.numAttrs = tc_pdl(B) ? 1 : 0;
       CU_TRY(cudaLaunchKernelEx(&cfg, tail_s2_const_kernel<5, 1, 12, 4>, Q, Wt));
       ctx->launches++; ctx->kinds[SNTC_LAUNCH_FINAL_F32]++;
       CU_TRY(cudaGetLastError());
@@ -952,7 +964,7 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         if (fin) { to.f32 = fin->full; to.u8 = fin->u8; to.crop = fin->crop; to.H = fin->H; to.W = fin->W; }
         std::string err;
         ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
-        if (tail_mma_run(ctx->tc, c, m->tail_mma[op.conv], cur.f32, B, ch, cw, to, tc_pdl(), s, &ctx->launches, &err,
+        if (tail_mma_run(ctx->tc, c, m->tail_mma[op.conv], cur.f32, B, ch, cw, to, tc_pdl(B), s, &ctx->launches, &err,
                          m->desc.precision != SNTC_PRECISION_TC_F16X3_SYN2) != 0)
           return fail(SNTC_E_CUDA, "warp-MMA tail: " + err);
         ctx->kinds[SNTC_LAUNCH_TAIL_MMA]++;
@@ -1127,8 +1139,11 @@ static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tenso
   if (out_yhat && on_device(out_yhat)) d_yhat = tdata(out_yhat);
   else { TRY(m->d_yhat.ensure(n_lat * 4)); d_yhat = m->d_yhat.p; }
 
-  CU_TRY(cudaEventRecord(m->ev[0], s));
   Cur ycur;
+  // Everything that is enqueued on the stream for the decode itself; `capturing`: the stream is being captured into a CUDA graph
+  // (no event records: events recorded inside a capture cannot be timed).
+  auto enqueue = [&](bool capturing) -> int {
+  if (!capturing) { CU_TRY(cudaEventRecord(m->ev[0], s)); m->ev_valid = true; }
   RateConst rc{};
   if (rate) {
     // Fixed configs for the ScaleIndexedEntropyModel, float32 like the reference computes them   mshyper/models.py:27-32
@@ -1190,7 +1205,7 @@ static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tenso
       FinalOut fin; fin.full = (float*)m->d_hs.p;
       Cur c0; c0.f32 = (const float*)d_z;
       TRY(run_transform(m, m->hyper, true, c0, B, hz, wz, &fin, nullptr, s));
-      CU_TRY(cudaEventRecord(m->ev[1], s));
+      if (!capturing) CU_TRY(cudaEventRecord(m->ev[1], s));
       ProfScope ps(m, s, "dequant_index", 0);
       DequantParams P{};
       P.hs = (const float*)m->d_hs.p; P.q = d_q; P.q_kind = q_kind; P.npix = (size_t)B * hy * wy; P.C = Cy;
@@ -1211,10 +1226,10 @@ static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tenso
         CU_TRY(cudaGetLastError());
       }
     } else {
-      CU_TRY(cudaEventRecord(m->ev[1], s));
+      if (!capturing) CU_TRY(cudaEventRecord(m->ev[1], s));
     }
   } else {
-    CU_TRY(cudaEventRecord(m->ev[1], s));
+    if (!capturing) CU_TRY(cudaEventRecord(m->ev[1], s));
     if (q_kind == 0) {
       // y_hat = q, already float32; a caller-owned device out_yhat still has to receive it
       if (out_yhat && on_device(out_yhat) && d_yhat != d_q) CU_TRY(cudaMemcpyAsync(d_yhat, d_q, n_lat * 4, cudaMemcpyDeviceToDevice, s));
@@ -1226,11 +1241,80 @@ static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tenso
     }
     ycur.f32 = (const float*)d_yhat;
   }
-  CU_TRY(cudaEventRecord(m->ev[2], s));
+  if (!capturing) CU_TRY(cudaEventRecord(m->ev[2], s));
   {
     FinalOut fin; fin.u8 = (uint8_t*)d_u8; fin.crop = (float*)d_f32; fin.H = H; fin.W = W;
     TRY(run_transform(m, m->syn, false, ycur, B, hy, wy, &fin, nullptr, s));
   }
+  return SNTC_OK;
+  };
+  // ---- small batches are launch-bound (6 launches of 10-40 us each, ~60 us of host work per decode): replay the decode as ONE
+  // CUDA graph.  Eligible: every tensor device-resident, no metrics / rate / profiling (nothing returns to the host), batch <=
+  // SNTC_GRAPH_MAX_BATCH (4).  A (shapes, pointers, stream) key is run eagerly the first time (sizes the workspaces, uploads the
+  // band tables), captured the second time, replayed from then on; any change of a pointer -- the caller's or a workspace's --
+  // is a different key.  sntc_model_enable_graphs(m, 0) or SNTC_GRAPH=0 turns it off.
+  bool graph_ok = m->graphs_on && tc_env_int("SNTC_GRAPH", 1) != 0 && B <= tc_env_int("SNTC_GRAPH_MAX_BATCH", 4) && !original_u8 && !rate && !m->prof_on &&
+                  !tc_env_int("SNTC_TC_TRACE", 0) && on_device(q_y) && on_device(out_u8) && (!z_hat || on_device(z_hat)) && (!out_idx || on_device(out_idx)) &&
+                  (!out_yhat || on_device(out_yhat)) && (!out_f32 || on_device(out_f32));
+  bool ran = false;
+  if (graph_ok) {
+    GraphKey key{};
+    key.v[0] = B; key.v[1] = H; key.v[2] = W; key.v[3] = hy; key.v[4] = wy; key.v[5] = q_kind;
+    const void* ptrs[] = {d_q, d_z, d_u8, d_idx, d_f32, out_yhat ? tdata(out_yhat) : nullptr, (void*)s, m->ws_a.p, m->ws_b.p, m->d_yhat.p, m->d_hs.p, m->d_flag.p,
+                          m->tc.plane[0].p, m->tc.plane[1].p, m->tc.plane[2].p, m->tc.plane[3].p, m->tc.yh[0].p, m->tc.yh[1].p};
+    static_assert(sizeof(ptrs) / sizeof(ptrs[0]) <= sizeof(key.p) / sizeof(key.p[0]), "GraphKey too small");
+    for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) key.p[i] = ptrs[i];
+    GraphEntry* ge = nullptr;
+    for (auto& e : m->graphs) if (memcmp(&e.key, &key, sizeof(key)) == 0) { ge = &e; break; }
+    if (ge && ge->exec && ge->epoch != ctx->tc.table_epoch) {   // a band table was re-uploaded for another geometry since the capture
+      cudaGraphExecDestroy(ge->exec);
+      ge->exec = nullptr;
+      TRY(enqueue(false));                                       // re-uploads this geometry's tables; captured again on the next call
+      ran = true;
+    } else if (ge && ge->exec) {
+      CU_TRY(cudaGraphLaunch(ge->exec, s));
+      ctx->launches += ge->launches;
+      for (int i = 0; i < SNTC_LAUNCH_KINDS; ++i) ctx->kinds[i] += ge->kinds[i];
+      m->ev_valid = false;
+      ran = true;
+    } else if (ge && !ge->failed) {
+      const uint64_t l0 = ctx->launches;
+      uint64_t k0[SNTC_LAUNCH_KINDS];
+      for (int i = 0; i < SNTC_LAUNCH_KINDS; ++i) k0[i] = ctx->kinds[i];
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+      int r = ce == cudaSuccess ? enqueue(true) : SNTC_E_CUDA;
+      if (ce == cudaSuccess) ce = cudaStreamEndCapture(s, &graph);
+      if (r == SNTC_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&ge->exec, graph, 0) == cudaSuccess) {
+        ge->launches = ctx->launches - l0;
+        ge->epoch = ctx->tc.table_epoch;
+        for (int i = 0; i < SNTC_LAUNCH_KINDS; ++i) ge->kinds[i] = ctx->kinds[i] - k0[i];
+        cudaGraphDestroy(graph);
+        CU_TRY(cudaGraphLaunch(ge->exec, s));
+        m->ev_valid = false;
+        ran = true;
+      } else {   // capture refused (a workspace grew, an unsupported call ...): this key stays on the eager path
+        if (graph) cudaGraphDestroy(graph);
+        ge->exec = nullptr; ge->failed = true;
+        ctx->launches = l0;
+        for (int i = 0; i < SNTC_LAUNCH_KINDS; ++i) ctx->kinds[i] = k0[i];
+        cudaGetLastError();
+      }
+    }
+    if (!ran) {
+      TRY(enqueue(false));
+      ran = true;
+      if (!ge) {   // remember the key as it looks AFTER the eager run (workspaces sized)
+        const void* ptrs2[] = {d_q, d_z, d_u8, d_idx, d_f32, out_yhat ? tdata(out_yhat) : nullptr, (void*)s, m->ws_a.p, m->ws_b.p, m->d_yhat.p, m->d_hs.p, m->d_flag.p,
+                               m->tc.plane[0].p, m->tc.plane[1].p, m->tc.plane[2].p, m->tc.plane[3].p, m->tc.yh[0].p, m->tc.yh[1].p};
+        for (size_t i = 0; i < sizeof(ptrs2) / sizeof(ptrs2[0]); ++i) key.p[i] = ptrs2[i];
+        if (m->graphs.size() >= 16) { if (m->graphs.front().exec) cudaGraphExecDestroy(m->graphs.front().exec); m->graphs.erase(m->graphs.begin()); }
+        GraphEntry ne; ne.key = key;
+        m->graphs.push_back(ne);
+      }
+    }
+  }
+  if (!ran) TRY(enqueue(false));
   if (original_u8) {
     TRY(m->d_ssd.ensure((size_t)B * 8));
     if (m->h_ssd_cap < B) {
@@ -1251,8 +1335,7 @@ static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tenso
     CU_TRY(cudaMemcpyAsync(m->h_rate, m->d_rate.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s));
     need_sync = true;
   }
-  CU_TRY(cudaEventRecord(m->ev[3], s));
-  m->ev_valid = true;
+  CU_TRY(cudaEventRecord(m->ev[3], s));   // stage times are valid for eager decodes only (ev_valid)
   TRY(unstage_out(out_u8, n_img, d_u8, s, &need_sync));
   if (out_idx) TRY(unstage_out(out_idx, n_lat, d_idx, s, &need_sync));
   if (out_f32) TRY(unstage_out(out_f32, n_img * 4, d_f32, s, &need_sync));
@@ -1643,7 +1726,7 @@ extern "C" int sntc_allreduce_metrics(sntc_comm* c, double sums[5]) { return snt
 
 extern "C" int sntc_last_stage_times_ms(sntc_model* m, float out[4]) {
   if (!m || !out) return fail(SNTC_E_INVALID, "sntc_last_stage_times_ms: bad argument");
-  if (!m->ev_valid) return fail(SNTC_E_STATE, "sntc_last_stage_times_ms: no decode recorded yet");
+  if (!m->ev_valid) return fail(SNTC_E_STATE, "sntc_last_stage_times_ms: no eagerly launched decode recorded (graph replays carry no stage events: sntc_model_enable_graphs(m, 0))");
   CU_TRY(cudaSetDevice(m->ctx->device));
   CU_TRY(cudaEventSynchronize(m->ev[3]));
   CU_TRY(cudaEventElapsedTime(&out[0], m->ev[0], m->ev[1]));

@@ -1121,6 +1121,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 struct TcDriver {
   PFN_encodeTiled encode = nullptr;
   int num_sms = 148;
+  uint64_t table_epoch = 0;   // bumped whenever a band table is re-uploaded (its item_begin fields depend on the batch geometry):
+                              // CUDA graphs captured before the bump read stale tables and must not be replayed (decode_impl)
   std::string err;
   void init() {
     void* fn = nullptr;
@@ -1218,12 +1220,14 @@ inline int tc_bn_max() {
   if (v < 0) { v = tc_env_int("SNTC_TC_BN_MAX", 256); if (v < 16 || v > TC_ACC_COLS) v = 256; }
   return v;
 }
-inline bool tc_pdl() {
-  static int v = -1;
-  // OFF by default: measured on B200 (power-capped at ~1.67 GHz under this workload) the overlap of the next layer's
-  // prologue with this layer's tail changes the step time by less than the run-to-run noise (1.020 vs 1.013 ms).
-  if (v < 0) v = tc_env_int("SNTC_TC_PDL", 0) ? 1 : 0;
-  return v != 0;
+// Programmatic dependent launch between the kernels of one decode: the next kernel's prologue (barrier init, TMEM allocation,
+// tensor-map prefetch, weight-fragment loads) overlaps the tail of the previous one; every kernel executes griddepcontrol.wait
+// before it touches the previous kernel's output.  Measured on B200: +2-4 % at B <= 4 (launch-bound), nothing at B = 24 (one
+// CTA per SM owns all shared memory / TMEM, the successor cannot become resident early) -> auto: on for small batches.
+// SNTC_TC_PDL=0 / 1 forces it off / on.
+inline bool tc_pdl(int batch) {
+  static const int env = tc_env_int("SNTC_TC_PDL", -1);
+  return env >= 0 ? env != 0 : batch <= 4;
 }
 inline int tc_cta_group() {   // read when a model is finalized (not cached: tests build both variants in one process)
   const int v = tc_env_int("SNTC_TC_CTA_GROUP", 2);
@@ -1514,6 +1518,7 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
     e = cudaMemcpyAsync(d_bands, bands.data(), sizeof(TcBandDev) * nbands, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) { *err = std::string("band table upload: ") + cudaGetErrorString(e); return TC_ERROR; }
     uploaded_mtiles = mtiles * 2 + order_mode;
+    drv.table_epoch++;
   }
   P.bands = d_bands; P.nbands = nbands; P.total_items = item;
   P.kblocks = t.kblocks; P.last_kmma = t.last_kmma;
@@ -1576,7 +1581,7 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = tc_pdl() ? 2 : 1;
+    cfg.attrs = attr; cfg.numAttrs = tc_pdl(B) ? 2 : 1;
     e = cudaLaunchKernelEx(&cfg, band_gemm_tc_kernel<2>, mapAhi, mapAlo, P);
     if (e != cudaSuccess) { *err = std::string("band_gemm_tc_kernel<2> launch: ") + cudaGetErrorString(e); return TC_ERROR; }
   } else {
@@ -1585,7 +1590,7 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = tc_pdl() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = tc_pdl(B) ? 1 : 0;
     e = cudaLaunchKernelEx(&cfg, band_gemm_tc_kernel<1>, mapAhi, mapAlo, P);
     if (e != cudaSuccess) { *err = std::string("band_gemm_tc_kernel<1> launch: ") + cudaGetErrorString(e); return TC_ERROR; }
   }

@@ -170,6 +170,8 @@ class Model:
              else TransformDesc(kind=_lib.T_NONE))
     syn = self._synthesis.desc(self._bottleneck_size)
     self._native = _create_model(self._ctx, hyper, syn, self._weights, self.precision, self.index_rounding, prior=self._with_prior)
+    if self._profile:   # stage times come from CUDA events around eagerly launched kernels: no graph replay
+      check(lib.sntc_model_enable_graphs(self._native.handle, 0))
 
   @property
   def ctx(self) -> Context:

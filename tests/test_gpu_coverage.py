@@ -345,3 +345,40 @@ def test_nccl_group_of_one_rank(gpu_ctx, tmp_path):
   assert np.array_equal(g.allreduce_sum(v), v) and np.array_equal(parallel.max_over_ranks(g, v), v)
   g.barrier()
   g.close()
+
+
+# --------------------------------------------------------------------------------------------------
+# small-batch decodes replayed as CUDA graphs (+ programmatic dependent launch): same bytes as the eager launches
+
+@pytest.mark.parametrize("name", ["jpegl", "two_layer_syn", "two_layer_syn2:24", "bls2017"])
+def test_cuda_graph_replay_of_small_batches_is_bit_identical(gpu_ctx, name, monkeypatch):
+  H, W = 200, 300
+  model, wts, z, q = make_case(name, 2, H, W, "stress", "tc", gpu_ctx)
+  hyper = model.hyperprior
+  args = (lambda zz, qq: (zz, qq, (H, W))) if hyper else (lambda zz, qq: (qq, (H, W)))
+  host = model.decompress(*args(z, q), return_yhat=hyper)                       # host tensors: always eager
+  other = model.decompress(*args(z[:1], q[:1]))                                  # a second geometry in between
+  dz, dq = (gpu_ctx.to_device(z) if hyper else None), gpu_ctx.to_device(q.astype(np.int16))
+  out = dict(image=gpu_ctx.to_device(np.full((2, H, W, 3), 0x5A, np.uint8)))
+  if hyper:
+    out["idx"] = gpu_ctx.empty(q.shape, np.uint8)
+    out["y_hat"] = gpu_ctx.empty(q.shape, np.float32)
+  n0 = gpu_ctx.launch_counts["total"]
+  per_call = []
+  for it in range(6):                                                            # eager, capture, replay x4
+    out["image"].fill_bytes(0x5A)
+    gpu_ctx.sync()
+    before = gpu_ctx.launch_counts["total"]
+    got = model.decompress(*args(dz, dq), return_yhat=hyper, out=out)
+    per_call.append(gpu_ctx.launch_counts["total"] - before)
+    assert np.array_equal(got["image"].to_host(), host["image"]), it
+    if hyper:
+      assert np.array_equal(got["idx"].to_host(), host["idx"]) and np.array_equal(got["y_hat"].to_host(), host["y_hat"]), it
+    if it == 3:                                                                  # another geometry on the same model re-uploads band tables
+      again = model.decompress(*args(z[:1], q[:1]))
+      assert np.array_equal(again["image"], other["image"])
+  assert len(set(per_call)) == 1 and per_call[0] >= 2, per_call                 # replays account for the kernels they launch
+  # graphs off: same bytes
+  monkeypatch.setenv("SNTC_GRAPH", "0")
+  got = model.decompress(*args(dz, dq), out=out)
+  assert np.array_equal(got["image"].to_host(), host["image"])
