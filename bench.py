@@ -292,8 +292,9 @@ def main():
   ap.add_argument("--e2e-depth", type=int, default=2, help="device buffer sets of the streaming pipeline (copy/compute overlap); measured 2 / 3 / 4: 8.52 / 8.14 / 8.07 Gpx/s")
   ap.add_argument("--height", type=int, default=512, help="image height (side runs of the other BASELINE configs; the headline is 512x768)")
   ap.add_argument("--width", type=int, default=768)
-  ap.add_argument("--tile-bands", type=int, default=0, help="split every frame into this many latent-row bands (halo recomputed) and give rank r band r: "
-                                                              "the intra-frame sharding of BASELINE configs[4]; 0 = whole frames per rank")
+  ap.add_argument("--tile-frames", action="store_true", help="intra-frame sharding (BASELINE configs[4]): every frame is split into WORLD_SIZE latent-row bands "
+                                                             "(halo recomputed, shallow_ntc_b200/tiling.py) and rank r decodes band r of the same `batch` frames: strong scaling of a frame; "
+                                                             "default = whole frames per rank (weak scaling)")
   args = ap.parse_args()
   global H, W
   H, W = args.height, args.width
@@ -326,12 +327,20 @@ def main():
   model = make_model(precision)       # no fallback: a box without the tcgen05 path fails here, loudly
 
   zs, ys = model.latent_shapes(B, H, W)
+  hyper = zs is not None                      # the factorized model (bls2017) has no z_hat and no scale indexes
+  frame_h, band = H, None
   # this rank's shard of the seeded image list; `rotate` distinct batches so consecutive steps never reuse inputs
   sets = []
   for r in range(args.rotate):
-    z, q = synthetic.make_latents(zs, ys, first_index=(rank * args.rotate + r) * B)
+    z, q = synthetic.make_latents(zs, ys, first_index=((0 if args.tile_frames else rank) * args.rotate + r) * B)
     sets.append((z, q))
-  hyper = zs is not None                      # the factorized model (bls2017) has no z_hat and no scale indexes
+  if args.tile_frames and world > 1:
+    # every rank holds band `rank` (rows + halo) of the SAME frames: what the range decoder of a tiled stream would hand it
+    band = model.band_plan((H, W), world)[rank]
+    sets = [model.band_inputs(z, q, band) for z, q in sets]
+    H = band.sub_h                            # from here on this rank decodes a (sub_h x W) "image"; its own rows are band.rows
+    zs, ys = model.latent_shapes(B, H, W)
+    assert tuple(sets[0][1].shape) == tuple(ys), (sets[0][1].shape, ys)
   dev = [(ctx.to_device(z) if hyper else None, ctx.to_device(q)) for z, q in sets]
   out_dev = dict(image=ctx.empty((B, H, W, 3), np.uint8))
   if hyper:
@@ -499,8 +508,11 @@ def main():
   if rank == 0:
     headline = args.config == "two_layer_syn" and (H, W) == (512, 768)
     workload = (f"mshyper two_layer_syn decode (BASELINE configs[1]): {B} x 768x512 per GPU, random-init 'stress' weights" if headline else
-                f"{args.config} decode (side run, not the headline workload): {B} x {W}x{H} per GPU, random-init 'stress' weights")
-    px_step = world * B * H * W
+                f"{args.config} decode (side run, not the headline workload): {B} x {W}x{frame_h} per GPU, random-init 'stress' weights")
+    if band is not None:
+      workload = (f"{args.config} decode, intra-frame sharding: {B} frames of {W}x{frame_h} split into {world} latent-row bands, one band (+ recomputed halo) per GPU; "
+                  f"rank 0 decodes rows {band.rows} from a {H}-row sub-frame")
+    px_step = B * frame_h * W if band is not None else world * B * H * W      # tiled: all ranks work on the same frames
     mpx = lambda t_ms: px_step * args.steps / (t_ms * 1e-3) / 1e6
     value = mpx(ms)
     # dominant kernel = the layer with the largest share of device time
@@ -537,7 +549,7 @@ def main():
                               note="aggregate page-locked copy GB/s over all ranks copying at once, buffers of the e2e step's sizes ('both' = the two "
                                    "directions concurrently): the roofline of the e2e numbers on this box"))
     line = dict(metric="decoded Mpx/s", value=value, unit="Mpx/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong" if band is not None else "weak", vs_baseline=None,
                 dtype="f32" if precision == "fp32" else "f16x3-split/f32-accum", data="synthetic",
                 config=dict(workload=workload,
                             images_per_gpu=B, precision=precision, index_rounding=model.index_rounding,

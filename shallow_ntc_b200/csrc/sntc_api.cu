@@ -67,7 +67,7 @@ struct sntc_ctx {
 };
 
 struct GraphKey { long long v[6]; const void* p[20]; };
-struct GraphEntry { GraphKey key{}; cudaGraphExec_t exec = nullptr; bool failed = false; uint64_t epoch = 0; uint64_t launches = 0; uint64_t kinds[SNTC_LAUNCH_KINDS] = {0, 0, 0, 0, 0, 0}; };
+struct GraphEntry { GraphKey key{}; cudaGraphExec_t exec = nullptr; bool failed = false; uint64_t launches = 0; uint64_t kinds[SNTC_LAUNCH_KINDS] = {0, 0, 0, 0, 0, 0}; };
 
 struct ProfRec { std::string label; cudaEvent_t a = nullptr, b = nullptr; double macs = 0; };
 struct ProfAgg { std::string label; float ms = 0; int n = 0; double macs = 0; };
@@ -1266,12 +1266,7 @@ static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tenso
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) key.p[i] = ptrs[i];
     GraphEntry* ge = nullptr;
     for (auto& e : m->graphs) if (memcmp(&e.key, &key, sizeof(key)) == 0) { ge = &e; break; }
-    if (ge && ge->exec && ge->epoch != ctx->tc.table_epoch) {   // a band table was re-uploaded for another geometry since the capture
-      cudaGraphExecDestroy(ge->exec);
-      ge->exec = nullptr;
-      TRY(enqueue(false));                                       // re-uploads this geometry's tables; captured again on the next call
-      ran = true;
-    } else if (ge && ge->exec) {
+    if (ge && ge->exec) {
       CU_TRY(cudaGraphLaunch(ge->exec, s));
       ctx->launches += ge->launches;
       for (int i = 0; i < SNTC_LAUNCH_KINDS; ++i) ctx->kinds[i] += ge->kinds[i];
@@ -1287,7 +1282,6 @@ static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tenso
       if (ce == cudaSuccess) ce = cudaStreamEndCapture(s, &graph);
       if (r == SNTC_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&ge->exec, graph, 0) == cudaSuccess) {
         ge->launches = ctx->launches - l0;
-        ge->epoch = ctx->tc.table_epoch;
         for (int i = 0; i < SNTC_LAUNCH_KINDS; ++i) ge->kinds[i] = ctx->kinds[i] - k0[i];
         cudaGraphDestroy(graph);
         CU_TRY(cudaGraphLaunch(ge->exec, s));

@@ -45,7 +45,8 @@ struct alignas(64) TcBandDev {
   CUtensorMap mapBhi, mapBlo;     // packed K-major band matrix, hi / lo fp16 planes
   int phy0, nphx, phx0, Ty, Tx, mloy, mlox;
   int N, BN, ntiles;
-  int item_begin;                 // first work item (m-tile, n-tile) of this band in the layer's item list
+  int item_begin;                 // n-tiles of all bands before this one (static).  First work item of the band: item_begin * m-tile groups
+                                  // (band-major order) or slot item_begin of every group (group-major order)
   int oshift;                     // added to the output coordinate (merged bands: s*dlo + p, see ConvLayer::merged)
   int pad_[4];
 };
@@ -54,6 +55,7 @@ struct TcParams {
   const TcBandDev* bands; int nbands; int total_items;
   int ipg;            // > 0: items are m-tile-group major (item = group * ipg + slot, bands[].item_begin = first slot of the band:
                       // a unit walks through all bands, so heavy-MMA and heavy-epilogue items alternate); 0: band major
+                      // (items of band i start at bands[i].item_begin * groups).  The band table itself never depends on the batch.
   int B, hin, win, s, p;
   int TH, TW, tiles_y, tiles_x;
   int kblocks;        // 64-channel blocks per tap
@@ -309,9 +311,10 @@ __device__ __forceinline__ TcItem tc_decode_item(const TcParams& P, int item, in
       if (slot >= P.bands[i].item_begin) bi = i;
     nt = slot - P.bands[bi].item_begin;
   } else {
+    const int groups = (P.mtiles + CG - 1) / CG;
     for (int i = 1; i < P.nbands; ++i)
-      if (item >= P.bands[i].item_begin) bi = i;
-    const int local = item - P.bands[bi].item_begin;
+      if (item >= P.bands[i].item_begin * groups) bi = i;
+    const int local = item - P.bands[bi].item_begin * groups;
     nt = local % P.bands[bi].ntiles; mg = local / P.bands[bi].ntiles;
   }
   const TcBandDev& bd = P.bands[bi];
@@ -1121,8 +1124,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 struct TcDriver {
   PFN_encodeTiled encode = nullptr;
   int num_sms = 148;
-  uint64_t table_epoch = 0;   // bumped whenever a band table is re-uploaded (its item_begin fields depend on the batch geometry):
-                              // CUDA graphs captured before the bump read stale tables and must not be replayed (decode_impl)
   std::string err;
   void init() {
     void* fn = nullptr;
@@ -1152,11 +1153,10 @@ struct TcConv {
   std::vector<int> items_per_mtile;                        // n-tiles per band
   TcBandDev* d_bands = nullptr;
   int nbands = 0;
-  int uploaded_mtiles = -1;                                // geometry the device band table was built for
   // Second tiling of the same packed weights with narrow n-tiles (<= 64 columns), for batches whose wide tiling has
   // fewer work items than half the persistent units (a single 768x512 image gives the 3x3 hyper head 18 items for 74
   // CTA pairs): more, shorter items -> the layer's latency drops with the serial K loop of one item.
-  struct Tiling { std::vector<TcBandDev> bands; TcBandDev* d_bands = nullptr; int nbands = 0, bn_max = 16, stages = 2, uploaded_mtiles = -1; } narrow;
+  struct Tiling { std::vector<TcBandDev> bands; TcBandDev* d_bands = nullptr; int nbands = 0, bn_max = 16, stages = 2; } narrow;
 };
 
 inline int tc_env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
@@ -1356,8 +1356,11 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
     const int reserve = 2048 + (c.cout + (pixel_cols >= 48 ? 48 * 48 + 48 + 8 : 700)) * 4;   // alignment slack + barriers + epilogue constants (bias | gamma | beta)
     stages = std::min(8, (227 * 1024 - reserve) / stage_bytes);
     if (stages < 2) { *err = "not enough shared memory for a 2-stage pipeline"; return false; }
+    int prefix = 0;
+    for (auto& bd : bands) { bd.item_begin = prefix; prefix += bd.ntiles; }
     if (cudaMalloc((void**)&d_bands, sizeof(TcBandDev) * std::max(1, nbands)) != cudaSuccess) { *err = "cudaMalloc (band table) failed"; return false; }
     owned.push_back(d_bands);
+    if (nbands > 0 && cudaMemcpy(d_bands, bands.data(), sizeof(TcBandDev) * nbands, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy (band table) failed"; return false; }
     return true;
   };
   if (!build_tiling(tc_bn_max(), t.bands, t.nbands, t.bn_max, t.stages, t.d_bands)) return false;
@@ -1503,23 +1506,13 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   std::vector<TcBandDev>& bands = narrow ? t.narrow.bands : t.bands;
   TcBandDev* const d_bands = narrow ? t.narrow.d_bands : t.d_bands;
   const int nbands = narrow ? t.narrow.nbands : t.nbands, bn_max = narrow ? t.narrow.bn_max : t.bn_max, stages = narrow ? t.narrow.stages : t.stages;
-  int& uploaded_mtiles = narrow ? t.narrow.uploaded_mtiles : t.uploaded_mtiles;
-  int item = 0;
-  if (order_mode) {
-    for (auto& bd : bands) { bd.item_begin = item; item += bd.ntiles; }
-    P.ipg = item;
-    item *= groups;
-  } else {
-    for (auto& bd : bands) { bd.item_begin = item; item += groups * bd.ntiles; }
-  }
-  // the band table depends on the batch geometry only through item_begin: refresh it when that changes
+  // the device band table is static (uploaded once at finalize: no in-stream uploads, so the launches are safe to capture into
+  // a CUDA graph and to overlap with programmatic dependent launch); only the item count depends on the batch
+  int per_group = 0;
+  for (auto& bd : bands) per_group += bd.ntiles;
+  if (order_mode) P.ipg = per_group;
+  const int item = per_group * groups;
   cudaError_t e = cudaSuccess;
-  if (uploaded_mtiles != mtiles * 2 + order_mode) {
-    e = cudaMemcpyAsync(d_bands, bands.data(), sizeof(TcBandDev) * nbands, cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) { *err = std::string("band table upload: ") + cudaGetErrorString(e); return TC_ERROR; }
-    uploaded_mtiles = mtiles * 2 + order_mode;
-    drv.table_epoch++;
-  }
   P.bands = d_bands; P.nbands = nbands; P.total_items = item;
   P.kblocks = t.kblocks; P.last_kmma = t.last_kmma;
   P.cout = c.cout; P.bn_max = bn_max; P.stages = stages;
