@@ -162,16 +162,17 @@ def to_tf(arr):
   return _tf().experimental.dlpack.from_dlpack(to_dlpack(arr))
 
 
-def symbols_of(tf_model, image, training=False):
+def symbols_of(tf_model, image):
   """The integer symbols the decode starts from, computed with the reference's own encoder side (out of scope here):
   ``infer_latent_rvs`` (mshyper/models.py:212-232) -> z_hat = round(z) (:253-259), mu from the reference hyper-synthesis,
   q = round(y - mu) (:278-283, latent_rvs_lib.py:95-102).  Returns numpy (z_hat | None, q) ready for ``Model.decompress``."""
   tf = _tf()
-  rvs = tf_model.infer_latent_rvs(image, training=training)
-  y = rvs["latent"].loc if hasattr(rvs["latent"], "loc") else rvs["latent"]
+  rvs = tf_model.infer_latent_rvs(image)            # LatentRVCollection(uq=(UQLatentRV(z), UQLatentRV(y))); (rvs, timing) when profile=True
+  if isinstance(rvs, tuple):
+    rvs = rvs[0]
   if getattr(tf_model, "_hyper_synthesis", None) is None:
-    return None, np.rint(_np(y))
-  z = rvs["hyper_latent"].loc if hasattr(rvs["hyper_latent"], "loc") else rvs["hyper_latent"]
+    return None, np.rint(_np(rvs.uq[0].loc))       # factorized/models.py:70-87: uq = (UQLatentRV(y),)
+  z, y = rvs.uq[0].loc, rvs.uq[1].loc
   z_hat = tf.round(z)
   hs = tf_model._hyper_synthesis(z_hat)
   if isinstance(hs, tuple):          # profile=True: (result, seconds)
