@@ -223,6 +223,21 @@ int sntc_decode_rd(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q
  * SNTC_E_INVALID when the smallest of the 5 scales is below the 11x11 window (TensorFlow asserts there too). */
 int sntc_image_msssim(sntc_ctx* ctx, const sntc_tensor* a_u8, const sntc_tensor* b_u8, double* msssim, void* stream);
 
+/* LPIPS per image of two image batches [B,H,W,3] (uint8, or float32 in [0, 255]; host or device), on the device: the `lpips`
+ * column of the evaluate records -- learned_perceptual_metric_model([image_batch, reconstruction]) of the vendored lpips_tf2
+ * (lpips_tf2/lpips_tensorflow.py:14-72, called at mshyper/models.py:334-340, factorized/models.py:158-164): Keras VGG16 features of five
+ * blocks, unit-normalised over channels, squared difference, learned 1x1 weights, spatial mean, sum over layers.
+ * Variables (sntc_lpips_load_weights, float32, Keras layouts): lpips.conv_i.kernel [3,3,Cin,Cout], lpips.conv_i.bias [Cout]
+ * (i = 0..12: the 13 VGG16 convolutions in order), lpips.lin_l.kernel [C_l] (l = 0..4: the five Conv2D(1, 1, use_bias=False)).
+ * precision: SNTC_PRECISION_TC_F16X3 runs conv_1 .. conv_12 on the tcgen05 band GEMM, SNTC_PRECISION_FP32 everything on FFMA.
+ * lpips[B] (host) is valid on return; per_layer[B][5] (nullable) receives the five layer terms. */
+typedef struct sntc_lpips sntc_lpips;
+int sntc_lpips_create(sntc_ctx* ctx, int precision, sntc_lpips** out);
+int sntc_lpips_destroy(sntc_lpips* lp);
+int sntc_lpips_load_weights(sntc_lpips* lp, const char* name, const float* host, const int64_t* shape, int ndim);
+int sntc_lpips_finalize(sntc_lpips* lp);
+int sntc_image_lpips(sntc_lpips* lp, const sntc_tensor* a, const sntc_tensor* b, double* lpips, double* per_layer, void* stream);
+
 /* ---- two-phase decode ----
  * A real decoder cannot have q_y before it knows the scale-table rows: the range decoder needs idx to pick the CDF
  * of every symbol (tfc LocationScaleIndexedEntropyModel.decompress(strings, indexes, loc)).  Phase 1 runs

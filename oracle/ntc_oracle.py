@@ -534,3 +534,94 @@ def count_params(wts, prefix):
 def convt_macs(h, w, k, s, cin, cout):
   """MACs of a transposed conv as TF's profiler counts them: every (input pixel, tap) pair."""
   return h * w * k * k * cin * cout
+
+
+# --------------------------------------------------------------------------
+# LPIPS (evaluate-loop metric, SURVEY row f4): lpips_tf2/lpips_tensorflow.py:14-72 as called by mshyper/models.py:334-340
+
+VGG_BLOCKS = ((64, 64), (128, 128), (256, 256, 256), (512, 512, 512), (512, 512, 512))   # Keras VGG16 conv stacks, block1 .. block5
+LPIPS_SCALE = (0.458, 0.448, 0.450)     # image_preprocess, lpips_tensorflow.py:18-19
+LPIPS_SHIFT = (-0.030, -0.088, -0.188)
+
+
+def lpips_variable_shapes():
+  """name -> shape: 13 VGG16 convs ``lpips.conv_i.kernel`` [3,3,Cin,Cout] / ``.bias`` (Keras Conv2D layout) and the five
+  1x1 ``lpips.lin_l.kernel`` [C_l] (Conv2D(1, 1, use_bias=False) over channels)."""
+  v, cin, i = {}, 3, 0
+  for block in VGG_BLOCKS:
+    for cout in block:
+      v[f"lpips.conv_{i}.kernel"] = (3, 3, cin, cout)
+      v[f"lpips.conv_{i}.bias"] = (cout,)
+      cin, i = cout, i + 1
+  for l, block in enumerate(VGG_BLOCKS):
+    v[f"lpips.lin_{l}.kernel"] = (block[-1],)
+  return v
+
+
+def conv2d_same(x, kernel_io, bias, dtype=np.float64):
+  """Keras Conv2D(3x3, padding='same', strides 1): out[o] = sum_a x[o + a - 1] * K[a]  (cross-correlation), kernel [kh,kw,Cin,Cout]."""
+  x = np.asarray(x, dtype=dtype)
+  k = np.asarray(kernel_io, dtype=dtype)
+  B, h, w, cin = x.shape
+  kh, kw = k.shape[:2]
+  ph, pw = (kh - 1) // 2, (kw - 1) // 2
+  xp = np.zeros((B, h + kh - 1, w + kw - 1, cin), dtype=dtype)
+  xp[:, ph:ph + h, pw:pw + w] = x
+  out = np.zeros((B, h, w, k.shape[3]), dtype=dtype)
+  for ay in range(kh):
+    for ax in range(kw):
+      out += xp[:, ay:ay + h, ax:ax + w] @ k[ay, ax]
+  return out + np.asarray(bias, dtype=dtype)
+
+
+def maxpool2(x):
+  """Keras MaxPooling2D(2, 2, 'valid'): odd trailing rows / columns are dropped."""
+  B, h, w, c = x.shape
+  x = x[:, :h // 2 * 2, :w // 2 * 2]
+  return x.reshape(B, h // 2, 2, w // 2, 2, c).max(axis=(2, 4))
+
+
+def vgg16_features(wts, x, dtype=np.float64, prefix="lpips"):
+  """perceptual_model (lpips_tensorflow.py:124-136): outputs of block1_conv2, block2_conv2, block3_conv3, block4_conv3, block5_conv3."""
+  feats, i = [], 0
+  for b, block in enumerate(VGG_BLOCKS):
+    if b > 0:
+      x = maxpool2(x)
+    for _ in block:
+      x = relu(conv2d_same(x, wts[f"{prefix}.conv_{i}.kernel"], wts[f"{prefix}.conv_{i}.bias"], dtype))
+      i += 1
+    feats.append(x)
+  return feats
+
+
+def lpips(wts, image_a, image_b, dtype=np.float64, prefix="lpips", return_layers=False):
+  """learned_perceptual_metric_model([a, b]) for images [B,H,W,3] in [0, 255] (the reference passes image_batch and
+  reconstruction as they are, mshyper/models.py:339): preprocess, VGG16 features, unit-normalise over channels (x * rsqrt(sum x^2),
+  NO epsilon: an all-zero feature vector gives NaN, as in the reference), squared difference, 1x1 lin, spatial mean, sum over layers."""
+  def pre(im):
+    x = np.asarray(im, dtype=dtype) / 127.5 - 1.0
+    return (x - np.asarray(LPIPS_SHIFT, dtype=dtype)) / np.asarray(LPIPS_SCALE, dtype=dtype)
+  fa, fb = vgg16_features(wts, pre(image_a), dtype, prefix), vgg16_features(wts, pre(image_b), dtype, prefix)
+  per_layer = []
+  with np.errstate(divide="ignore", invalid="ignore"):
+    for l, (a, b) in enumerate(zip(fa, fb)):
+      na = a * (1.0 / np.sqrt(np.sum(a * a, axis=-1, keepdims=True)))
+      nb = b * (1.0 / np.sqrt(np.sum(b * b, axis=-1, keepdims=True)))
+      d = (na - nb) ** 2 @ np.asarray(wts[f"{prefix}.lin_{l}.kernel"], dtype=dtype)
+      per_layer.append(d.mean(axis=(1, 2)))
+  total = np.sum(per_layer, axis=0)
+  return (total, np.stack(per_layer, axis=-1)) if return_layers else total
+
+
+def lpips_weights_from_reference_checkpoints(vgg_prefix, lin_prefix, prefix="lpips"):
+  """The vendored checkpoints of the reference (lpips_tf2/models/{vgg,lin}/exported, read with oracle/tf_checkpoint.py) under
+  the names above.  Keras tracks ``layer_with_weights-i`` in layer order: VGG16's 13 convs, the linear model's five 1x1 convs."""
+  from . import tf_checkpoint
+  vgg, lin = tf_checkpoint.load_checkpoint(vgg_prefix), tf_checkpoint.load_checkpoint(lin_prefix)
+  w = {}
+  for i in range(13):
+    w[f"{prefix}.conv_{i}.kernel"] = vgg[f"layer_with_weights-{i}/kernel/.ATTRIBUTES/VARIABLE_VALUE"]
+    w[f"{prefix}.conv_{i}.bias"] = vgg[f"layer_with_weights-{i}/bias/.ATTRIBUTES/VARIABLE_VALUE"]
+  for l in range(5):
+    w[f"{prefix}.lin_{l}.kernel"] = lin[f"layer_with_weights-{l}/kernel/.ATTRIBUTES/VARIABLE_VALUE"].reshape(-1)
+  return w

@@ -10,7 +10,8 @@ from .tensors import Context, DeviceArray, as_tensor  # noqa: F401
 from .pipeline import DecodePipeline  # noqa: F401
 from .codec import EntropyCoder  # noqa: F401
 from . import codec, eval_lib  # noqa: F401
+from .lpips import Lpips  # noqa: F401
 from ._lib import SntcError, EXPORTED_SYMBOLS, LIB_PATH  # noqa: F401
 
 __all__ = ["class_builder", "ClassBuilder", "Model", "FactorizedModel", "CONFIGS", "build_config", "Context",
-           "DeviceArray", "as_tensor", "DecodePipeline", "EntropyCoder", "codec", "eval_lib", "SntcError", "EXPORTED_SYMBOLS", "LIB_PATH"]
+           "DeviceArray", "as_tensor", "DecodePipeline", "EntropyCoder", "Lpips", "codec", "eval_lib", "SntcError", "EXPORTED_SYMBOLS", "LIB_PATH"]

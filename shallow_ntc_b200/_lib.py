@@ -70,6 +70,11 @@ _PROTOS = {
   "sntc_device_name": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
   "sntc_device_pci_bus_id": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
   "sntc_image_msssim": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(C.c_double), _P]),
+  "sntc_lpips_create": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+  "sntc_lpips_destroy": (C.c_int, [_P]),
+  "sntc_lpips_load_weights": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.c_int]),
+  "sntc_lpips_finalize": (C.c_int, [_P]),
+  "sntc_image_lpips": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(C.c_double), C.POINTER(C.c_double), _P]),
   "sntc_model_create": (C.c_int, [_P, C.POINTER(ModelDesc), C.POINTER(_P)]),
   "sntc_model_destroy": (C.c_int, [_P]),
   "sntc_model_num_variables": (C.c_int, [_P]),

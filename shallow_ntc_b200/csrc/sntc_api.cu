@@ -19,6 +19,7 @@
 #include "sntc_kernels_tail_tc.cuh"
 #include "sntc_kernels_tail_mma.cuh"
 #include "sntc_kernels_msssim.cuh"
+#include "sntc_kernels_lpips.cuh"
 #include "sntc_coder.hpp"
 
 using namespace sntc;
@@ -1717,6 +1718,248 @@ extern "C" int sntc_comm_allreduce_f64(sntc_comm* c, double* values, int n, int 
 }
 
 extern "C" int sntc_allreduce_metrics(sntc_comm* c, double sums[5]) { return sntc_comm_allreduce_f64(c, sums, 5, SNTC_REDUCE_SUM); }
+
+
+// ------------------------------------------------------------------------------------------------
+// LPIPS of two image batches (evaluate-loop metric; see sntc_kernels_lpips.cuh)
+struct sntc_lpips {
+  sntc_ctx* ctx = nullptr;
+  int precision = SNTC_PRECISION_TC_F16X3;
+  std::vector<ConvLayer> convs;          // 13 x ConvT(3, 1, p = 1) with the flipped VGG16 kernels, relu fused
+  std::vector<TcConv> tc;                // tensor-core packing of conv_1 .. conv_12
+  std::vector<int> block_last;           // index of the last conv of each VGG block (the tapped layers)
+  HostWeights hw;
+  float* d_lin[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<void*> owned;
+  bool finalized = false;
+  DevBuf f_a, f_b, st_a, st_b, slots, d_out;
+  TcDevBuf plane[4];
+  double* h_out = nullptr; int h_out_cap = 0;
+};
+
+static const int LPIPS_BLOCKS[5][3] = {{64, 64, 0}, {128, 128, 0}, {256, 256, 256}, {512, 512, 512}, {512, 512, 512}};
+
+extern "C" int sntc_lpips_create(sntc_ctx* ctx, int precision, sntc_lpips** out) {
+  if (!ctx || !out) return fail(SNTC_E_INVALID, "sntc_lpips_create: bad argument");
+  *out = nullptr;
+  if (precision != SNTC_PRECISION_FP32 && precision != SNTC_PRECISION_TC_F16X3) return fail(SNTC_E_INVALID, "sntc_lpips_create: precision must be FP32 or TC_F16X3");
+  auto lp = std::make_unique<sntc_lpips>();
+  lp->ctx = ctx; lp->precision = precision;
+  int cin = 3, i = 0;
+  for (int b = 0; b < 5; ++b) {
+    for (int j = 0; j < 3 && LPIPS_BLOCKS[b][j]; ++j, ++i) {
+      const int cout = LPIPS_BLOCKS[b][j];
+      lp->convs.push_back(make_conv("lpips", "conv_" + std::to_string(i), 3, 1, cin, cout, LAYOUT_TFC_IO, true, SNTC_ACT_RELU));
+      cin = cout;
+    }
+    lp->block_last.push_back(i - 1);
+  }
+  *out = lp.release();
+  return SNTC_OK;
+}
+
+extern "C" int sntc_lpips_destroy(sntc_lpips* lp) {
+  if (!lp) return SNTC_OK;
+  cudaSetDevice(lp->ctx->device);
+  cudaStreamSynchronize(lp->ctx->stream);
+  for (void* p : lp->owned) cudaFree(p);
+  for (DevBuf* b : {&lp->f_a, &lp->f_b, &lp->st_a, &lp->st_b, &lp->slots, &lp->d_out}) b->release();
+  for (auto& b : lp->plane) b.release();
+  if (lp->h_out) cudaFreeHost(lp->h_out);
+  delete lp;
+  return SNTC_OK;
+}
+
+// Variables: lpips.conv_i.kernel [3,3,Cin,Cout] / lpips.conv_i.bias [Cout] (Keras Conv2D layouts, i = 0..12), lpips.lin_l.kernel [C_l] (l = 0..4)
+extern "C" int sntc_lpips_load_weights(sntc_lpips* lp, const char* name, const float* host, const int64_t* shape, int ndim) {
+  if (!lp || !name || !host || !shape) return fail(SNTC_E_INVALID, "sntc_lpips_load_weights: bad argument");
+  if (lp->finalized) return fail(SNTC_E_STATE, "sntc_lpips_load_weights: already finalized");
+  std::vector<int64_t> want;
+  const std::string n(name);
+  for (size_t i = 0; i < lp->convs.size(); ++i) {
+    const ConvLayer& c = lp->convs[i];
+    if (n == c.sources[0].kernel) want = {3, 3, c.cin, c.cout};
+    if (n == c.sources[0].bias) want = {c.cout};
+  }
+  for (int l = 0; l < 5; ++l)
+    if (n == "lpips.lin_" + std::to_string(l) + ".kernel") want = {lp->convs[lp->block_last[l]].cout};
+  if (want.empty()) return fail(SNTC_E_INVALID, "sntc_lpips_load_weights: unknown variable " + n);
+  if ((int)want.size() != ndim) return fail(SNTC_E_INVALID, "sntc_lpips_load_weights: rank mismatch for " + n);
+  size_t cnt = 1;
+  for (int d = 0; d < ndim; ++d) { if (shape[d] != want[d]) return fail(SNTC_E_INVALID, "sntc_lpips_load_weights: shape mismatch for " + n); cnt *= (size_t)shape[d]; }
+  for (size_t i = 0; i < cnt; ++i) if (!std::isfinite(host[i])) return fail(SNTC_E_INVALID, "sntc_lpips_load_weights: non-finite value in " + n);
+  std::vector<float> v(host, host + cnt);
+  if (ndim == 4) {   // correlation kernel K[a] -> transposed-conv kernel W[a'] = K[2 - a'] (same [kh,kw,Cin,Cout] layout)
+    const size_t plane = (size_t)shape[2] * shape[3];
+    for (int ay = 0; ay < 3; ++ay) for (int ax = 0; ax < 3; ++ax)
+      memcpy(&v[((size_t)ay * 3 + ax) * plane], host + ((size_t)(2 - ay) * 3 + (2 - ax)) * plane, plane * sizeof(float));
+  }
+  lp->hw[n] = {std::vector<int64_t>(shape, shape + ndim), std::move(v)};
+  return SNTC_OK;
+}
+
+extern "C" int sntc_lpips_finalize(sntc_lpips* lp) {
+  if (!lp) return fail(SNTC_E_INVALID, "sntc_lpips_finalize: NULL");
+  if (lp->finalized) return SNTC_OK;
+  CU_TRY(cudaSetDevice(lp->ctx->device));
+  for (auto& c : lp->convs)
+    for (const std::string& nm : {c.sources[0].kernel, c.sources[0].bias})
+      if (!lp->hw.count(nm)) return fail(SNTC_E_STATE, "sntc_lpips_finalize: missing variable " + nm);
+  auto up = [&](const void* h, size_t bytes, void** d) -> int {
+    CU_TRY(cudaMalloc(d, bytes ? bytes : 4));
+    lp->owned.push_back(*d);
+    CU_TRY(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+    return SNTC_OK;
+  };
+  lp->tc.assign(lp->convs.size(), TcConv{});
+  for (size_t i = 0; i < lp->convs.size(); ++i) {
+    ConvLayer& c = lp->convs[i];
+    std::vector<float> b = pack_bias(c, lp->hw);
+    TRY(up(b.data(), b.size() * 4, (void**)&c.d_bias));
+    c.h_bias = b;
+    const bool on_tc = lp->precision == SNTC_PRECISION_TC_F16X3 && tc_conv_supported(c);
+    if (on_tc) {
+      std::string err;
+      if (!lp->ctx->tc.encode) return fail(SNTC_E_CUDA, "sntc_lpips_finalize: cuTensorMapEncodeTiled unavailable");
+      if (!tc_pack_conv(lp->ctx->tc, c, lp->hw, lp->tc[i], 0, lp->owned, &err)) return fail(SNTC_E_CUDA, "sntc_lpips_finalize: " + err);
+    } else {
+      std::vector<float> w = pack_band_weights(c, lp->hw);
+      TRY(up(w.data(), w.size() * 4, (void**)&c.d_w));
+    }
+  }
+  for (int l = 0; l < 5; ++l) {
+    const std::string nm = "lpips.lin_" + std::to_string(l) + ".kernel";
+    if (!lp->hw.count(nm)) return fail(SNTC_E_STATE, "sntc_lpips_finalize: missing variable " + nm);
+    const auto& v = lp->hw.at(nm).second;
+    TRY(up(v.data(), v.size() * 4, (void**)&lp->d_lin[l]));
+  }
+  if (lp->precision == SNTC_PRECISION_TC_F16X3) {
+    cudaError_t e = cudaFuncSetAttribute(band_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(band_gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail(SNTC_E_CUDA, std::string("sntc_lpips_finalize: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+  }
+  lp->hw.clear();
+  lp->finalized = true;
+  return SNTC_OK;
+}
+
+extern "C" int sntc_image_lpips(sntc_lpips* lp, const sntc_tensor* a, const sntc_tensor* b, double* lpips, double* per_layer, void* stream) {
+  if (!lp || !lpips) return fail(SNTC_E_INVALID, "sntc_image_lpips: bad argument");
+  if (!lp->finalized) return fail(SNTC_E_STATE, "sntc_image_lpips: not finalized (weights missing?)");
+  if (!a || !b) return fail(SNTC_E_INVALID, "sntc_image_lpips: tensor is NULL");
+  const bool u8 = a->dtype_code == SNTC_DL_UINT && a->dtype_bits == 8;
+  if (!u8 && !(a->dtype_code == SNTC_DL_FLOAT && a->dtype_bits == 32)) return fail(SNTC_E_INVALID, "sntc_image_lpips: images must be uint8 or float32 in [0, 255]");
+  TRY(check_tensor(a, "a", a->dtype_code, a->dtype_bits, 4));
+  TRY(check_tensor(b, "b", a->dtype_code, a->dtype_bits, 4));
+  for (int i = 0; i < 4; ++i) if (a->shape[i] != b->shape[i]) return fail(SNTC_E_INVALID, "sntc_image_lpips: the two image batches differ in shape");
+  const int B = (int)a->shape[0], H = (int)a->shape[1], W = (int)a->shape[2];
+  if (a->shape[3] != 3) return fail(SNTC_E_INVALID, "sntc_image_lpips: images must have 3 channels");
+  if (B == 0) return SNTC_OK;
+  if (H < 16 || W < 16) return fail(SNTC_E_INVALID, "sntc_image_lpips: images must be at least 16 x 16 (five VGG16 blocks)");
+  sntc_ctx* ctx = lp->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick_stream(ctx, stream);
+  const size_t px = (size_t)H * W, esz = u8 ? 1 : 4;
+  // pairs per pass: the widest activation (block 1: 64 channels at full resolution) of both images stays below ~1 GiB
+  const int nb_max = (int)std::max<size_t>(1, ((size_t)1 << 30) / (2 * px * 64 * 4));
+  const int nbm = std::min(B, nb_max);
+  const size_t n_max = 2 * (size_t)nbm;
+  TRY(lp->f_a.ensure(n_max * px * 64 * 4));
+  TRY(lp->f_b.ensure(n_max * px * 64 * 4));
+  const bool tc = lp->precision == SNTC_PRECISION_TC_F16X3;
+  if (tc) for (auto& pb : lp->plane) if (!pb.ensure(n_max * px * 64 * 2)) return fail(SNTC_E_CUDA, "sntc_image_lpips: cudaMalloc failed for the activation planes");
+  const int spi = 256;
+  TRY(lp->slots.ensure((size_t)nbm * spi * 8));
+  TRY(lp->d_out.ensure((size_t)B * 6 * 8));
+  CU_TRY(cudaMemsetAsync(lp->d_out.p, 0, (size_t)B * 6 * 8, s));
+  const char* ha = (const char*)tdata(a); const char* hb = (const char*)tdata(b);
+  LpipsPre pre{{0.458f, 0.448f, 0.450f}, {-0.030f, -0.088f, -0.188f}};   // lpips_tensorflow.py:18-19
+  for (int b0 = 0; b0 < B; b0 += nbm) {
+    const int nb = std::min(nbm, B - b0), n = 2 * nb;
+    // stage / locate the two image chunks, preprocess them into one [n, H, W, 4] tensor (a first, then b)
+    const void* da = ha + (size_t)b0 * px * 3 * esz; const void* db = hb + (size_t)b0 * px * 3 * esz;
+    if (!on_device(a)) { TRY(lp->st_a.ensure((size_t)nbm * px * 3 * esz)); CU_TRY(cudaMemcpyAsync(lp->st_a.p, da, (size_t)nb * px * 3 * esz, cudaMemcpyHostToDevice, s)); da = lp->st_a.p; }
+    if (!on_device(b)) { TRY(lp->st_b.ensure((size_t)nbm * px * 3 * esz)); CU_TRY(cudaMemcpyAsync(lp->st_b.p, db, (size_t)nb * px * 3 * esz, cudaMemcpyHostToDevice, s)); db = lp->st_b.p; }
+    float* x0 = (float*)lp->f_a.p;
+    const size_t np1 = (size_t)nb * px;
+    lpips_preprocess_kernel<<<(unsigned)((np1 + 255) / 256), 256, 0, s>>>(da, u8 ? 1 : 0, np1, pre, (float4*)x0);
+    lpips_preprocess_kernel<<<(unsigned)((np1 + 255) / 256), 256, 0, s>>>(db, u8 ? 1 : 0, np1, pre, (float4*)x0 + np1);
+    ctx->launches += 2;
+    CU_TRY(cudaGetLastError());
+    int h = H, w = W, pflip = 0;
+    float* cur_f32 = x0;                   // current activation as fp32 (nullptr when only planes exist)
+    __half* cur_hi = nullptr; __half* cur_lo = nullptr;
+    auto other_f32 = [&](float* p) { return p == (float*)lp->f_a.p ? (float*)lp->f_b.p : (float*)lp->f_a.p; };
+    auto next_planes = [&](__half** hi, __half** lo) { *hi = (__half*)lp->plane[pflip * 2].p; *lo = (__half*)lp->plane[pflip * 2 + 1].p; pflip ^= 1; };
+    size_t ci = 0;
+    for (int blk = 0; blk < 5; ++blk) {
+      for (; (int)ci <= lp->block_last[blk]; ++ci) {
+        ConvLayer& c = lp->convs[ci];
+        const bool tap = (int)ci == lp->block_last[blk];
+        const bool this_tc = tc && lp->tc[ci].ok;
+        const bool next_tc = tc && !tap && ci + 1 < lp->convs.size() && lp->tc[ci + 1].ok;
+        if (this_tc) {
+          if (!cur_hi) {   // fp32 -> fp16 hi/lo planes
+            __half *hi, *lo;
+            next_planes(&hi, &lo);
+            const size_t n8 = (size_t)n * h * w * c.cin / 8;
+            split_planes_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>(cur_f32, hi, lo, n8, nullptr);
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+            cur_hi = hi; cur_lo = lo;
+          }
+          TcConvOut o;
+          float* dst = nullptr;
+          __half *nhi = nullptr, *nlo = nullptr;
+          if (tap || !next_tc) { dst = cur_f32 ? other_f32(cur_f32) : (float*)lp->f_a.p; o.f32 = dst; }
+          if (next_tc) { next_planes(&nhi, &nlo); o.hi = nhi; o.lo = nlo; }
+          std::string err;
+          if (tc_run_conv(ctx->tc, c, lp->tc[ci], cur_hi, cur_lo, n, h, w, o, s, &ctx->launches, &err) != TC_OK) return fail(SNTC_E_CUDA, "sntc_image_lpips: " + err);
+          ctx->kinds[SNTC_LAUNCH_BAND_TC]++;
+          cur_f32 = dst; cur_hi = nhi; cur_lo = nlo;
+        } else {
+          if (!cur_f32) return fail(SNTC_E_STATE, "sntc_image_lpips: fp32 layer without an fp32 input");
+          float* dst = other_f32(cur_f32);
+          TRY(run_conv_f32(ctx, c, cur_f32, n, h, w, dst, nullptr, s));
+          cur_f32 = dst; cur_hi = nullptr; cur_lo = nullptr;
+        }
+      }
+      // head of this block: cur_f32 = features [n, h, w, C]
+      const ConvLayer& lc = lp->convs[lp->block_last[blk]];
+      const int npix = h * w;
+      lpips_head_kernel<<<dim3(spi, nb), 256, 0, s>>>(cur_f32, nb, npix, lc.cout, lp->d_lin[blk], (double*)lp->slots.p, spi);
+      lpips_layer_finalize_kernel<<<nb, 32, 0, s>>>((const double*)lp->slots.p, spi, 1.0 / (double)npix, (double*)lp->d_out.p + (size_t)B * (1 + blk) + b0);
+      ctx->launches += 2;
+      CU_TRY(cudaGetLastError());
+      if (blk < 4) {   // MaxPooling2D(2, 2) into the next block's input
+        const int ho = h / 2, wo = w / 2;
+        const size_t tot = (size_t)n * ho * wo * (lc.cout / 8);
+        const bool nxt_tc = tc && lp->tc[ci].ok;
+        __half *hi = nullptr, *lo = nullptr;
+        float* dst = nullptr;
+        if (nxt_tc) next_planes(&hi, &lo); else dst = other_f32(cur_f32);
+        lpips_maxpool_planes_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(cur_f32, n, h, w, lc.cout, hi, lo, dst);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        cur_f32 = dst; cur_hi = hi; cur_lo = lo;
+        h = ho; w = wo;
+      }
+    }
+  }
+  if (lp->h_out_cap < B) {
+    if (lp->h_out) cudaFreeHost(lp->h_out);
+    CU_TRY(cudaHostAlloc((void**)&lp->h_out, (size_t)B * 6 * 8, cudaHostAllocDefault));
+    lp->h_out_cap = B;
+  }
+  CU_TRY(cudaMemcpyAsync(lp->h_out, lp->d_out.p, (size_t)B * 6 * 8, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  for (int i = 0; i < B; ++i) {
+    double t = 0.0;
+    for (int l = 0; l < 5; ++l) { const double v = lp->h_out[(size_t)B * (1 + l) + i]; t += v; if (per_layer) per_layer[(size_t)i * 5 + l] = v; }
+    lpips[i] = t;
+  }
+  return SNTC_OK;
+}
 
 extern "C" int sntc_last_stage_times_ms(sntc_model* m, float out[4]) {
   if (!m || !out) return fail(SNTC_E_INVALID, "sntc_last_stage_times_ms: bad argument");

@@ -4,8 +4,8 @@ metrics record per image and ``eval_lib.eval_workdir`` (common/eval_lib.py:91-10
 Here the loop starts from decoded symbols instead of images (the encoder is out of scope): every image is decoded by
 libsntc -- batched, which the reference does not do (it evaluates image by image) -- and the per-image record carries
 the scalars the reference's results files hold and this path can produce on the device: ``bpp``, ``psnr``, ``mse``,
-``rd_loss`` (= bpp + rd_lambda * mse, :343), ``msssim`` / ``msssim_db`` (:321-332, ``Context.msssim``), ``instance_id``.
-``lpips`` needs the pretrained LPIPS network (lpips_tf2 submodule weights, not available offline): not computed."""
+``rd_loss`` (= bpp + rd_lambda * mse, :343), ``msssim`` / ``msssim_db`` (:321-332, ``Context.msssim``), ``lpips`` (:334-340, when an
+``lpips.Lpips`` object holding the network's weights is passed), ``instance_id``."""
 from __future__ import annotations
 
 import json
@@ -21,7 +21,7 @@ def msssim_defined(H, W):
   return H >= 11 and W >= 11
 
 
-def evaluate_symbols(model, z_hat, q_y, originals, image_hw=None, batch_size=24, rd_lambda=None, extra=None, msssim=True):
+def evaluate_symbols(model, z_hat, q_y, originals, image_hw=None, batch_size=24, rd_lambda=None, extra=None, msssim=True, lpips=None):
   """Yields one dict per image, in order.  z_hat / q_y: arrays (or lists of per-image arrays of one shape) of decoded
   symbols; originals: uint8 [N,H,W,3].  ``extra``: hyper-parameters added to every record (parse_runname's role)."""
   originals = np.asarray(originals)
@@ -35,10 +35,13 @@ def evaluate_symbols(model, z_hat, q_y, originals, image_hw=None, batch_size=24,
     ms = None
     if msssim and msssim_defined(H, W):
       ms = model.ctx.msssim(np.ascontiguousarray(originals[lo:hi]), out["image"])
+    lp = lpips(np.ascontiguousarray(originals[lo:hi]), out["image"]) if lpips is not None else None   # lpips_model([image_batch, reconstruction])
     for i in range(hi - lo):
       rec = dict(instance_id=lo + i, psnr=float(out["psnr"][i]), mse=float(out["mse"][i]))
       if ms is not None:
         rec.update(msssim=float(ms[0][i]), msssim_db=float(ms[1][i]))
+      if lp is not None:
+        rec["lpips"] = float(lp[i])
       if "bpp" in out:
         rec.update(bpp=float(out["bpp"][i]), latent_bpp=float(out["bits_y"][i] / (H * W)), hyper_latent_bpp=float(out["bits_z"][i] / (H * W)))
         if rd_lambda is not None:
