@@ -104,11 +104,13 @@ __global__ void __launch_bounds__(256) lpips_head_kernel(const float* __restrict
     for (int c = lane * 4; c < C; c += 128) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(fa + c)), q = __ldg(reinterpret_cast<const float4*>(fb + c));
       const float4 wv = __ldg(reinterpret_cast<const float4*>(lin + c));
+      // normalise each side (rounded), THEN subtract, as the reference does: a fused a*ra - q*rb would leave the rounding error of
+      // one product behind and make lpips(x, x) non-zero
       float t;
-      t = a.x * ra - q.x * rb; d = fmaf(t * t, wv.x, d);
-      t = a.y * ra - q.y * rb; d = fmaf(t * t, wv.y, d);
-      t = a.z * ra - q.z * rb; d = fmaf(t * t, wv.z, d);
-      t = a.w * ra - q.w * rb; d = fmaf(t * t, wv.w, d);
+      t = __fsub_rn(__fmul_rn(a.x, ra), __fmul_rn(q.x, rb)); d = fmaf(t * t, wv.x, d);
+      t = __fsub_rn(__fmul_rn(a.y, ra), __fmul_rn(q.y, rb)); d = fmaf(t * t, wv.y, d);
+      t = __fsub_rn(__fmul_rn(a.z, ra), __fmul_rn(q.z, rb)); d = fmaf(t * t, wv.z, d);
+      t = __fsub_rn(__fmul_rn(a.w, ra), __fmul_rn(q.w, rb)); d = fmaf(t * t, wv.w, d);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
