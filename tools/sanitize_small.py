@@ -17,3 +17,27 @@ for name, B, H, W in (("two_layer_syn", 2, 97, 149), ("jpegl", 1, 100, 150), ("t
   print(name, "ok", out["image"].shape, flush=True)
 a = np.random.default_rng(0).integers(0, 256, (1, 192, 181, 3), dtype=np.uint8)
 print("msssim", ctx.msssim(a, a)[0])
+# round 2: device-resident small-batch decodes (CUDA-graph capture + replay, programmatic dependent launch), the band split,
+# the other hyper-synthesis classes, LPIPS
+from shallow_ntc_b200 import Model, lpips as L
+m = build_config("two_layer_syn", precision="tc", ctx=ctx)
+m.load_weights(synthetic.make_weights(m.variable_shapes(), "stress", synthesis_cls="TwoLayerResSynthesis"))
+zs, ys = m.latent_shapes(2, 97, 149)
+z, q = synthetic.make_latents(zs, ys)
+dz, dq = ctx.to_device(z), ctx.to_device(q.astype(np.int16))
+out = dict(image=ctx.empty((2, 97, 149, 3), np.uint8), idx=ctx.empty(ys, np.uint8))
+for _ in range(4):
+  m.decompress(dz, dq, (97, 149), out=out)
+print("graph replay ok", flush=True)
+t = m.decompress_tiled(z, q, (97, 149), 2)
+print("tiled ok", t["image"].shape, flush=True)
+for hcfg in (dict(cls="JPEGLikeHyperSynthesis", bottleneck_size=320, kernel_size=6), dict(cls="HyperSynthesisSmall", bottleneck_size=320)):
+  cfg = dict(analysis=dict(cls="ElicAnalysis", channels=(192, 192, 192, 320)), synthesis=dict(cls="JPEGLikeSynthesis", kernel_size=18, strides=16), hyper_synthesis=hcfg)
+  mm = Model(cfg, precision="tc", ctx=ctx)
+  mm.load_weights(synthetic.make_weights(mm.variable_shapes(), "stress", synthesis_cls="JPEGLikeSynthesis"))
+  zs, ys = mm.latent_shapes(1, 70, 90)
+  z, q = synthetic.make_latents(zs, ys)
+  mm.decompress(z, q, (70, 90))
+  print(hcfg["cls"], "ok", flush=True)
+b = np.clip(a.astype(int) + 9, 0, 255).astype(np.uint8)
+print("lpips", L.Lpips(ctx, L.random_weights())(a[:, :64, :80], b[:, :64, :80]))
