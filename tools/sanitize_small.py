@@ -40,4 +40,4 @@ for hcfg in (dict(cls="JPEGLikeHyperSynthesis", bottleneck_size=320, kernel_size
   mm.decompress(z, q, (70, 90))
   print(hcfg["cls"], "ok", flush=True)
 b = np.clip(a.astype(int) + 9, 0, 255).astype(np.uint8)
-print("lpips", L.Lpips(ctx, L.random_weights())(a[:, :64, :80], b[:, :64, :80]))
+print("lpips", L.Lpips(ctx, L.random_weights())(np.ascontiguousarray(a[:, :64, :80]), np.ascontiguousarray(b[:, :64, :80])))
