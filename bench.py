@@ -340,7 +340,10 @@ def main():
     sets.append((z, q))
   if args.tile_frames and world > 1:
     # every rank holds band `rank` (rows + halo) of the SAME frames: what the range decoder of a tiled stream would hand it
-    band = model.band_plan((H, W), world)[rank]
+    plan = model.band_plan((H, W), world)
+    if len(plan) != world:
+      raise SystemExit(f"--tile-frames: a {W}x{H} frame has only {len(plan)} latent-row bands to give to {world} ranks")
+    band = plan[rank]
     sets = [model.band_inputs(z, q, band) for z, q in sets]
     H = band.sub_h                            # from here on this rank decodes a (sub_h x W) "image"; its own rows are band.rows
     zs, ys = model.latent_shapes(B, H, W)

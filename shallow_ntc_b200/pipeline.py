@@ -131,6 +131,8 @@ class DecodePipeline:
   def submit(self, z_host, q_host, image_host, idx_host=None) -> int:
     """Enqueue one batch; returns a ticket for wait().  Nothing blocks the host.  ``idx_host`` is filled only when the
     pipeline was built with ``return_idx=True``."""
+    if self.has_z and z_host is None:
+      raise ValueError("this model has a hyperprior: submit() needs z_host")
     s = self.slots[self.n % self.depth]
     if s["used"]:
       self.s_in.wait(s["ev_done"])                       # the decode that last read this input set
