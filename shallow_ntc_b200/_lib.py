@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsntc.so")
+LIB_PATH = os.environ.get("SNTC_LIB_PATH") or os.path.join(_HERE, "libsntc.so")   # SNTC_LIB_PATH: experimental builds (tools/)
 
 SNTC_OK = 0
 DL_CPU, DL_CUDA, DL_CUDA_HOST = 1, 2, 3

@@ -26,7 +26,10 @@
 
 namespace sntc {
 
-constexpr int TM_TX = 64, TM_RW = 8;              // t-pixels per CTA: 8 rows x 64 columns; one warp = one 16-column strip
+#ifndef SNTC_TAIL_TX
+#define SNTC_TAIL_TX 64
+#endif
+constexpr int TM_TX = SNTC_TAIL_TX, TM_RW = 8;    // t-pixels per CTA: 8 rows x TM_TX columns; one warp = one 16-column strip
 constexpr int TM_TXH = TM_TX + 2, TM_TYH = TM_RW + 2;
 constexpr int TM_NFRAG = 15;                      // (parity, tap): phy=0 -> dy in {-1,0}; phy=1 -> dy in {-1,0,+1}; jx in {-1,0,+1}
 constexpr int TM_THREADS = 32 * (TM_TX / 16);
@@ -78,7 +81,7 @@ __device__ __forceinline__ uint32_t tm_pixel(float x) {
 // staging buffer; the load of tile n+1 is issued as soon as tile n has been converted, so it overlaps the MMA phase.
 // WLO = false drops the t_hi * w_lo cross term (SNTC_PRECISION_TC_F16X3_SYN2: 30 instead of 45 MMAs per row step).
 template <int C1, bool FAST, bool WLO = true>
-__global__ void __launch_bounds__(TM_THREADS, 3) tail_s2_mma_kernel(const __grid_constant__ CUtensorMap mapT, const TailMmaParams Q) {
+__global__ void __launch_bounds__(TM_THREADS, (TM_TX >= 64 ? 3 : (TM_TX >= 32 ? 5 : 10))) tail_s2_mma_kernel(const __grid_constant__ CUtensorMap mapT, const TailMmaParams Q) {
   static_assert(C1 % 4 == 0 && C1 <= 16, "one K=16 step per tap");
   constexpr int NPX = TM_TYH * TM_TXH;
   constexpr int PLANE = 2 * NPX;                                  // uint4 units per plane: [octet][row][x]
