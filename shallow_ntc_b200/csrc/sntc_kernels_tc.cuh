@@ -1169,7 +1169,9 @@ inline bool tc_use_narrow(const TcConv& t, int mtiles, int num_sms) {
   const int groups = (mtiles + t.cg - 1) / t.cg;
   long items = 0;
   for (auto& bd : t.bands) items += (long)groups * bd.ntiles;
-  return 2 * items <= num_sms / t.cg;
+  // SNTC_TC_NARROW_WAVES (x 0.01): narrow when the wide tiling has fewer items than this many waves of the persistent units
+  static const int waves_pct = tc_env_int("SNTC_TC_NARROW_WAVES", 50);
+  return items * 100 <= (long)waves_pct * (num_sms / t.cg);
 }
 
 struct TcDevBuf {
