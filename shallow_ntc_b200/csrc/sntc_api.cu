@@ -18,6 +18,7 @@
 #include "sntc_kernels_tc.cuh"
 #include "sntc_kernels_tail_tc.cuh"
 #include "sntc_kernels_tail_mma.cuh"
+#include "sntc_kernels_tail_tz.cuh"
 #include "sntc_kernels_msssim.cuh"
 #include "sntc_kernels_lpips.cuh"
 #include "sntc_coder.hpp"
@@ -98,6 +99,7 @@ struct sntc_model {
   int ph_B = 0, ph_hy = 0, ph_wy = 0;   // geometry of that call (0 = none pending)
   TcModelState tc;                      // tensor-core plan state (tensor maps, fp16 planes)
   std::vector<TailMma> tail_mma;       // parallel to syn.convs: warp-MMA tail of a two-layer synthesis (tc precision only)
+  std::vector<TailTz> tail_tz;         // parallel to syn.convs: window-GEMM tcgen05 tail (hidden width 12; takes precedence over tail_mma)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
   bool graphs_on = true;                // sntc_model_enable_graphs
@@ -465,6 +467,15 @@ extern "C" int sntc_model_finalize(sntc_model* m) {
         if (op.type != OP_CONVT_RGB || !tail_mma_supported(m->syn.convs[op.conv])) continue;
         if (!tail_mma_pack(m->syn.convs[op.conv], m->hw, m->tail_mma[op.conv], m->owned, &err))
           return fail(SNTC_E_CUDA, "sntc_model_finalize (warp-MMA tail): " + err);
+      }
+    }
+    // window-GEMM tcgen05 tail (sntc_kernels_tail_tz.cuh) for hidden width 12; SNTC_TAIL_TZ=0 keeps the warp-MMA tail
+    if (m->has_syn && tc_env_int("SNTC_TAIL_TZ", 1)) {
+      m->tail_tz.assign(m->syn.convs.size(), TailTz{});
+      for (auto& op : m->syn.ops) {
+        if (op.type != OP_CONVT_RGB || !tail_tz_supported(m->syn.convs[op.conv])) continue;
+        if (!tail_tz_pack(m->syn.convs[op.conv], m->hw, m->tail_tz[op.conv], m->owned, &err))
+          return fail(SNTC_E_CUDA, "sntc_model_finalize (window-GEMM tail): " + err);
       }
     }
   }
@@ -954,6 +965,20 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
         if (tail_tc_run(ctx->tc, c, tt, tt.bias, cur.hi, cur.lo, B, ch, cw, to, s, &ctx->launches, &err) != TC_OK)
           return fail(SNTC_E_CUDA, "tensor-core tail: " + err);
+        ctx->kinds[SNTC_LAUNCH_TAIL_TC]++;
+        ch *= c.s; cw *= c.s; cc = c.cout;
+        cur = Cur{};
+        continue;
+      }
+      if (op.type == OP_CONVT_RGB && cur.f32 && !is_hyper && op.conv < (int)m->tail_tz.size() && m->tail_tz[op.conv].ok) {
+        // ---- window-GEMM tcgen05 tail: stride-2 conv 12 -> 3 channels + crop + uint8 ----
+        TailTzOut to;
+        if (fin) { to.f32 = fin->full; to.u8 = fin->u8; to.crop = fin->crop; to.H = fin->H; to.W = fin->W; }
+        std::string err;
+        ProfScope ps(m, s, lbl, conv_macs(c, B, ch, cw));
+        if (tail_tz_run(ctx->tc, c, m->tail_tz[op.conv], cur.f32, B, ch, cw, to, tc_pdl(B), s, &ctx->launches, &err,
+                        m->desc.precision != SNTC_PRECISION_TC_F16X3_SYN2) != 0)
+          return fail(SNTC_E_CUDA, "window-GEMM tail: " + err);
         ctx->kinds[SNTC_LAUNCH_TAIL_TC]++;
         ch *= c.s; cw *= c.s; cc = c.cout;
         cur = Cur{};

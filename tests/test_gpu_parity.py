@@ -296,8 +296,11 @@ def test_warp_mma_tail_kernel(gpu_ctx, monkeypatch, name, B, H, W):
   """The warp-MMA tail (sntc_kernels_tail_mma.cuh, default for C1 = 12 on the tensor-core path): same gates against the
   oracle as every other kernel; its uint8-only fast path writes exactly the bytes of its generic path (odd widths,
   crops and ragged tiles included); and it agrees with the FFMA tail (SNTC_TAIL_MMA=0) far inside the tolerance."""
+  monkeypatch.setenv("SNTC_TAIL_TZ", "0")     # the window-GEMM tcgen05 tail is the default for C1 = 12 since round 2
   model, wts, z, q = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
+  n0 = gpu_ctx.launch_counts
   got = model.decompress(z, q, (H, W), return_float=True, return_yhat=True)
+  assert gpu_ctx.launch_counts["tail_mma"] == n0["tail_mma"] + 1
   if H * W <= 128 * 192:
     ref = oracle_decode(model, wts, z, q, H, W)
     print(name, check_against_oracle(got, ref, precision="tc"))
@@ -308,6 +311,32 @@ def test_warp_mma_tail_kernel(gpu_ctx, monkeypatch, name, B, H, W):
   ffma = base.decompress(z, q, (H, W), return_float=True)
   assert np.abs(ffma["float"] - got["float"]).max() < 2e-6
   d = np.abs(ffma["image"].astype(int) - got["image"].astype(int))
+  assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize("name,B,H,W", [("two_layer_syn", 2, 128, 192), ("two_layer_syn2", 1, 100, 150), ("two_layer_syn2", 2, 97, 149),
+                                        ("two_layer_syn", 3, 72, 520), ("two_layer_syn", 1, 512, 768), ("two_layer_syn2", 1, 1200, 1200)])
+def test_window_gemm_tail_kernel(gpu_ctx, monkeypatch, name, B, H, W):
+  """The window-GEMM tcgen05 tail (sntc_kernels_tail_tz.cuh, default for C1 = 12 on the tensor-core path): one GEMM row =
+  4 t-pixels, banded weights, [w_hi | w_lo] in N.  Same gates against the oracle as every other kernel; its 8-byte-store
+  fast path writes exactly the bytes of its generic path (odd widths, crops, ragged tiles, several tiles per row); it
+  agrees with the warp-MMA tail (SNTC_TAIL_TZ=0) to fp32 rounding; and the launch counters prove which kernel ran."""
+  model, wts, z, q = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
+  n0 = gpu_ctx.launch_counts
+  got = model.decompress(z, q, (H, W), return_float=True, return_yhat=True)
+  n = {k: v - n0[k] for k, v in gpu_ctx.launch_counts.items()}
+  assert n["tail_tc"] == 1 and n["tail_mma"] == 0 and n["final_f32"] == 0 and n["band_f32"] == 0, n
+  if H * W <= 128 * 192:
+    ref = oracle_decode(model, wts, z, q, H, W)
+    print(name, check_against_oracle(got, ref, precision="tc"))
+  fast = model.decompress(z, q, (H, W))
+  assert np.array_equal(fast["image"], got["image"])
+  monkeypatch.setenv("SNTC_TAIL_TZ", "0")
+  base, _, _, _ = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
+  mma = base.decompress(z, q, (H, W), return_float=True)
+  assert np.array_equal(mma["idx"], got["idx"])
+  assert np.abs(mma["float"] - got["float"]).max() < 2e-6
+  d = np.abs(mma["image"].astype(int) - got["image"].astype(int))
   assert d.max() <= 1 and (d > 0).mean() < 1e-3
 
 
