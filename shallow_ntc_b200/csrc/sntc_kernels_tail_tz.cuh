@@ -19,7 +19,7 @@
 // through a descriptor whose start is shifted by one tile row.  Windows overlap (stride 4 pixels = 6 chunks, length 10
 // chunks), so the conversion warps write chunks 0-3 of a window a second time as chunks 6-9 of its left neighbour.
 //
-// Pipeline per persistent CTA (one per SM):  warp 0: TMA of the raw fp32 halo tile (2 stages)  ->  warps 8-11: fp32 ->
+// Pipeline per persistent CTA (one per SM):  warp 0: TMA of the raw fp32 halo tile (2 stages)  ->  warps 8-15: fp32 ->
 // fp16 hi / lo split into the window layout (2 stages)  ->  warp 1: 30 UMMAs per tile  ->  TMEM (2 buffers)  ->
 // warps 4-7: scale, bias, sat_u8(rint((x + .5) * 255)), 24 contiguous bytes per thread and image row.
 #pragma once
@@ -42,8 +42,8 @@ constexpr uint32_t TZ_PLANE = (TZ_NCH * TZ_CS + 127u) & ~127u;      // one fp16 
 constexpr uint32_t TZ_RAW = ((uint32_t)TZ_RH * TZ_TXH * TZ_C1 * 4 + 127u) & ~127u;
 constexpr uint32_t TZ_WSTEP = 2 * 96 * 16;                          // weights of one K step: [2 chunks][96 columns][8 fp16]
 constexpr uint32_t TZ_WBYTES = 3 * TZ_KSTEPS * TZ_WSTEP;
-constexpr int TZ_THREADS = 384;
-constexpr int TZ_CONV_WARPS = 4;
+constexpr int TZ_CONV_WARPS = 8;                  // warps 8..15
+constexpr int TZ_THREADS = 32 * (8 + TZ_CONV_WARPS);
 constexpr uint32_t TZ_ACC_STRIDE = 128;            // TMEM columns per accumulator buffer (96 used)
 constexpr size_t TZ_SMEM = 1024 + TZ_WBYTES + 4 * TZ_PLANE + 2 * TZ_RAW + 256;
 
@@ -56,6 +56,7 @@ struct TailTzParams {
   uint8_t* out_u8; float* out_crop; int H, W;
   const uint4* w;                // [15 K steps][2 chunks][96 columns][8 fp16]: columns < 48 = hi, >= 48 = lo
   int fast;                      // uint8 is the only destination, W % 8 == 0, 8-byte aligned base: 8-byte stores
+  long long* trace;              // debug timeline (SNTC_TC_TRACE=1): block 0, [64 tiles][8] clock64 stamps
 };
 
 __device__ __forceinline__ uint32_t tz_pixel(float x) {   // data_lib.floats_to_pixels(training=False), as float_to_pixel()
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1) tail_tz_kernel(const __grid_con
       int b, ty0, tx0;
       tile_origin(tile_of(k), b, ty0, tx0);
       tcx::mbar_wait(&raw_empty[st], ph ^ 1u);
+      if (P.trace && blockIdx.x == 0 && lane == 0 && it < 64) P.trace[it * 8 + 0] = clock64();
       if (tcx::elect_one()) {
         tcx::mbar_expect_tx(&raw_full[st], (uint32_t)TZ_RH * TZ_TXH * TZ_C1 * 4);
         tcx::tma_load_4d(raw + st * TZ_RAW, &mapT, &raw_full[st], 0, tx0 - 1, ty0 - 1, b);
@@ -148,6 +150,8 @@ __global__ void __launch_bounds__(TZ_THREADS, 1) tail_tz_kernel(const __grid_con
       tcx::mbar_wait(&acc_empty[st], ph ^ 1u);
       tcx::mbar_wait(&pl_full[st], ph);
       tcx::tc_fence_after();
+      long long* tr = (P.trace && blockIdx.x == 0 && lane == 0 && it < 64) ? P.trace + it * 8 : nullptr;
+      if (tr) tr[3] = clock64();
       const uint32_t tacc = tmem_base + st * TZ_ACC_STRIDE;
       const uint32_t a_hi = planes_base + st * 2 * TZ_PLANE, a_lo = a_hi + TZ_PLANE;
       if (tcx::elect_one()) {
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1) tail_tz_kernel(const __grid_con
         tcx::umma_commit(&acc_full[st]);
       }
       __syncwarp();
+      if (tr) tr[4] = clock64();
     }
   } else if (warp >= 8) {
     // ===== conversion: raw fp32 -> fp16 hi / lo in the window layout =====
@@ -174,31 +179,60 @@ __global__ void __launch_bounds__(TZ_THREADS, 1) tail_tz_kernel(const __grid_con
     for (int k = blockIdx.x; k < P.ntiles; k += gridDim.x, ++it) {
       const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
       tcx::mbar_wait(&raw_full[st], ph);
-      tcx::mbar_wait(&pl_empty[st], ph ^ 1u);
+      long long* tr = (P.trace && blockIdx.x == 0 && ct == 0 && it < 64) ? P.trace + it * 8 : nullptr;
+      if (tr) tr[1] = clock64();
       const uint8_t* src = raw + st * TZ_RAW;
       uint8_t* dhi = planes + st * 2 * TZ_PLANE;
       uint8_t* dlo = dhi + TZ_PLANE;
-#pragma unroll 2
-      for (int i = ct; i < TZ_RH * TZ_ROWCH; i += 32 * TZ_CONV_WARPS) {
-        const int rr = i / TZ_ROWCH, f = i - rr * TZ_ROWCH;
-        const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)rr * (TZ_TXH * TZ_C1 * 4) + (size_t)f * 32);
-        uint4 hi, lo;
-        tz_split8(s4[0], s4[1], hi, lo);
-        const int xb = f / TZ_CHS, c = f - xb * TZ_CHS;
-        const uint32_t o = (uint32_t)c * TZ_CS + (uint32_t)rr * (TZ_XB * 16) + (uint32_t)xb * 16;
-        if (xb < TZ_XB) {
-          *reinterpret_cast<uint4*>(dhi + o) = hi;
-          *reinterpret_cast<uint4*>(dlo + o) = lo;
+      constexpr int NTASK = TZ_RH * TZ_ROWCH, NIT = (NTASK + 32 * TZ_CONV_WARPS - 1) / (32 * TZ_CONV_WARPS);
+      // Phase 1: raw tile -> registers -> hi / lo.  A thread owns 32-byte chunk i; within a quarter warp the two 16-byte halves are
+      // fetched in swapped order by lanes 4-7 (conflict-free LDS.128).  The raw stage is released as soon as it has been read, so
+      // that the TMA of tile + 2 (latency ~2700 clk) is in flight while this tile is still being stored.
+      const int hsw = (lane >> 2) & 1;
+      uint4 hi[NIT], lo[NIT];
+      {
+        float4 in[NIT][2];
+#pragma unroll
+        for (int u = 0; u < NIT; ++u) {
+          const int i = ct + u * 32 * TZ_CONV_WARPS;
+          if (i < NTASK) {
+            const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)i * 32);   // rows are dense: chunk i of the tile = 32 bytes at 32 i
+            in[u][0] = s4[hsw]; in[u][1] = s4[1 - hsw];
+          }
         }
-        if (c < TZ_NCH - TZ_CHS && xb >= 1) {            // the same chunk seen from the window to the left
-          const uint32_t o2 = o + TZ_CHS * TZ_CS - 16;
-          *reinterpret_cast<uint4*>(dhi + o2) = hi;
-          *reinterpret_cast<uint4*>(dlo + o2) = lo;
+#pragma unroll
+        for (int u = 0; u < NIT; ++u) {
+          const int i = ct + u * 32 * TZ_CONV_WARPS;
+          if (i < NTASK) tz_split8(hsw ? in[u][1] : in[u][0], hsw ? in[u][0] : in[u][1], hi[u], lo[u]);
         }
       }
-      tcx::fence_proxy_async();                          // generic writes -> visible to the tensor-core (async) proxy; reads of `raw` done
+      tcx::fence_proxy_async();                            // order the reads before the async-proxy overwrite (next TMA)
       __syncwarp();
-      if (lane == 0) { tcx::mbar_arrive(&pl_full[st]); tcx::mbar_arrive(&raw_empty[st]); }
+      if (lane == 0) tcx::mbar_arrive(&raw_empty[st]);     // generic-proxy reads of `raw` are complete (values consumed above)
+      // Phase 2: hi / lo -> window layout of this stage's planes (once the MMAs of tile - 2 have finished reading them)
+      tcx::mbar_wait(&pl_empty[st], ph ^ 1u);
+#pragma unroll
+      for (int u = 0; u < NIT; ++u) {
+        const int i = ct + u * 32 * TZ_CONV_WARPS;
+        if (i < NTASK) {
+          const int rr = i / TZ_ROWCH, f = i - rr * TZ_ROWCH;
+          const int xb = f / TZ_CHS, c = f - xb * TZ_CHS;
+          const uint32_t o = (uint32_t)c * TZ_CS + (uint32_t)rr * (TZ_XB * 16) + (uint32_t)xb * 16;
+          if (xb < TZ_XB) {
+            *reinterpret_cast<uint4*>(dhi + o) = hi[u];
+            *reinterpret_cast<uint4*>(dlo + o) = lo[u];
+          }
+          if (c < TZ_NCH - TZ_CHS && xb >= 1) {          // the same chunk seen from the window to the left
+            const uint32_t o2 = o + TZ_CHS * TZ_CS - 16;
+            *reinterpret_cast<uint4*>(dhi + o2) = hi[u];
+            *reinterpret_cast<uint4*>(dlo + o2) = lo[u];
+          }
+        }
+      }
+      tcx::fence_proxy_async();                          // generic writes -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) tcx::mbar_arrive(&pl_full[st]);
+      if (tr) tr[2] = clock64();
     }
   } else if (warp >= 4) {
     // ===== epilogue: one thread = one window = 8 x 2 output pixels (24 contiguous bytes on each of two image rows) =====
@@ -211,6 +245,8 @@ __global__ void __launch_bounds__(TZ_THREADS, 1) tail_tz_kernel(const __grid_con
       tile_origin(tile_of(k), b, ty0, tx0);
       tcx::mbar_wait(&acc_full[st], ph);
       tcx::tc_fence_after();
+      long long* tr = (P.trace && blockIdx.x == 0 && qd == 0 && lane == 0 && it < 64) ? P.trace + it * 8 : nullptr;
+      if (tr) tr[5] = clock64();
       uint32_t a0[32], a1[32], a2[32];
       const uint32_t taddr = tmem_base + st * TZ_ACC_STRIDE + ((uint32_t)(qd * 32) << 16);
       tcx::tmem_ld32_nowait(taddr, a0);
@@ -229,7 +265,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1) tail_tz_kernel(const __grid_con
         v[i] = fmaf(s, P.inv_scale, P.bias[co]);
       }
       const int ty = ty0 + r, x0 = tx0 + TZ_J * xb;
-      if (ty >= P.hin || x0 >= P.win) continue;
+      if (ty >= P.hin || x0 >= P.win) { if (tr) tr[6] = clock64(); continue; }
       if (P.fast && x0 + TZ_J <= P.win && 2 * (x0 + TZ_J) <= P.W) {
 #pragma unroll
         for (int phy = 0; phy < 2; ++phy) {
@@ -258,6 +294,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1) tail_tz_kernel(const __grid_con
           }
         }
       }
+      if (tr) tr[6] = clock64();
     }
   }
   tcx::tc_fence_before();
@@ -353,10 +390,25 @@ inline int tail_tz_run(TcDriver& drv, const ConvLayer& c, TailTz& t, const float
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  static const bool trace_on = tc_env_int("SNTC_TC_TRACE", 0) != 0;
+  long long* d_trace = nullptr;
+  if (trace_on) { cudaMalloc((void**)&d_trace, 64 * 8 * 8); cudaMemsetAsync(d_trace, 0, 64 * 8 * 8, s); P.trace = d_trace; }
   cudaError_t e = w_lo ? cudaLaunchKernelEx(&cfg, tail_tz_kernel<true>, mapT, P) : cudaLaunchKernelEx(&cfg, tail_tz_kernel<false>, mapT, P);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("tail_tz_kernel launch: ") + cudaGetErrorString(e); return 2; }
   if (launches) (*launches)++;
+  if (trace_on) {
+    long long hbuf[64 * 8];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(hbuf, d_trace, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    cudaFree(d_trace);
+    fprintf(stderr, "[tc-trace] window-GEMM tail: tiles=%d grid=%d\n", P.ntiles, (int)cfg.gridDim.x);
+    for (int j = 0; j < 32; ++j) {
+      const long long* r = hbuf + j * 8; const long long t0 = hbuf[0];
+      fprintf(stderr, "[tc-trace]  tile %2d: tma-issue %7lld  conv: start %7lld done %7lld  mma: data %7lld issued %7lld  epi: full %7lld done %7lld\n", j,
+              r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0);
+    }
+  }
   return 0;
 }
 
