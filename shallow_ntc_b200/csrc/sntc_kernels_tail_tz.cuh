@@ -37,7 +37,7 @@ constexpr int TZ_NCH = 2 * TZ_KSTEPS;              // 16-byte chunks per window
 constexpr int TZ_CHS = TZ_J * TZ_C1 / 8;           // chunk stride between neighbouring windows (6)
 constexpr int TZ_ROWCH = TZ_TXH * TZ_C1 / 8;       // chunks of one raw tile row (99)
 constexpr int TZ_NOUT = 48;                        // (phy, j, phx, co)
-constexpr uint32_t TZ_CS = TZ_RH * TZ_XB * 16 + 16;                 // bytes between chunk planes (+16: conversion stores spread over the banks)
+constexpr uint32_t TZ_CS = TZ_RH * TZ_XB * 16;                      // bytes between chunk planes
 constexpr uint32_t TZ_PLANE = (TZ_NCH * TZ_CS + 127u) & ~127u;      // one fp16 plane (hi or lo) of a tile
 constexpr uint32_t TZ_RAW = ((uint32_t)TZ_RH * TZ_TXH * TZ_C1 * 4 + 127u) & ~127u;
 constexpr uint32_t TZ_WSTEP = 2 * 96 * 16;                          // weights of one K step: [2 chunks][96 columns][8 fp16]
@@ -175,6 +175,33 @@ __global__ void __launch_bounds__(TZ_THREADS, 1) tail_tz_kernel(const __grid_con
   } else if (warp >= 8) {
     // ===== conversion: raw fp32 -> fp16 hi / lo in the window layout =====
     const int ct = threadIdx.x - 8 * 32;
+    // Tasks: one 32-byte chunk (8 values) each.  Slot s = ct + 256 u; a row's first 96 chunks are dealt to 96 consecutive slots
+    // in an order that makes BOTH the LDS.128 of the raw tile and the STS.128 into the window layout conflict-free within every
+    // quarter warp: slot 8 k + p of a 48-chunk block takes window w = p with bits 1 and 2 swapped and chunk c = k (w < 4) or
+    // k ^ 1 (w >= 4) -- 8 distinct windows (16-byte bank groups of the planes) and chunk indices 6 w + c that cover every
+    // residue mod 4 twice (32-byte slots of the raw tile; lanes 4-7 of a quarter fetch their two halves in swapped order).
+    // The last 3 chunks of each row (pixel 64, 65: only seen by the last window) are 30 left-over slots.
+    constexpr int NMAIN = TZ_RH * 96, NTASK = NMAIN + TZ_RH * (TZ_ROWCH - 96), NIT = (NTASK + 32 * TZ_CONV_WARPS - 1) / (32 * TZ_CONV_WARPS);
+    static_assert(TZ_ROWCH - 96 == 3 && TZ_CHS == 6 && TZ_XB == 16, "slot map is written for 16 windows of 6-chunk stride");
+    const int hsw = (lane >> 2) & 1;
+    uint32_t t_src[NIT], t_dst[NIT];   // byte offsets in the raw tile / in a plane; t_dst bit 0: first store, bit 1: second store
+#pragma unroll
+    for (int u = 0; u < NIT; ++u) {
+      const int sl = ct + u * 32 * TZ_CONV_WARPS;
+      int rr, xb, c;
+      if (sl < NMAIN) {
+        rr = sl / 96;
+        const int pos = sl - rr * 96, blk = pos >= 48, l48 = pos - 48 * blk, k = l48 >> 3, pp = l48 & 7;
+        const int w = (pp & 1) | ((pp & 2) << 1) | ((pp & 4) >> 1);
+        xb = 8 * blk + w; c = w < 4 ? k : (k ^ 1);
+      } else {
+        const int r = sl - NMAIN;
+        rr = r / 3; xb = TZ_XB; c = r - 3 * rr;
+      }
+      t_src[u] = (uint32_t)rr * (TZ_TXH * TZ_C1 * 4) + (uint32_t)(xb * TZ_CHS + c) * 32;
+      t_dst[u] = ((uint32_t)c * TZ_CS + (uint32_t)rr * (TZ_XB * 16) + (uint32_t)xb * 16) | (xb < TZ_XB ? 1u : 0u) | ((c < TZ_NCH - TZ_CHS && xb >= 1) ? 2u : 0u);
+      if (sl >= NTASK) { t_src[u] = 0; t_dst[u] = 0; }
+    }
     uint32_t it = 0;
     for (int k = blockIdx.x; k < P.ntiles; k += gridDim.x, ++it) {
       const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
@@ -184,27 +211,18 @@ __global__ void __launch_bounds__(TZ_THREADS, 1) tail_tz_kernel(const __grid_con
       const uint8_t* src = raw + st * TZ_RAW;
       uint8_t* dhi = planes + st * 2 * TZ_PLANE;
       uint8_t* dlo = dhi + TZ_PLANE;
-      constexpr int NTASK = TZ_RH * TZ_ROWCH, NIT = (NTASK + 32 * TZ_CONV_WARPS - 1) / (32 * TZ_CONV_WARPS);
-      // Phase 1: raw tile -> registers -> hi / lo.  A thread owns 32-byte chunk i; within a quarter warp the two 16-byte halves are
-      // fetched in swapped order by lanes 4-7 (conflict-free LDS.128).  The raw stage is released as soon as it has been read, so
-      // that the TMA of tile + 2 (latency ~2700 clk) is in flight while this tile is still being stored.
-      const int hsw = (lane >> 2) & 1;
+      // Phase 1: raw tile -> registers -> hi / lo.  The raw stage is released as soon as it has been read, so that the TMA of
+      // tile + 2 (latency ~2700 clk) is in flight while this tile is still being stored.
       uint4 hi[NIT], lo[NIT];
       {
         float4 in[NIT][2];
 #pragma unroll
         for (int u = 0; u < NIT; ++u) {
-          const int i = ct + u * 32 * TZ_CONV_WARPS;
-          if (i < NTASK) {
-            const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)i * 32);   // rows are dense: chunk i of the tile = 32 bytes at 32 i
-            in[u][0] = s4[hsw]; in[u][1] = s4[1 - hsw];
-          }
+          const float4* s4 = reinterpret_cast<const float4*>(src + t_src[u]);
+          in[u][0] = s4[hsw]; in[u][1] = s4[1 - hsw];
         }
 #pragma unroll
-        for (int u = 0; u < NIT; ++u) {
-          const int i = ct + u * 32 * TZ_CONV_WARPS;
-          if (i < NTASK) tz_split8(hsw ? in[u][1] : in[u][0], hsw ? in[u][0] : in[u][1], hi[u], lo[u]);
-        }
+        for (int u = 0; u < NIT; ++u) tz_split8(hsw ? in[u][1] : in[u][0], hsw ? in[u][0] : in[u][1], hi[u], lo[u]);
       }
       tcx::fence_proxy_async();                            // order the reads before the async-proxy overwrite (next TMA)
       __syncwarp();
@@ -213,20 +231,15 @@ __global__ void __launch_bounds__(TZ_THREADS, 1) tail_tz_kernel(const __grid_con
       tcx::mbar_wait(&pl_empty[st], ph ^ 1u);
 #pragma unroll
       for (int u = 0; u < NIT; ++u) {
-        const int i = ct + u * 32 * TZ_CONV_WARPS;
-        if (i < NTASK) {
-          const int rr = i / TZ_ROWCH, f = i - rr * TZ_ROWCH;
-          const int xb = f / TZ_CHS, c = f - xb * TZ_CHS;
-          const uint32_t o = (uint32_t)c * TZ_CS + (uint32_t)rr * (TZ_XB * 16) + (uint32_t)xb * 16;
-          if (xb < TZ_XB) {
-            *reinterpret_cast<uint4*>(dhi + o) = hi[u];
-            *reinterpret_cast<uint4*>(dlo + o) = lo[u];
-          }
-          if (c < TZ_NCH - TZ_CHS && xb >= 1) {          // the same chunk seen from the window to the left
-            const uint32_t o2 = o + TZ_CHS * TZ_CS - 16;
-            *reinterpret_cast<uint4*>(dhi + o2) = hi[u];
-            *reinterpret_cast<uint4*>(dlo + o2) = lo[u];
-          }
+        const uint32_t o = t_dst[u] & ~15u;
+        if (t_dst[u] & 1u) {
+          *reinterpret_cast<uint4*>(dhi + o) = hi[u];
+          *reinterpret_cast<uint4*>(dlo + o) = lo[u];
+        }
+        if (t_dst[u] & 2u) {                               // the same chunk seen from the window to the left
+          const uint32_t o2 = o + TZ_CHS * TZ_CS - 16;
+          *reinterpret_cast<uint4*>(dhi + o2) = hi[u];
+          *reinterpret_cast<uint4*>(dlo + o2) = lo[u];
         }
       }
       tcx::fence_proxy_async();                          // generic writes -> visible to the tensor-core (async) proxy
