@@ -68,7 +68,11 @@ enum sntc_transform_kind {
   SNTC_T_TWO_LAYER_RES = 12,       /* TwoLayerResSynthesis      common/transforms.py:320-361 (res_type="conv") */
   SNTC_T_MBT2018 = 13,             /* MBT2018Synthesis          common/transforms.py:158-175 */
   SNTC_T_BLS2017 = 14,             /* BLS2017Synthesis          common/transforms.py:115-134 */
-  SNTC_T_CNN = 15                  /* CNNSynthesis              common/transforms.py:195-206 */
+  SNTC_T_CNN = 15,                 /* CNNSynthesis              common/transforms.py:195-206 */
+  SNTC_T_TWO_LAYER_RES_D2S = 16    /* TwoLayerResSynthesis(res_type="d2s")  common/transforms.py:339-348: the residual branch is
+                                      depth_to_space(2), Conv2D 1x1 (-> 192) + leaky_relu, depth_to_space(2), Conv2D 1x1
+                                      (-> 4 * C1) + leaky_relu, depth_to_space(2); variables res.conv_0 / res.conv_1
+                                      (kernel [1,1,Cin,Cout], bias).  strides[0] must be 8 and in_channels % 16 == 0. */
 };
 
 /* get_activation_op, common/transforms.py:66-78 */

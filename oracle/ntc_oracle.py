@@ -230,13 +230,37 @@ def two_layer_synthesis(wts, y_hat, strides=(8, 2), activation_type="igdn", dtyp
   return keras_conv2d_transpose(x, wts[f"{prefix}.conv2.kernel"], wts[f"{prefix}.conv2.bias"], strides[1], dtype, gemm_form)
 
 
+def depth_to_space2(x):
+  """tf.nn.depth_to_space(x, 2) on NHWC (DCR order): out[b, 2y+dy, 2x+dx, c] = in[b, y, x, (2 dy + dx) * C + c]."""
+  B, h, w, c4 = x.shape
+  c = c4 // 4
+  return x.reshape(B, h, w, 2, 2, c).transpose(0, 1, 3, 2, 4, 5).reshape(B, 2 * h, 2 * w, c)
+
+
+def d2s_residual(wts, y_hat, dtype=np.float64, prefix="synthesis"):
+  """common/transforms.py:339-348, the res_type="d2s" Sequential: depth_to_space(2), Conv2D 1x1 + leaky_relu (twice), then
+  depth_to_space(2).  A11: the Keras activation string 'leaky_relu' = tf.nn.leaky_relu, alpha 0.2 (Keras 2.10 itself does not
+  know the string; later versions define it with negative_slope 0.2)."""
+  x = np.asarray(y_hat, dtype)
+  for i in range(2):
+    x = depth_to_space2(x)
+    x = x @ np.asarray(wts[f"{prefix}.res.conv_{i}.kernel"], dtype)[0, 0] + np.asarray(wts[f"{prefix}.res.conv_{i}.bias"], dtype)
+    x = np.where(x > 0, x, dtype(0.2) * x)
+  return depth_to_space2(x)
+
+
 def two_layer_res_synthesis(wts, y_hat, strides=(8, 2), activation_type="igdn", dtype=np.float64, gemm_form=False,
-                            prefix="synthesis"):
-  """common/transforms.py:320-361 TwoLayerResSynthesis(res_type="conv"):
+                            prefix="synthesis", res_type="conv"):
+  """common/transforms.py:320-361 TwoLayerResSynthesis:
   out_conv(act(base_conv(z)) + res(z)); the activation sits inside base_conv (:331-334)."""
   base = keras_conv2d_transpose(y_hat, wts[f"{prefix}.base_conv.kernel"], wts[f"{prefix}.base_conv.bias"], strides[0], dtype, gemm_form)
   base = apply_activation(base, activation_type, wts, f"{prefix}.activation")
-  res = keras_conv2d_transpose(y_hat, wts[f"{prefix}.res.kernel"], wts[f"{prefix}.res.bias"], strides[0], dtype, gemm_form)
+  if res_type == "conv":
+    res = keras_conv2d_transpose(y_hat, wts[f"{prefix}.res.kernel"], wts[f"{prefix}.res.bias"], strides[0], dtype, gemm_form)
+  elif res_type == "d2s":
+    res = d2s_residual(wts, y_hat, dtype, prefix)
+  else:
+    raise NotImplementedError(res_type)
   return keras_conv2d_transpose(base + res, wts[f"{prefix}.out_conv.kernel"], wts[f"{prefix}.out_conv.bias"], strides[1], dtype, gemm_form)
 
 
@@ -278,7 +302,7 @@ _SYNTHESIS = {
   "TwoLayerSynthesis": lambda w, y, kw, dt, g: two_layer_synthesis(
     w, y, kw.get("strides", (8, 2)), kw.get("activation_type", "igdn"), dt, g),
   "TwoLayerResSynthesis": lambda w, y, kw, dt, g: two_layer_res_synthesis(
-    w, y, kw.get("strides", (8, 2)), kw.get("activation_type", "igdn"), dt, g),
+    w, y, kw.get("strides", (8, 2)), kw.get("activation_type", "igdn"), dt, g, res_type=kw.get("res_type", "conv")),
   "MBT2018Synthesis": lambda w, y, kw, dt, g: mbt2018_synthesis(w, y, kw.get("n_layers", 4), dt, g, gdn_form=kw.get("gdn_form", "gdn1")),
   "BLS2017Synthesis": lambda w, y, kw, dt, g: bls2017_synthesis(w, y, dt, g),
   "CNNSynthesis": lambda w, y, kw, dt, g: cnn_synthesis(w, y, kw.get("activation_type", "leaky_relu"), dt, g),

@@ -17,6 +17,7 @@ DL_INT, DL_UINT, DL_FLOAT = 0, 1, 2
 T_NONE = 0
 T_HYPER_SYNTHESIS, T_JPEG_LIKE_HYPER, T_HYPER_SMALL = 1, 2, 3
 T_JPEG_LIKE_SYNTHESIS, T_TWO_LAYER, T_TWO_LAYER_RES, T_MBT2018, T_BLS2017, T_CNN = 10, 11, 12, 13, 14, 15
+T_TWO_LAYER_RES_D2S = 16
 # enum sntc_activation
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_IGDN1, ACT_GDN1, ACT_IGDN_CLASSIC = 0, 1, 2, 3, 4, 5
 PRECISION_FP32, PRECISION_TC_F16X3, PRECISION_TC_F16X3_SYN2 = 0, 1, 2

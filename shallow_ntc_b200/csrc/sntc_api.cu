@@ -837,6 +837,8 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
         ch *= c.s; cw *= c.s;
         max_f32 = std::max(max_f32, (size_t)B * ch * cw * c.cout * 4);
         max_pl = std::max(max_pl, (size_t)B * ch * cw * std::max(c.cout, 32) * 2);   // >= the 16-padded planes of the tail input
+      } else if (op.type == OP_STASH) {
+        ch = h; cw = w;
       }
     }
   }
@@ -847,6 +849,8 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
     for (auto& pb : m->tc.plane)
       if (!pb.ensure(max_pl)) return fail(SNTC_E_CUDA, "cudaMalloc failed for the fp16 activation planes");
   int ch = h, cw = w, cc = t.in_channels;
+  const Cur cur0 = cur;                      // the transform's input (OP_STASH goes back to it)
+  const float* stash = nullptr; int stash_c = 0;
   int flip = 0, pflip = 0;
   auto next_buf = [&]() { float* p = (float*)(flip ? m->ws_b.p : m->ws_a.p); flip ^= 1; return p; };
   auto next_planes = [&](__half** hi, __half** lo) { *hi = (__half*)m->tc.plane[pflip * 2].p; *lo = (__half*)m->tc.plane[pflip * 2 + 1].p; pflip ^= 1; };
@@ -1044,6 +1048,28 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
       float* dst = next_buf();
       ProfScope ps(m, s, gl.beta.substr(0, gl.beta.size() - 5), (double)B * ch * cw * gl.C * gl.C);
       TRY(run_gdn_f32(ctx, gl, cur.f32, (size_t)B * ch * cw, dst, s));
+      cur = Cur{}; cur.f32 = dst;
+    } else if (op.type == OP_STASH) {
+      // residual branch of TwoLayerResSynthesis(res_type="d2s") is complete up to its last depth_to_space: keep it, restart from the input
+      if (!cur.f32) return fail(SNTC_E_STATE, "executor: the d2s residual branch must end in an fp32 tensor");
+      const size_t bytes = (size_t)B * ch * cw * cc * 4;
+      TRY(m->ws_c.ensure(bytes));
+      CU_TRY(cudaMemcpyAsync(m->ws_c.p, cur.f32, bytes, cudaMemcpyDeviceToDevice, s));
+      stash = (const float*)m->ws_c.p; stash_c = cc;
+      cur = cur0;   // the caller's fp32 tensor and / or its planes (the y_hat planes of a decode live in their own buffers, not in the ping-pong pair)
+      ch = h; cw = w; cc = t.in_channels;
+    } else if (op.type == OP_ACT_RES_D2S) {
+      if (!cur.f32 || !stash) return fail(SNTC_E_STATE, "executor: d2s residual stage without its inputs");
+      const int C = cc;
+      if (stash_c != 4 * C || (ch & 1) || (cw & 1)) return fail(SNTC_E_STATE, "executor: d2s residual geometry");
+      if (C > 64) return fail(SNTC_E_UNSUPPORTED, "two-layer hidden width > 64");
+      float* dst = next_buf();
+      ActResParams P{};
+      P.in = cur.f32; P.in_stride = cc; P.out = dst; P.npix = (size_t)B * ch * cw; P.C = C; P.act = op.act; P.has_res = 2;
+      P.res_ext = stash; P.H1 = ch; P.W1 = cw;
+      if (op.gdn >= 0) { const GdnLayer& g = t.gdns[op.gdn]; P.beta = g.d_beta; P.gamma = g.d_gamma; P.gamma_stride = g.Npad; P.inverse = g.inverse; }
+      ProfScope ps(m, s, "synthesis.activation+res_d2s", (double)P.npix * C * C);
+      TRY(launch_act_res(ctx, P, s));
       cur = Cur{}; cur.f32 = dst;
     } else if (op.type == OP_ACT_RES) {
       if (!cur.f32) return fail(SNTC_E_STATE, "executor: activation stage needs an fp32 input");

@@ -608,6 +608,9 @@ struct ActResParams {
   const float* in; int in_stride; float* out; size_t npix; int C;
   int act; int has_res;
   const float* beta; const float* gamma; int gamma_stride; int inverse;  // gamma [in][out]
+  // has_res == 2 (TwoLayerResSynthesis res_type="d2s", transforms.py:339-348): the residual is the last depth_to_space(2) of
+  // res_ext [B, H1/2, W1/2, 4C]; the pixels of `in` are [B, H1, W1]
+  const float* res_ext; int H1, W1;
 };
 
 __global__ void __launch_bounds__(128) act_res_kernel(const ActResParams P) {
@@ -638,7 +641,11 @@ __global__ void __launch_bounds__(128) act_res_kernel(const ActResParams P) {
     } else {
       v = apply_act(x, P.act);
     }
-    if (P.has_res) v += P.in[pix * P.in_stride + P.C + j];
+    if (P.has_res == 1) v += P.in[pix * P.in_stride + P.C + j];
+    else if (P.has_res == 2) {
+      const int x = (int)(pix % P.W1), y = (int)((pix / P.W1) % P.H1); const size_t b = pix / ((size_t)P.W1 * P.H1);
+      v += P.res_ext[((b * (P.H1 / 2) + y / 2) * (P.W1 / 2) + x / 2) * (4 * P.C) + (2 * (y & 1) + (x & 1)) * P.C + j];
+    }
     P.out[pix * P.C + j] = v;
   }
 }

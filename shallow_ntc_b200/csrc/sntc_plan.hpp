@@ -21,7 +21,11 @@
 
 namespace sntc {
 
-enum KernelLayout { LAYOUT_KERAS_OI = 0 /* [kh,kw,Cout,Cin] */, LAYOUT_TFC_IO = 1 /* [kh,kw,Cin,Cout] */ };
+enum KernelLayout { LAYOUT_KERAS_OI = 0 /* [kh,kw,Cout,Cin] */, LAYOUT_TFC_IO = 1 /* [kh,kw,Cin,Cout] */,
+                    // tf.nn.depth_to_space(x, 2) followed by a Keras Conv2D 1x1 (variable [1,1,Cin/4,Cout]) IS a transposed conv with
+                    // k = s = 2, p = 0 whose tap (dy, dx) only sees input channels [(2 dy + dx) Cin/4, (2 dy + dx + 1) Cin/4):
+                    //   out[2y+dy, 2x+dx, co] = sum_c in[y, x, (2 dy + dx) Cin/4 + c] * K[0, 0, c, co]      (NHWC / DCR order)
+                    LAYOUT_D2S_1X1 = 2 };
 enum GdnKind { GDN_NONE = 0, GDN_1 = 1 /* beta + |x| gamma */, GDN_CLASSIC = 2 /* sqrt(beta + x^2 gamma) */ };
 
 struct Band1D {
@@ -101,7 +105,10 @@ enum OpType {
   OP_CONVT = 0,     // band-GEMM transposed conv (+bias, +relu/leaky)
   OP_GDN = 1,       // GDN over all channels of the current tensor
   OP_ACT_RES = 2,   // current tensor is [.., 2*C] = base || res: out[.., C] = act(base) + res
-  OP_CONVT_RGB = 3  // final conv to <=4 channels, fused crop + uint8 epilogue
+  OP_CONVT_RGB = 3, // final conv to <=4 channels, fused crop + uint8 epilogue
+  OP_STASH = 4,     // TwoLayerResSynthesis(res_type="d2s"): the current tensor is the residual branch before its last depth_to_space;
+                    // keep it aside and go back to the transform's input
+  OP_ACT_RES_D2S = 5  // out[b,y,x,c] = act(cur[b,y,x,:])[c] + stash[b, y/2, x/2, (2 (y%2) + x%2) C + c]
 };
 
 struct Op { int type; int conv = -1; int gdn = -1; int act = SNTC_ACT_NONE; };
@@ -260,6 +267,34 @@ inline Transform build_transform(const sntc_transform_desc& d, const std::string
       t.out_channels = Co; t.upsample = s1 * s2;
       break;
     }
+    case SNTC_T_TWO_LAYER_RES_D2S: {  // transforms.py:320-361, res_type="d2s" (:339-348)
+      int C1 = d.channels[0], Co = d.channels[1];
+      int k1 = d.kernel_sizes[0], k2 = d.kernel_sizes[1], s1 = d.strides[0], s2 = d.strides[1];
+      if (s1 != 8) throw std::invalid_argument("TwoLayerResSynthesis(res_type='d2s'): three depth_to_space(2) steps need strides[0] == 8");
+      if (d.in_channels % 16 != 0) throw std::invalid_argument("TwoLayerResSynthesis(res_type='d2s'): input channels must be a multiple of 16");
+      auto d2s_conv = [&](const std::string& name, int cin, int cout) {
+        ConvLayer c = make_conv(prefix, name, 2, 2, cin, cout, LAYOUT_D2S_1X1, true, SNTC_ACT_LEAKY_RELU);
+        c.p = 0;
+        finish_conv(c);
+        return c;
+      };
+      add_conv(d2s_conv("res.conv_0", d.in_channels, 192));
+      add_conv(d2s_conv("res.conv_1", 192, 4 * C1));
+      { Op o; o.type = OP_STASH; t.ops.push_back(o); }
+      add_conv(make_conv(prefix, "base_conv", k1, s1, d.in_channels, C1, LAYOUT_KERAS_OI, true, SNTC_ACT_NONE));
+      {
+        Op o; o.type = OP_ACT_RES_D2S; o.act = d.activation;
+        if (d.activation == SNTC_ACT_IGDN1 || d.activation == SNTC_ACT_GDN1) {
+          GdnLayer g; g.C = C1; g.kind = GDN_1; g.inverse = d.activation == SNTC_ACT_IGDN1;
+          g.beta = prefix + ".activation.beta"; g.gamma = prefix + ".activation.gamma";
+          t.gdns.push_back(g); o.gdn = (int)t.gdns.size() - 1;
+        }
+        t.ops.push_back(o);
+      }
+      add_conv(make_conv(prefix, "out_conv", k2, s2, C1, Co, LAYOUT_KERAS_OI, true, SNTC_ACT_NONE));
+      t.out_channels = Co; t.upsample = s1 * s2;
+      break;
+    }
     case SNTC_T_MBT2018: {  // transforms.py:158-175
       int C = d.channels[0]; int Co = d.channels[1] > 0 ? d.channels[1] : C; int nl = d.n_layers > 0 ? d.n_layers : 4;
       int cin = d.in_channels; int up = 1;
@@ -314,6 +349,7 @@ inline std::vector<VarSpec> transform_variables(const Transform& t) {
       int cin = c.cin + (c.append_ones ? 1 : 0);
       for (auto& s : c.sources) {
         if (c.layout == LAYOUT_KERAS_OI) v.push_back({s.kernel, {c.k, c.k, s.cout, cin}});
+        else if (c.layout == LAYOUT_D2S_1X1) v.push_back({s.kernel, {1, 1, cin / 4, s.cout}});
         else v.push_back({s.kernel, {c.k, c.k, cin, s.cout}});
         if (!s.bias.empty()) v.push_back({s.bias, {s.cout}});
       }
@@ -336,6 +372,10 @@ inline float conv_w(const ConvLayer& c, const HostWeights& hw, int ay, int ax, i
       const auto& arr = hw.at(s.kernel).second;
       int cl = co - base;
       int cin = c.cin + (c.append_ones ? 1 : 0);
+      if (c.layout == LAYOUT_D2S_1X1) {   // Conv2D kernel [1,1,Cin/4,Cout] seen through the preceding depth_to_space(2)
+        const int cq = cin / 4;
+        return ci / cq == 2 * ay + ax ? arr[(size_t)(ci % cq) * s.cout + cl] : 0.f;
+      }
       size_t idx = c.layout == LAYOUT_KERAS_OI
                      ? (((size_t)ay * c.k + ax) * s.cout + cl) * cin + ci
                      : (((size_t)ay * c.k + ax) * cin + ci) * s.cout + cl;

@@ -75,9 +75,14 @@ def export_transform_weights(layer, role: str) -> dict:
     _conv(w, f"{role}.conv2", layer.conv2)
   elif cls == "TwoLayerResSynthesis":                                            # :320-361
     _conv(w, f"{role}.base_conv", layer.base_conv)
-    if type(layer.res).__name__ != "Conv2DTranspose" and not hasattr(layer.res, "kernel"):
-      raise NotImplementedError("TwoLayerResSynthesis(res_type='d2s') is not on the B200 path")
-    _conv(w, f"{role}.res", layer.res)
+    if type(layer.res).__name__ == "Conv2DTranspose" or hasattr(layer.res, "kernel"):   # res_type="conv"
+      _conv(w, f"{role}.res", layer.res)
+    else:                                                                          # res_type="d2s" (:339-348): Sequential of
+      convs = [l for l in layer.res.layers if hasattr(l, "kernel")]               # Lambda(d2s), Conv2D, Lambda, Conv2D, Lambda
+      if len(convs) != 2:
+        raise NotImplementedError("TwoLayerResSynthesis: unknown residual branch (expected res_type 'conv' or 'd2s')")
+      for i, sub in enumerate(convs):
+        _conv(w, f"{role}.res.conv_{i}", sub)
     if _is_gdn(layer.activation):
       _gdn(w, f"{role}.activation", layer.activation)
     _conv(w, f"{role}.out_conv", layer.out_conv)

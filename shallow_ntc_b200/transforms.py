@@ -276,20 +276,35 @@ class TwoLayerSynthesis(Transform):
 
 
 class TwoLayerResSynthesis(TwoLayerSynthesis):
-  """common/transforms.py:320-361 (res_type='conv'; 'd2s' is not used by any shipped config)."""
+  """common/transforms.py:320-361.  ``res_type="conv"`` (every shipped config): the residual is a second transposed conv.
+  ``res_type="d2s"`` (:339-348): the residual is depth_to_space(2) -> Conv2D 1x1 (192) + leaky_relu -> depth_to_space(2) ->
+  Conv2D 1x1 (4 * channels[0]) + leaky_relu -> depth_to_space(2); its variables are ``res.conv_0`` / ``res.conv_1`` (kernel
+  ``[1, 1, Cin, Cout]``, bias).  ``'leaky_relu'`` is taken as ``tf.nn.leaky_relu`` (alpha 0.2, what the string means in the Keras
+  versions that know it; Keras 2.10 does not -- assumption A11 in DESIGN.md section 5)."""
+
+  D2S_WIDTH = 192
 
   def __init__(self, channels=(12, 3), strides=(8, 2), kernel_sizes=(13, 5), activation_type="igdn", res_type="conv"):
     super().__init__(channels, strides, kernel_sizes, activation_type)
-    if res_type != "conv":
-      raise NotImplementedError(f"res_type={res_type!r}")
+    if res_type not in ("conv", "d2s"):
+      raise NotImplementedError(f"res_type={res_type!r}")     # the reference raises NotImplementedError too (:349-350)
+    if res_type == "d2s" and self.strides[0] != 8:
+      raise ValueError("res_type='d2s' upsamples by three depth_to_space(2) steps: strides[0] must be 8")
     self.res_type = res_type
 
   def _kind(self):
-    return _lib.T_TWO_LAYER_RES
+    return _lib.T_TWO_LAYER_RES if self.res_type == "conv" else _lib.T_TWO_LAYER_RES_D2S
 
   def variable_shapes(self, in_channels):
     v = _keras_convt(self.role, "base_conv", self.kernel_sizes[0], in_channels, self.channels[0])
-    v.update(_keras_convt(self.role, "res", self.kernel_sizes[0], in_channels, self.channels[0]))
+    if self.res_type == "conv":
+      v.update(_keras_convt(self.role, "res", self.kernel_sizes[0], in_channels, self.channels[0]))
+    else:
+      if in_channels % 16:
+        raise ValueError("res_type='d2s' needs a latent channel count that is a multiple of 16")
+      w = self.D2S_WIDTH
+      v.update({f"{self.role}.res.conv_0.kernel": (1, 1, in_channels // 4, w), f"{self.role}.res.conv_0.bias": (w,),
+                f"{self.role}.res.conv_1.kernel": (1, 1, w // 4, 4 * self.channels[0]), f"{self.role}.res.conv_1.bias": (4 * self.channels[0],)})
     if activation_code(self.activation_type) in (_lib.ACT_IGDN1, _lib.ACT_GDN1):
       v.update(_gdn(self.role, "activation", self.channels[0]))
     v.update(_keras_convt(self.role, "out_conv", self.kernel_sizes[1], self.channels[0], self.channels[1]))

@@ -123,6 +123,29 @@ def test_two_layer_activation_variants(gpu_ctx, cls, act, precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
+@pytest.mark.parametrize("act,B,H,W", [("igdn", 2, 100, 150), ("relu", 1, 128, 192), ("igdn", 1, 512, 768)])
+def test_two_layer_res_synthesis_d2s(gpu_ctx, act, B, H, W, precision):
+  """TwoLayerResSynthesis(res_type="d2s") (common/transforms.py:339-348): the residual is depth_to_space(2) -> Conv2D 1x1 (192)
+  + leaky_relu -> depth_to_space(2) -> Conv2D 1x1 (48) + leaky_relu -> depth_to_space(2).  On the device each
+  depth_to_space + 1x1 conv pair is ONE k = s = 2 transposed conv (band GEMM, tcgen05 under 'tc'), the last depth_to_space is
+  the addressing of the residual in the activation stage."""
+  syn = dict(cls="TwoLayerResSynthesis", channels=(12, 3), strides=(8, 2), kernel_sizes=(13, 5), activation_type=act, res_type="d2s")
+  model, wts, z, q = case_from_config(dict(analysis=ELIC, synthesis=syn), B, H, W, "stress", precision, gpu_ctx)
+  assert wts["synthesis.res.conv_0.kernel"].shape == (1, 1, 80, 192) and wts["synthesis.res.conv_1.kernel"].shape == (1, 1, 48, 48)
+  if H * W <= 128 * 192:
+    got, ref, rep, n = run_and_check(model, wts, z, q, H, W, precision, gpu_ctx)
+    print(rep, n)
+  else:   # full size: tensor path against the fp32 CUDA-core path of the same library (the float64 oracle takes minutes here)
+    got = model.decompress(z, q, (H, W), return_float=True)
+    if precision == "tc":
+      base, _, _, _ = case_from_config(dict(analysis=ELIC, synthesis=syn), B, H, W, "stress", "fp32", gpu_ctx)
+      f32 = base.decompress(z, q, (H, W), return_float=True)
+      assert np.abs(f32["float"] - got["float"]).max() < 1e-4
+  fast = model.decompress(z, q, (H, W))
+  assert np.array_equal(fast["image"], got["image"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
 @pytest.mark.parametrize("gdn_form", ["gdn1", "classic"])
 def test_mbt2018_gdn_forms(gpu_ctx, gdn_form, precision):
   """MBT2018Synthesis builds tfc.GDN(inverse=True) with the tfc 2.x defaults (alpha = epsilon = 1: IGDN1, oracle A5);

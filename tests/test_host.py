@@ -19,8 +19,14 @@ def test_registry_has_the_decoder_classes_of_the_reference():
   assert t.upsample == 16 and t.out_channels == 3
   with pytest.raises(KeyError):
     class_builder.build("ElicAnalysis")
+  d2s = class_builder.build("TwoLayerResSynthesis", res_type="d2s")       # common/transforms.py:339-348
+  v = d2s.variable_shapes(320)
+  assert v["synthesis.res.conv_0.kernel"] == (1, 1, 80, 192) and v["synthesis.res.conv_1.kernel"] == (1, 1, 48, 48)
+  assert "synthesis.res.kernel" not in v and d2s.desc(320).kind == 16
   with pytest.raises(NotImplementedError):
-    class_builder.build("TwoLayerResSynthesis", res_type="d2s")
+    class_builder.build("TwoLayerResSynthesis", res_type="bilinear")     # the reference raises NotImplementedError too (:349-350)
+  with pytest.raises(ValueError):
+    class_builder.build("TwoLayerResSynthesis", strides=(4, 4), res_type="d2s")
   with pytest.raises(NotImplementedError):
     T.activation_code("prelu")
 

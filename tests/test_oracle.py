@@ -36,6 +36,35 @@ def test_two_layer_res_synthesis_golden():
   assert np.abs(got - GOLD["tlr_out"]).max() < 1e-11
 
 
+def test_d2s_residual_matches_an_independent_torch_statement():
+  """TwoLayerResSynthesis(res_type="d2s") (common/transforms.py:339-348) against torch: F.pixel_shuffle orders the channels
+  (c, dy, dx) where tf.nn.depth_to_space orders them (dy, dx, c), hence the channel permutation; 1x1 convs as F.conv2d."""
+  import torch
+  import torch.nn.functional as F
+  from shallow_ntc_b200 import transforms as T
+  rng = np.random.default_rng(11)
+  shapes = T.TwoLayerResSynthesis(res_type="d2s").variable_shapes(320)
+  wts = synthetic.make_weights(shapes, "stress", synthesis_cls="TwoLayerResSynthesis")
+  y = rng.standard_normal((2, 3, 5, 320)).astype(np.float32)
+  got = O.d2s_residual(wts, y)
+  assert got.shape == (2, 24, 40, 12)
+
+  def tf_d2s(x):     # NCHW tensor holding TF's channel order (dy, dx, c) -> pixel_shuffle's (c, dy, dx)
+    B, C4, h, w = x.shape
+    c = C4 // 4
+    return F.pixel_shuffle(x.reshape(B, 2, 2, c, h, w).permute(0, 3, 1, 2, 4, 5).reshape(B, C4, h, w), 2)
+  x = torch.from_numpy(y.astype(np.float64)).permute(0, 3, 1, 2)
+  for i in range(2):
+    k = torch.from_numpy(wts[f"synthesis.res.conv_{i}.kernel"].astype(np.float64))[0, 0].T[:, :, None, None]   # [Cout, Cin, 1, 1]
+    x = F.leaky_relu(F.conv2d(tf_d2s(x), k, torch.from_numpy(wts[f"synthesis.res.conv_{i}.bias"].astype(np.float64))), 0.2)
+  want = tf_d2s(x).permute(0, 2, 3, 1).numpy()
+  assert np.abs(got - want).max() < 1e-12
+  # and the whole transform: out_conv(act(base_conv(z)) + res(z)) with the res branch swapped in
+  full = O.two_layer_res_synthesis(wts, y, res_type="d2s")
+  base = O.apply_activation(O.keras_conv2d_transpose(y, wts["synthesis.base_conv.kernel"], wts["synthesis.base_conv.bias"], 8), "igdn", wts, "synthesis.activation")
+  assert np.abs(full - O.keras_conv2d_transpose(base + want, wts["synthesis.out_conv.kernel"], wts["synthesis.out_conv.bias"], 2)).max() < 1e-12
+
+
 def test_hyper_synthesis_golden():
   got = O.hyper_synthesis(_wts("hs_w:"), GOLD["hs_z"])
   assert got.shape == (1, 8, 12, 8) and np.abs(got - GOLD["hs_out"]).max() < 1e-11

@@ -114,12 +114,23 @@ def test_profile_wrappers_are_unwrapped():
   assert set(w) == {"synthesis.conv.kernel", "synthesis.conv.bias"}
 
 
-def test_d2s_residual_and_unknown_classes_are_refused():
+def test_d2s_residual_is_exported_and_unknown_classes_are_refused():
+  """res_type="d2s" (common/transforms.py:339-348): Sequential [Lambda, Conv2D, Lambda, Conv2D, Lambda] -> res.conv_0 / res.conv_1."""
   rng = np.random.default_rng(3)
-  d2s = _fake("TwoLayerResSynthesis", base_conv=Conv2DTranspose(rng, 13, 320, 12), res=_fake("Sequential", layers=[]), activation=None,
+  conv2d = lambda cin, cout: types.SimpleNamespace(kernel=_Var(rng.standard_normal((1, 1, cin, cout))), bias=_Var(rng.standard_normal(cout)), use_bias=True)
+  lam = lambda: types.SimpleNamespace()
+  seq = _fake("Sequential", layers=[lam(), conv2d(80, 192), lam(), conv2d(48, 48), lam()])
+  d2s = _fake("TwoLayerResSynthesis", base_conv=Conv2DTranspose(rng, 13, 320, 12), res=seq, activation=None,
               out_conv=Conv2DTranspose(rng, 5, 12, 3))
+  w = tf_glue.export_transform_weights(d2s, "synthesis")
+  assert w["synthesis.res.conv_0.kernel"].shape == (1, 1, 80, 192) and w["synthesis.res.conv_1.bias"].shape == (48,)
+  from shallow_ntc_b200 import transforms as T
+  want = T.TwoLayerResSynthesis(activation_type=None, res_type="d2s").variable_shapes(320)
+  assert {k: v.shape for k, v in w.items()} == {k: tuple(v) for k, v in want.items()}
+  broken = _fake("TwoLayerResSynthesis", base_conv=Conv2DTranspose(rng, 13, 320, 12), res=_fake("Sequential", layers=[]), activation=None,
+                 out_conv=Conv2DTranspose(rng, 5, 12, 3))
   with pytest.raises(NotImplementedError):
-    tf_glue.export_transform_weights(d2s, "synthesis")
+    tf_glue.export_transform_weights(broken, "synthesis")
   with pytest.raises(NotImplementedError):
     tf_glue.export_transform_weights(_fake("ElicSynthesis"), "synthesis")
 
