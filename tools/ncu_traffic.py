@@ -32,5 +32,5 @@ for path in sys.argv[1:]:
     i += 1
 print(json.dumps(dict(source="ncu --set full --clock-control none under `python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-io-stage --no-side`: "
                              "the four band_gemm_tc_kernel<2> launches of the first timed step (-k regex:band_gemm_tc_kernel -s 12 -c 4) and one "
-                             "tail_s2_mma_kernel launch; summaries in profiles/r02_ncu_full_tc.txt / r02_ncu_full_tail.txt",
+                             "tail launch (tail_tz_kernel since v3); summaries in profiles/r02_ncu_full_tc*.txt / r02_ncu_full_tail*.txt",
                       batch=24, step_total_dram_bytes=sum(v["dram_bytes_per_launch"] for v in kernels.values()), kernels=kernels), indent=1))
