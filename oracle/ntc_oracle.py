@@ -188,6 +188,95 @@ def apply_activation(x, act, weights=None, prefix=None):
 
 
 # --------------------------------------------------------------------------
+# decoder backward (f4: the gradient tf.GradientTape takes through the transforms in itinf_train_step,
+# mshyper/models.py:401-408) -- the adjoints of the statements above, by definition
+
+def conv_transpose_input_grad(g, w_oi, s: int, p: int, dtype=np.float64):
+  """Adjoint of conv_transpose_scatter w.r.t. x:  gx[b, ny, nx, ci] = sum_{ay, ax, co} g[b, ny*s+ay-p, nx*s+ax-p, co] * w_oi[ay, ax, co, ci]
+  (positions outside g contribute nothing; the bias has no input gradient)."""
+  g = np.asarray(g, dtype=dtype)
+  w_oi = np.asarray(w_oi, dtype=dtype)
+  B, H, W, cout = g.shape
+  kh, kw, cout2, cin = w_oi.shape
+  assert cout == cout2 and H % s == 0 and W % s == 0
+  h, w = H // s, W // s
+  gx = np.zeros((B, h, w, cin), dtype=dtype)
+  for ay in range(kh):
+    ylo, yhi = _valid_range(h, s, ay, p)
+    if yhi < ylo:
+      continue
+    for ax in range(kw):
+      xlo, xhi = _valid_range(w, s, ax, p)
+      if xhi < xlo:
+        continue
+      oy0, ox0 = ylo * s + ay - p, xlo * s + ax - p
+      gx[:, ylo:yhi + 1, xlo:xhi + 1, :] += g[:, oy0:oy0 + (yhi - ylo) * s + 1:s, ox0:ox0 + (xhi - xlo) * s + 1:s, :] @ w_oi[ay, ax]
+  return gx
+
+
+def gdn1_vjp(x, g, beta, gamma, inverse: bool):
+  """Adjoint of gdn1 at x:  t_j = x_j * n_j (inverse) or x_j / n_j,  n_j = beta_j + sum_i |x_i| gamma_ij
+     inverse:  gx_k = g_k n_k + sign(x_k) sum_j g_j x_j gamma_kj
+     forward:  gx_k = g_k / n_k - sign(x_k) sum_j g_j x_j / n_j^2 gamma_kj        (sign(0) = 0, the subgradient TF uses for abs)"""
+  dt = x.dtype
+  gamma = np.asarray(gamma, dtype=dt)
+  n = np.abs(x) @ gamma + np.asarray(beta, dtype=dt)
+  if inverse:
+    return g * n + np.sign(x) * ((g * x) @ gamma.T)
+  return g / n - np.sign(x) * ((g * x / (n * n)) @ gamma.T)
+
+
+def activation_vjp(pre, g, act, weights=None, prefix=None):
+  """Adjoint of apply_activation at the pre-activation value `pre` (tf.nn.relu / leaky_relu: derivative 0 / alpha at pre <= 0 ... < 0)."""
+  if act is None:
+    return g
+  a = act.lower()
+  if a == "relu":
+    return g * (pre > 0)
+  if a in ("leaky_relu", "lrelu"):
+    return g * np.where(pre > 0, 1.0, 0.2).astype(g.dtype)
+  if a in ("igdn", "igdn1"):
+    return gdn1_vjp(pre, g, weights[prefix + ".beta"], weights[prefix + ".gamma"], True)
+  if a in ("gdn", "gdn1"):
+    return gdn1_vjp(pre, g, weights[prefix + ".beta"], weights[prefix + ".gamma"], False)
+  raise NotImplementedError(act)
+
+
+def hyper_synthesis_vjp(wts, z_hat, g, activation_type="relu", prefix="hyper_synthesis"):
+  """J^T g of hyper_synthesis at z_hat (float64): returns (out, grad_z)."""
+  dt = np.float64
+  K = lambda i: np.asarray(wts[f"{prefix}.layer_{i}.kernel"], dt)
+  pre0 = keras_conv2d_transpose(z_hat, K(0), wts[f"{prefix}.layer_0.bias"], 2, dt)
+  a0 = apply_activation(pre0, activation_type)
+  pre1 = keras_conv2d_transpose(a0, K(1), wts[f"{prefix}.layer_1.bias"], 2, dt)
+  a1 = apply_activation(pre1, activation_type)
+  out = keras_conv2d_transpose(a1, K(2), wts[f"{prefix}.layer_2.bias"], 1, dt)
+  g = conv_transpose_input_grad(g, K(2), 1, keras_same_pad(3, 1))
+  g = conv_transpose_input_grad(activation_vjp(pre1, g, activation_type), K(1), 2, keras_same_pad(5, 2))
+  g = conv_transpose_input_grad(activation_vjp(pre0, g, activation_type), K(0), 2, keras_same_pad(5, 2))
+  return out, g
+
+
+def two_layer_res_synthesis_vjp(wts, y_hat, g, strides=(8, 2), activation_type="igdn", prefix="synthesis", res=True):
+  """J^T g of two_layer_res_synthesis (res=True) / two_layer_synthesis (res=False) at y_hat (float64): (out, grad_y)."""
+  dt = np.float64
+  n1, n2 = ("base_conv", "out_conv") if res else ("conv1", "conv2")
+  K1, K2 = np.asarray(wts[f"{prefix}.{n1}.kernel"], dt), np.asarray(wts[f"{prefix}.{n2}.kernel"], dt)
+  pre = keras_conv2d_transpose(y_hat, K1, wts[f"{prefix}.{n1}.bias"], strides[0], dt)
+  t = apply_activation(pre, activation_type, wts, f"{prefix}.activation")
+  if res:
+    Kr = np.asarray(wts[f"{prefix}.res.kernel"], dt)
+    t = t + keras_conv2d_transpose(y_hat, Kr, wts[f"{prefix}.res.bias"], strides[0], dt)
+  out = keras_conv2d_transpose(t, K2, wts[f"{prefix}.{n2}.bias"], strides[1], dt)
+  gt = conv_transpose_input_grad(g, K2, strides[1], keras_same_pad(K2.shape[0], strides[1]))
+  p1 = keras_same_pad(K1.shape[0], strides[0])
+  gy = conv_transpose_input_grad(activation_vjp(pre, gt, activation_type, wts, f"{prefix}.activation"), K1, strides[0], p1)
+  if res:
+    gy = gy + conv_transpose_input_grad(gt, Kr, strides[0], p1)
+  return out, gy
+
+
+# --------------------------------------------------------------------------
 # transforms (weights: dict name -> ndarray in the reference's native layouts)
 
 def hyper_synthesis(wts, z_hat, activation_type="relu", dtype=np.float64, gemm_form=False, prefix="hyper_synthesis"):

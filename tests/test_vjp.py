@@ -1,0 +1,78 @@
+"""Decoder backward (f4: the gradient through the transforms in itinf_train_step, mshyper/models.py:401-408).
+CPU part: the two statements of the oracle (numpy adjoints by definition, torch float64 autograd) against each other and against
+the forward oracle.  GPU part (-m gpu): libsntc's sntc_*_vjp against the autograd oracle, fp32 and tensor-core backward."""
+import numpy as np
+import pytest
+
+from shallow_ntc_b200 import transforms as T, synthetic
+from oracle import ntc_oracle as O
+from oracle import torch_vjp as V
+
+CASES = [   # (class, ctor kwargs, input channels, latent h x w)
+  ("HyperSynthesis", dict(bottleneck_size=16), 16, (3, 4)),
+  ("HyperSynthesis", dict(bottleneck_size=16, activation_type="leaky_relu"), 16, (2, 3)),
+  ("JPEGLikeHyperSynthesis", dict(bottleneck_size=8), 12, (3, 2)),
+  ("HyperSynthesisSmall", dict(bottleneck_size=8), 8, (4, 3)),
+  ("JPEGLikeSynthesis", dict(kernel_size=18, strides=16), 16, (2, 3)),
+  ("JPEGLikeSynthesis", dict(kernel_size=18, strides=16, use_offset=True, use_bias=False), 16, (2, 2)),
+  ("TwoLayerSynthesis", dict(channels=(12, 3)), 16, (2, 3)),
+  ("TwoLayerSynthesis", dict(channels=(8, 3), activation_type="relu"), 16, (2, 2)),
+  ("TwoLayerSynthesis", dict(channels=(8, 3), activation_type="gdn"), 16, (2, 2)),
+  ("TwoLayerResSynthesis", dict(channels=(12, 3)), 16, (3, 2)),
+  ("MBT2018Synthesis", dict(channels_base=8), 8, (2, 3)),
+  ("BLS2017Synthesis", dict(num_filters=8), 8, (3, 2)),
+  ("CNNSynthesis", dict(channels_base=8, activation_type="igdn"), 8, (2, 2)),
+  ("CNNSynthesis", dict(channels_base=8), 8, (2, 2)),
+]
+
+
+def small_case(cls, kw, cin, hw, seed=5, B=2):
+  t = T.class_builder.build(cls, **kw)
+  wts = synthetic.make_weights(t.variable_shapes(cin), "stress", synthesis_cls=cls)
+  rng = np.random.default_rng(seed)
+  x = rng.standard_normal((B, hw[0], hw[1], cin)) * 1.5
+  g = rng.standard_normal((B, hw[0] * t.upsample, hw[1] * t.upsample, t.out_channels))
+  okw = {k: v for k, v in kw.items() if k not in ("bottleneck_size", "channels_base", "num_filters", "channels", "kernel_size")}
+  return t, wts, x, g, okw
+
+
+@pytest.mark.parametrize("cls,kw,cin,hw", CASES)
+def test_autograd_statement_forward_matches_the_oracle(cls, kw, cin, hw):
+  t, wts, x, g, okw = small_case(cls, kw, cin, hw)
+  fn = O.hyper_synthesis_by_name if t.role == "hyper_synthesis" else O.synthesis
+  want = fn(cls, wts, x, okw)
+  out, gin = V.transform_vjp(cls, wts, x, g, okw)
+  assert out.shape == want.shape and np.abs(out - want).max() < 1e-10 * max(1.0, np.abs(want).max())
+  assert gin.shape == x.shape
+  # <g, J v> == <J^T g, v>
+  v = np.random.default_rng(9).standard_normal(x.shape)
+  jv = V.transform_jvp(cls, wts, x, v, okw)
+  lhs, rhs = float((g * jv).sum()), float((gin * v).sum())
+  assert abs(lhs - rhs) < 1e-9 * max(1.0, abs(lhs))
+
+
+def test_numpy_adjoints_match_autograd():
+  """conv_transpose_input_grad / gdn1_vjp / activation_vjp by definition == autograd, through two whole transforms."""
+  t, wts, x, g, okw = small_case("HyperSynthesis", dict(bottleneck_size=16), 16, (3, 4))
+  out, gin = O.hyper_synthesis_vjp(wts, x, g)
+  o2, g2 = V.transform_vjp("HyperSynthesis", wts, x, g, okw)
+  assert np.abs(out - o2).max() < 1e-10 and np.abs(gin - g2).max() < 1e-10 * max(1.0, np.abs(g2).max())
+  for cls, res in (("TwoLayerResSynthesis", True), ("TwoLayerSynthesis", False)):
+    for act in ("igdn", "gdn", "relu"):
+      t, wts, x, g, okw = small_case(cls, dict(channels=(12, 3), activation_type=act), 16, (3, 2))
+      out, gin = O.two_layer_res_synthesis_vjp(wts, x, g, activation_type=act, res=res)
+      o2, g2 = V.transform_vjp(cls, wts, x, g, okw)
+      assert np.abs(out - o2).max() < 1e-10 and np.abs(gin - g2).max() < 1e-10 * max(1.0, np.abs(g2).max()), (cls, act)
+
+
+def test_conv_transpose_input_grad_geometries():
+  """every (k, s, p) on the path, ragged sizes: the adjoint identity <g, conv(x)> == <conv^T(g), x>."""
+  rng = np.random.default_rng(3)
+  for k, s, keras in ((13, 8, True), (5, 2, True), (3, 1, True), (18, 16, True), (6, 4, True), (5, 2, False), (9, 4, False), (3, 1, False)):
+    p = O.keras_same_pad(k, s) if keras else O.tfc_same_pad(k)
+    w = rng.standard_normal((k, k, 3, 4))
+    x = rng.standard_normal((1, 3, 2, 4))
+    g = rng.standard_normal((1, 3 * s, 2 * s, 3))
+    y = O.conv_transpose_scatter(x, w, None, s, p)
+    gx = O.conv_transpose_input_grad(g, w, s, p)
+    assert abs(float((g * y).sum()) - float((gx * x).sum())) < 1e-9
