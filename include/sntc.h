@@ -198,6 +198,20 @@ int sntc_model_enable_graphs(sntc_model* m, int on);
 int sntc_hyper_synthesis(sntc_model* m, const sntc_tensor* z_hat, sntc_tensor* out, void* stream);
 int sntc_synthesis(sntc_model* m, const sntc_tensor* y_hat, sntc_tensor* out, void* stream);
 
+/* ---- decoder backward (the gradient tf.GradientTape takes through the two transforms) ----
+ * itinf_train_step  mshyper/models.py:401-408:  gradients = tape.gradient(loss, latent_rvs.trainable_variables), where the loss
+ * reaches the latents through self._hyper_synthesis(z) (:273) and self._synthesis(y, training=True) (:297).  These two calls are
+ * the vector-Jacobian products a tf.custom_gradient around the transform-level calls above returns:
+ *   grad_in [B,h,w,Cin] = J_f(x)^T grad_out,   grad_out [B, h*up, w*up, Cout] = d loss / d f(x) on the FULL (padded) output grid
+ *   (zeros where unpad_images cropped).  `out` (nullable) receives f(x) of the same pass (fp32 kernels).
+ * The input-gradient of every transposed conv runs as a forward stride-1 band GEMM on a space-to-depth of the gradient (tcgen05
+ * for models created with a tensor-core precision); GDN1 / relu / leaky_relu adjoints are pointwise kernels.
+ * sntc_model_enable_vjp(m, 1) must precede sntc_model_finalize (the backward layers are packed from the host weights);
+ * TwoLayerResSynthesis(res_type="d2s") has no backward (SNTC_E_UNSUPPORTED). */
+int sntc_model_enable_vjp(sntc_model* m, int on);
+int sntc_synthesis_vjp(sntc_model* m, const sntc_tensor* y_hat, const sntc_tensor* grad_out, sntc_tensor* grad_in, sntc_tensor* out, void* stream);
+int sntc_hyper_synthesis_vjp(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* grad_out, sntc_tensor* grad_in, sntc_tensor* out, void* stream);
+
 /* ---- fused decode ----
  * Replaces mshyper/models.py:269-317 with training=False (factorized/models.py:101-141 when the
  * model has no hyperprior; then z_hat and out_idx must be NULL):

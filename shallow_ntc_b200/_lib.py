@@ -85,6 +85,9 @@ _PROTOS = {
   "sntc_model_enable_graphs": (C.c_int, [_P, C.c_int]),
   "sntc_hyper_synthesis": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), _P]),
   "sntc_synthesis": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), _P]),
+  "sntc_model_enable_vjp": (C.c_int, [_P, C.c_int]),
+  "sntc_synthesis_vjp": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), _P]),
+  "sntc_hyper_synthesis_vjp": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), _P]),
   "sntc_decode": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor),
                             C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(ImageMetrics), _P]),
   "sntc_decode_rd": (C.c_int, [_P, C.POINTER(Tensor), C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor),

@@ -21,6 +21,7 @@
 #include "sntc_kernels_tail_tz.cuh"
 #include "sntc_kernels_msssim.cuh"
 #include "sntc_kernels_lpips.cuh"
+#include "sntc_kernels_vjp.cuh"
 #include "sntc_coder.hpp"
 
 using namespace sntc;
@@ -74,6 +75,23 @@ struct GraphEntry { GraphKey key{}; cudaGraphExec_t exec = nullptr; bool failed 
 struct ProfRec { std::string label; cudaEvent_t a = nullptr, b = nullptr; double macs = 0; };
 struct ProfAgg { std::string label; float ms = 0; int n = 0; double macs = 0; };
 
+// Decoder backward (sntc_*_vjp): an fp32 plan of the transform (every conv a band GEMM, every op output kept) and, per conv,
+// its input-gradient as a forward stride-1 layer (sntc_plan.hpp make_backward_conv), packed for the tensor cores when the
+// model's precision asks for them.
+struct VjpPlan {
+  bool ok = false; std::string why;
+  Transform fwd;
+  std::vector<ConvLayer> bconv;         // parallel to fwd.convs
+  std::vector<TcConv> btc;              // parallel to fwd.convs (tensor-core precision only)
+  std::vector<float*> d_gamma_t;        // parallel to fwd.gdns: gamma^T [out][in] for the wide GDN adjoint (C > 64)
+  std::vector<DevBuf> acts;             // forward output of every op
+  DevBuf g[2], s2d, pl[2], ones, st_x, st_g, st_gin, st_out;
+  void release() {
+    for (auto& b : acts) b.release();
+    for (DevBuf* b : {&g[0], &g[1], &s2d, &pl[0], &pl[1], &ones, &st_x, &st_g, &st_gin, &st_out}) b->release();
+  }
+};
+
 struct sntc_model {
   sntc_ctx* ctx = nullptr;
   bool prof_on = false;
@@ -106,6 +124,8 @@ struct sntc_model {
   std::vector<GraphEntry> graphs;       // CUDA graphs of small-batch decodes, keyed by shapes + pointers (decode_impl)
   unsigned long long* h_ssd = nullptr;  // pinned
   int h_ssd_cap = 0;
+  bool want_vjp = false;                // sntc_model_enable_vjp: finalize also builds the backward plans
+  VjpPlan vjp_hyper, vjp_syn;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -360,6 +380,7 @@ extern "C" int sntc_model_destroy(sntc_model* m) {
                     &m->st_orig, &m->d_hs, &m->d_yhat, &m->d_ssd, &m->d_rate_slots, &m->d_rate_img, &m->d_rate_zslots, &m->d_rate, &m->d_mu, &m->d_flag})
     b->release();
   m->tc.release();
+  m->vjp_hyper.release(); m->vjp_syn.release();
   for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
   for (auto& r : m->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -411,6 +432,60 @@ static int upload(sntc_model* m, const void* host, size_t bytes, void** dptr) {
   CU_TRY(cudaMalloc(dptr, bytes ? bytes : 4));
   m->owned.push_back(*dptr);
   CU_TRY(cudaMemcpy(*dptr, host, bytes, cudaMemcpyHostToDevice));
+  return SNTC_OK;
+}
+
+extern "C" int sntc_model_enable_vjp(sntc_model* m, int on) {
+  if (!m) return fail(SNTC_E_INVALID, "sntc_model_enable_vjp: model is NULL");
+  if (m->finalized) return fail(SNTC_E_STATE, "sntc_model_enable_vjp: call it before sntc_model_finalize (the backward plans are packed from the host weights)");
+  m->want_vjp = on != 0;
+  return SNTC_OK;
+}
+
+// Builds the backward plan of one transform from the host weights (called by sntc_model_finalize).
+static int vjp_build(sntc_model* m, const sntc_transform_desc& d, const char* prefix, VjpPlan& P) {
+  try { P.fwd = build_transform(d, prefix); } catch (const std::exception& e) { return fail(SNTC_E_INVALID, std::string("vjp plan: ") + e.what()); }
+  for (auto& op : P.fwd.ops)
+    if (op.type == OP_STASH || op.type == OP_ACT_RES_D2S) { P.why = "TwoLayerResSynthesis(res_type='d2s') has no backward on this path"; return SNTC_OK; }
+  for (auto& c : P.fwd.convs) {
+    std::vector<float> b = pack_bias(c, m->hw), w = pack_band_weights(c, m->hw);
+    TRY(upload(m, b.data(), b.size() * 4, (void**)&c.d_bias));
+    TRY(upload(m, w.data(), w.size() * 4, (void**)&c.d_w));
+  }
+  P.d_gamma_t.assign(P.fwd.gdns.size(), nullptr);
+  for (size_t gi = 0; gi < P.fwd.gdns.size(); ++gi) {
+    GdnLayer& g = P.fwd.gdns[gi];
+    const auto& beta = m->hw.at(g.beta).second;
+    const auto& gamma = m->hw.at(g.gamma).second;
+    g.Npad = (g.C + 3) / 4 * 4;
+    std::vector<float> gp((size_t)g.C * g.Npad, 0.f), gt((size_t)g.C * g.Npad, 0.f);
+    for (int i = 0; i < g.C; ++i) for (int j = 0; j < g.C; ++j) {
+      gp[(size_t)i * g.Npad + j] = gamma[(size_t)i * g.C + j];
+      gt[(size_t)j * g.Npad + i] = gamma[(size_t)i * g.C + j];
+    }
+    TRY(upload(m, beta.data(), beta.size() * 4, (void**)&g.d_beta));
+    TRY(upload(m, gp.data(), gp.size() * 4, (void**)&g.d_gamma));
+    TRY(upload(m, gt.data(), gt.size() * 4, (void**)&P.d_gamma_t[gi]));
+  }
+  P.bconv.clear();
+  for (auto& c : P.fwd.convs) P.bconv.push_back(make_backward_conv(c));
+  const bool tc = is_tc(m->desc.precision);
+  P.btc.assign(P.bconv.size(), TcConv{});
+  for (size_t i = 0; i < P.bconv.size(); ++i) {
+    ConvLayer& bc = P.bconv[i];
+    std::vector<float> b = pack_bias(bc, m->hw);
+    TRY(upload(m, b.data(), b.size() * 4, (void**)&bc.d_bias));
+    if (tc && tc_conv_supported(bc)) {
+      std::string err;
+      if (!m->ctx->tc.encode) return fail(SNTC_E_CUDA, "vjp plan (tensor-core path): cuTensorMapEncodeTiled unavailable");
+      if (!tc_pack_conv(m->ctx->tc, bc, m->hw, P.btc[i], 0, m->owned, &err)) return fail(SNTC_E_CUDA, "vjp plan (tensor-core path): " + err);
+    }
+    if (!P.btc[i].ok) {
+      std::vector<float> w = pack_band_weights(bc, m->hw);
+      TRY(upload(m, w.data(), w.size() * 4, (void**)&bc.d_w));
+    }
+  }
+  P.ok = true;
   return SNTC_OK;
 }
 
@@ -501,6 +576,10 @@ extern "C" int sntc_model_finalize(sntc_model* m) {
     TRY(upload(m, pk.data(), pk.size() * 4, (void**)&m->d_prior));
   }
   for (auto& e : m->ev) CU_TRY(cudaEventCreate(&e));
+  if (m->want_vjp) {
+    if (m->has_hyper) TRY(vjp_build(m, m->desc.hyper, "hyper_synthesis", m->vjp_hyper));
+    if (m->has_syn) TRY(vjp_build(m, m->desc.synthesis, "synthesis", m->vjp_syn));
+  }
   m->hw.clear();
   m->finalized = true;
   return SNTC_OK;
@@ -677,7 +756,7 @@ static int run_conv_f32(sntc_ctx* ctx, const ConvLayer& c, const float* in, int 
       cell_range(c.by[yi], c.s, c.p, h, &P.mloy, &P.cnty);
       cell_range(c.bx[xi], c.s, c.p, w, &P.mlox, &P.cntx);
       P.act = c.act;
-      P.out = out; P.hout = h * c.s; P.wout = w * c.s; P.cstride = c.cout;
+      P.out = out; P.hout = h * c.s - c.out_crop; P.wout = w * c.s - c.out_crop; P.cstride = c.cout;
       if (fin) { P.out_u8 = fin->u8; P.out_crop = fin->crop; P.H = fin->H; P.W = fin->W; }
       P.gx = nullptr; P.gdn_mode = G_NONE;
       TRY(launch_band_gemm(ctx, P, s));
@@ -1130,6 +1209,180 @@ extern "C" int sntc_synthesis(sntc_model* m, const sntc_tensor* y_hat, sntc_tens
   TRY(unstage_out(out, tensor_elems(out) * 4, dout, s, &need_sync));
   if (need_sync) CU_TRY(cudaStreamSynchronize(s));
   return SNTC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder backward (f4; mshyper/models.py:401-408): grad_in = J(x)^T grad_out of one transform
+static int launch_act_bwd(sntc_ctx* ctx, const ActBwdParams& P, cudaStream_t s) {
+  if (P.npix == 0) return SNTC_OK;
+  if (P.C <= 64) {
+    const size_t smem = ((size_t)P.C * P.C + P.C + 2 * 128 * (P.C + 1)) * 4;
+    static size_t attr_bytes = 48 * 1024;
+    if (smem > attr_bytes) { CU_TRY(cudaFuncSetAttribute(act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+    act_bwd_kernel<<<(unsigned)((P.npix + 127) / 128), 128, smem, s>>>(P);
+  } else {
+    if (P.res_copy || !(P.act == SNTC_ACT_IGDN1 || P.act == SNTC_ACT_GDN1 || P.act == SNTC_ACT_IGDN_CLASSIC))
+      return fail(SNTC_E_UNSUPPORTED, "vjp: pointwise stage wider than 64 channels that is not a GDN");
+    const size_t smem = (size_t)2 * GB_PT * P.C * 4;
+    if (smem > 200 * 1024) return fail(SNTC_E_UNSUPPORTED, "vjp: GDN wider than 800 channels");
+    static size_t attr_bytes = 48 * 1024;
+    if (smem > attr_bytes) { CU_TRY(cudaFuncSetAttribute(gdn_bwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+    gdn_bwd_wide_kernel<<<(unsigned)((P.npix + GB_PT - 1) / GB_PT), 256, smem, s>>>(P);
+  }
+  ctx->launches++;
+  CU_TRY(cudaGetLastError());
+  return SNTC_OK;
+}
+
+static int vjp_run(sntc_model* m, VjpPlan& P, const float* x, const float* gout, float* gin, float* out, int B, int h, int w, cudaStream_t s) {
+  sntc_ctx* ctx = m->ctx;
+  Transform& t = P.fwd;
+  const size_t nops = t.ops.size();
+  if (P.acts.size() < nops) P.acts.resize(nops);
+  std::vector<int> ih(nops), iw(nops), ic(nops);
+  // ---- forward on the fp32 kernels, every op output kept ----
+  const float* cur = x;
+  int ch = h, cw = w, cc = t.in_channels;
+  for (size_t i = 0; i < nops; ++i) {
+    const Op& op = t.ops[i];
+    ih[i] = ch; iw[i] = cw; ic[i] = cc;
+    if (op.type == OP_CONVT) {
+      const ConvLayer& c = t.convs[op.conv];
+      const float* in = cur;
+      if (c.append_ones) {
+        const size_t n = (size_t)B * ch * cw * c.cin_pad;
+        TRY(P.ones.ensure(n * 4));
+        append_ones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cur, c.cin, (float*)P.ones.p, c.cin_pad, (size_t)B * ch * cw);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        in = (const float*)P.ones.p;
+      }
+      TRY(P.acts[i].ensure((size_t)B * ch * c.s * cw * c.s * c.cout * 4));
+      ProfScope ps(m, s, "vjp.forward." + c.sources[0].kernel.substr(0, c.sources[0].kernel.size() - 7), conv_macs(c, B, ch, cw));
+      TRY(run_conv_f32(ctx, c, in, B, ch, cw, (float*)P.acts[i].p, nullptr, s));
+      ch *= c.s; cw *= c.s; cc = c.cout;
+    } else if (op.type == OP_GDN) {
+      const GdnLayer& g = t.gdns[op.gdn];
+      TRY(P.acts[i].ensure((size_t)B * ch * cw * g.C * 4));
+      TRY(run_gdn_f32(ctx, g, cur, (size_t)B * ch * cw, (float*)P.acts[i].p, s));
+    } else if (op.type == OP_ACT_RES) {
+      const int C = cc / 2;
+      if (C > 64) return fail(SNTC_E_UNSUPPORTED, "two-layer hidden width > 64");
+      TRY(P.acts[i].ensure((size_t)B * ch * cw * C * 4));
+      ActResParams Q{};
+      Q.in = cur; Q.in_stride = cc; Q.out = (float*)P.acts[i].p; Q.npix = (size_t)B * ch * cw; Q.C = C; Q.act = op.act; Q.has_res = 1;
+      if (op.gdn >= 0) { const GdnLayer& g = t.gdns[op.gdn]; Q.beta = g.d_beta; Q.gamma = g.d_gamma; Q.gamma_stride = g.Npad; Q.inverse = g.inverse; }
+      TRY(launch_act_res(ctx, Q, s));
+      cc = C;
+    } else {
+      return fail(SNTC_E_UNSUPPORTED, "vjp: op without a backward");
+    }
+    cur = (const float*)P.acts[i].p;
+  }
+  if (out) CU_TRY(cudaMemcpyAsync(out, cur, (size_t)B * ch * cw * cc * 4, cudaMemcpyDeviceToDevice, s));
+  // ---- backward ----
+  const float* g = gout;
+  int flip = 0;
+  for (size_t ii = nops; ii-- > 0;) {
+    const Op& op = t.ops[ii];
+    const float* xin = ii > 0 ? (const float*)P.acts[ii - 1].p : x;
+    const size_t in_bytes = (size_t)B * ih[ii] * iw[ii] * ic[ii] * 4;
+    float* dst;
+    if (ii == 0) dst = gin;
+    else { TRY(P.g[flip].ensure(in_bytes)); dst = (float*)P.g[flip].p; flip ^= 1; }
+    if (op.type == OP_CONVT) {
+      const ConvLayer& c = t.convs[op.conv];
+      ConvLayer& bc = P.bconv[op.conv];
+      TcConv& btc = P.btc[op.conv];
+      const int T = bc.k, hm = ih[ii] + T - 1, wm = iw[ii] + T - 1;
+      const int Cp = btc.ok ? bc.cin : bc.cin_pad;
+      S2dGradParams Q{};
+      Q.g = g; Q.a = c.act != SNTC_ACT_NONE ? (const float*)P.acts[ii].p : nullptr; Q.act = c.act;
+      Q.B = B; Q.H = ih[ii] * c.s; Q.W = iw[ii] * c.s; Q.Cf = c.cout; Q.s = c.s; Q.p = c.p; Q.hm = hm; Q.wm = wm; Q.Cpad = Cp;
+      const size_t n = (size_t)B * hm * wm * Cp;
+      if (btc.ok) {
+        TRY(P.pl[0].ensure(n * 2)); TRY(P.pl[1].ensure(n * 2));
+        Q.hi = (__half*)P.pl[0].p; Q.lo = (__half*)P.pl[1].p;
+      } else {
+        TRY(P.s2d.ensure(n * 4));
+        Q.out = (float*)P.s2d.p;
+      }
+      const std::string lbl = "vjp.backward." + c.sources[0].kernel.substr(0, c.sources[0].kernel.size() - 7);
+      {
+        ProfScope ps(m, s, lbl + ".s2d", 0);
+        s2d_grad_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(Q);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+      }
+      ProfScope ps(m, s, lbl, conv_macs(bc, B, hm, wm));
+      if (btc.ok) {
+        TcConvOut o;
+        o.f32 = dst;
+        std::string err;
+        if (tc_run_conv(ctx->tc, bc, btc, Q.hi, Q.lo, B, hm, wm, o, s, &ctx->launches, &err) != TC_OK)
+          return fail(SNTC_E_CUDA, "vjp (tensor-core path): " + err);
+        ctx->kinds[SNTC_LAUNCH_BAND_TC]++;
+      } else {
+        TRY(run_conv_f32(ctx, bc, Q.out, B, hm, wm, dst, nullptr, s));
+      }
+    } else if (op.type == OP_GDN || op.type == OP_ACT_RES) {
+      ActBwdParams Q{};
+      const bool res = op.type == OP_ACT_RES;
+      const int C = res ? ic[ii] / 2 : ic[ii];
+      Q.x = xin; Q.x_stride = ic[ii]; Q.g = g; Q.g_stride = C; Q.out = dst; Q.out_stride = ic[ii];
+      Q.npix = (size_t)B * ih[ii] * iw[ii]; Q.C = C; Q.res_copy = res ? 1 : 0; Q.act = op.act;
+      if (op.gdn >= 0) {
+        const GdnLayer& gl = t.gdns[op.gdn];
+        Q.act = gl.kind == GDN_CLASSIC ? SNTC_ACT_IGDN_CLASSIC : (gl.inverse ? SNTC_ACT_IGDN1 : SNTC_ACT_GDN1);
+        Q.inverse = gl.inverse ? 1 : 0; Q.classic = gl.kind == GDN_CLASSIC ? 1 : 0;
+        Q.beta = gl.d_beta; Q.gamma = gl.d_gamma; Q.gamma_stride = gl.Npad; Q.gamma_t = P.d_gamma_t[op.gdn];
+      }
+      ProfScope ps(m, s, "vjp.backward.activation", (double)Q.npix * C * C * 2);
+      TRY(launch_act_bwd(ctx, Q, s));
+    }
+    g = dst;
+  }
+  return SNTC_OK;
+}
+
+static int vjp_entry(sntc_model* m, bool is_hyper, const sntc_tensor* x, const sntc_tensor* grad_out, sntc_tensor* grad_in, sntc_tensor* out, void* stream) {
+  const char* fn = is_hyper ? "sntc_hyper_synthesis_vjp" : "sntc_synthesis_vjp";
+  if (!m) return fail(SNTC_E_INVALID, std::string(fn) + ": model is NULL");
+  if (!m->finalized) return fail(SNTC_E_STATE, std::string(fn) + ": model not finalized");
+  if (is_hyper ? !m->has_hyper : !m->has_syn) return fail(SNTC_E_STATE, std::string(fn) + ": model has no such transform");
+  VjpPlan& P = is_hyper ? m->vjp_hyper : m->vjp_syn;
+  if (!m->want_vjp) return fail(SNTC_E_STATE, std::string(fn) + ": call sntc_model_enable_vjp(model, 1) before sntc_model_finalize");
+  if (!P.ok) return fail(SNTC_E_UNSUPPORTED, std::string(fn) + ": " + (P.why.empty() ? std::string("no backward plan") : P.why));
+  TRY(check_tensor(x, "x", SNTC_DL_FLOAT, 32, 4));
+  TRY(check_tensor(grad_out, "grad_out", SNTC_DL_FLOAT, 32, 4));
+  TRY(check_tensor(grad_in, "grad_in", SNTC_DL_FLOAT, 32, 4));
+  if (out) TRY(check_tensor(out, "out", SNTC_DL_FLOAT, 32, 4));
+  const Transform& t = P.fwd;
+  const int B = (int)x->shape[0], h = (int)x->shape[1], w = (int)x->shape[2];
+  if (x->shape[3] != t.in_channels) return fail(SNTC_E_INVALID, "x: wrong channel count");
+  TRY(expect_shape(grad_in, "grad_in", B, h, w, t.in_channels));
+  TRY(expect_shape(grad_out, "grad_out", B, (int64_t)h * t.upsample, (int64_t)w * t.upsample, t.out_channels));
+  if (out) TRY(expect_shape(out, "out", B, (int64_t)h * t.upsample, (int64_t)w * t.upsample, t.out_channels));
+  if (tensor_elems(x) == 0) return SNTC_OK;
+  CU_TRY(cudaSetDevice(m->ctx->device));
+  cudaStream_t s = pick_stream(m->ctx, stream);
+  const void *dx, *dg; void *dgin, *dout = nullptr; bool need_sync = false;
+  TRY(stage_in(m, x, tensor_elems(x) * 4, P.st_x, s, &dx));
+  TRY(stage_in(m, grad_out, tensor_elems(grad_out) * 4, P.st_g, s, &dg));
+  TRY(stage_out(m, grad_in, tensor_elems(grad_in) * 4, P.st_gin, &dgin));
+  if (out) TRY(stage_out(m, out, tensor_elems(out) * 4, P.st_out, &dout));
+  TRY(vjp_run(m, P, (const float*)dx, (const float*)dg, (float*)dgin, (float*)dout, B, h, w, s));
+  TRY(unstage_out(grad_in, tensor_elems(grad_in) * 4, dgin, s, &need_sync));
+  if (out) TRY(unstage_out(out, tensor_elems(out) * 4, dout, s, &need_sync));
+  if (need_sync) CU_TRY(cudaStreamSynchronize(s));
+  return SNTC_OK;
+}
+
+extern "C" int sntc_synthesis_vjp(sntc_model* m, const sntc_tensor* y_hat, const sntc_tensor* grad_out, sntc_tensor* grad_in, sntc_tensor* out, void* stream) {
+  return vjp_entry(m, false, y_hat, grad_out, grad_in, out, stream);
+}
+extern "C" int sntc_hyper_synthesis_vjp(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* grad_out, sntc_tensor* grad_in, sntc_tensor* out, void* stream) {
+  return vjp_entry(m, true, z_hat, grad_out, grad_in, out, stream);
 }
 
 static int decode_impl(sntc_model* m, const sntc_tensor* z_hat, const sntc_tensor* q_y, int H, int W,

@@ -1519,7 +1519,7 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   P.kblocks = t.kblocks; P.last_kmma = t.last_kmma;
   P.cout = c.cout; P.bn_max = bn_max; P.stages = stages;
   P.inv_scale = 1.f / t.scale; P.bias = c.d_bias; P.act = c.act;
-  P.hout = h * c.s; P.wout = w * c.s;
+  P.hout = h * c.s - c.out_crop; P.wout = w * c.s - c.out_crop;
   P.epi = o.hyper_final ? TC_EPI_HYPER_FINAL : (o.two_layer ? TC_EPI_TWO_LAYER : TC_EPI_PLAIN);
   P.out_hi = o.hi; P.out_lo = o.lo; P.out_f32 = o.f32; P.out_u8 = o.u8; P.out_crop = o.crop; P.H = o.H; P.W = o.W;
   P.q = o.q; P.q_kind = o.q_kind; P.Cy = o.Cy; P.max_index = o.max_index; P.trunc = o.trunc ? 1 : 0; P.y_hat = o.y_hat; P.idx = o.idx;

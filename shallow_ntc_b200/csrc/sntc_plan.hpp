@@ -25,7 +25,9 @@ enum KernelLayout { LAYOUT_KERAS_OI = 0 /* [kh,kw,Cout,Cin] */, LAYOUT_TFC_IO = 
                     // tf.nn.depth_to_space(x, 2) followed by a Keras Conv2D 1x1 (variable [1,1,Cin/4,Cout]) IS a transposed conv with
                     // k = s = 2, p = 0 whose tap (dy, dx) only sees input channels [(2 dy + dx) Cin/4, (2 dy + dx + 1) Cin/4):
                     //   out[2y+dy, 2x+dx, co] = sum_c in[y, x, (2 dy + dx) Cin/4 + c] * K[0, 0, c, co]      (NHWC / DCR order)
-                    LAYOUT_D2S_1X1 = 2 };
+                    LAYOUT_D2S_1X1 = 2,
+                    // the input-gradient of another layer written as a stride-1 layer of this plan (make_backward_conv)
+                    LAYOUT_BACKWARD = 3 };
 enum GdnKind { GDN_NONE = 0, GDN_1 = 1 /* beta + |x| gamma */, GDN_CLASSIC = 2 /* sqrt(beta + x^2 gamma) */ };
 
 struct Band1D {
@@ -77,6 +79,8 @@ struct ConvLayer {
   // r = o mod s of a cell (o = s*i + r), with a uniform tap window d = i - n in [dlo, dlo + T): a = r + p + s*d
   // (taps outside [0,k) are zero weights).  N = s*s*cout instead of a handful of 3-column bands.
   bool merged = false; int dlo = 0;
+  int out_crop = 0;          // the output grid is h*s - out_crop rows / columns (backward layers: the input carries T-1 extra rows)
+  std::vector<ConvLayer> bwd_src;   // LAYOUT_BACKWARD: copy of the forward layer whose input-gradient this layer computes
   int act = SNTC_ACT_NONE;   // only NONE / RELU / LEAKY_RELU are fused into the conv
   std::vector<ConvSource> sources;  // concatenated along Cout (base || res)
   std::vector<Band1D> by, bx;
@@ -177,6 +181,25 @@ inline ConvLayer make_conv(const std::string& prefix, const std::string& name, i
   c.k = k; c.s = s; c.cin = cin; c.cout = cout; c.layout = layout; c.has_bias = bias; c.act = act;
   c.p = layout == LAYOUT_KERAS_OI ? keras_pad(k, s) : tfc_pad(k);
   c.sources.push_back({prefix + "." + name + ".kernel", bias ? prefix + "." + name + ".bias" : std::string(), cout});
+  finish_conv(c);
+  return c;
+}
+
+// Input-gradient of the transposed conv `f` as a FORWARD layer of this plan (decoder backward, mshyper/models.py:401-408).
+//   gin[n, ci] = sum_{a, co} g[s n + a - p, co] W[a, co, ci].   Write a = s d + r (r in [0,s), d in [0,T), T = ceil(k/s)) and
+//   G'[m, (ry, rx, co)] = g[s m + r - p, co]  (zero outside g; m in [0, h + T - 1): a shifted space-to-depth of the gradient).
+//   Then gin[n] = sum_{d} G'[n + d] Wb[d],  Wb[d][(r, co), ci] = W[s d + r, co, ci] (zero where s d + r >= k):
+//   a stride-1 layer with T x T taps, Cin' = s*s*Cout, Cout' = Cin, p' = T - 1 in the ConvT form (tap a' = T - 1 - d),
+//   run on the [h + T - 1, w + T - 1] grid of G' with the output cropped to [h, w].
+inline ConvLayer make_backward_conv(const ConvLayer& f) {
+  ConvLayer c;
+  const int T = (f.k + f.s - 1) / f.s;
+  c.k = T; c.s = 1; c.p = T - 1; c.cin = f.s * f.s * f.cout; c.cout = f.cin;
+  c.layout = LAYOUT_BACKWARD; c.has_bias = false; c.act = SNTC_ACT_NONE; c.out_crop = T - 1;
+  for (auto& s : f.sources) c.sources.push_back({s.kernel, std::string(), 0});   // names only (weight range of the fp16 packing)
+  c.sources[0].cout = c.cout;
+  c.bwd_src.push_back(f);
+  c.bwd_src[0].bwd_src.clear();
   finish_conv(c);
   return c;
 }
@@ -366,6 +389,15 @@ using HostWeights = std::map<std::string, std::pair<std::vector<int64_t>, std::v
 
 // W[ay, ax, co, ci] of a conv layer with concatenated sources, from the reference's native layouts.
 inline float conv_w(const ConvLayer& c, const HostWeights& hw, int ay, int ax, int co, int ci) {
+  if (c.layout == LAYOUT_BACKWARD) {   // see make_backward_conv: tap a' = T-1-d, input channel (ry, rx, co_f), output channel ci_f
+    const ConvLayer& f = c.bwd_src[0];
+    const int dy = c.k - 1 - ay, dx = c.k - 1 - ax;
+    const int r = ci / f.cout, cof = ci - r * f.cout;
+    if (r >= f.s * f.s) return 0.f;
+    const int fay = f.s * dy + r / f.s, fax = f.s * dx + r % f.s;
+    if (fay >= f.k || fax >= f.k) return 0.f;
+    return conv_w(f, hw, fay, fax, cof, co);
+  }
   int base = 0;
   for (auto& s : c.sources) {
     if (co < base + s.cout) {

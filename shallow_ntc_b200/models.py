@@ -53,7 +53,7 @@ class _NativeModel:
 
 
 def _create_model(ctx: Context, hyper: TransformDesc, syn: TransformDesc, weights: dict, precision="fp32",
-                  index_rounding=DEFAULT_INDEX_ROUNDING, num_scales=NUM_SCALES, prior=False) -> _NativeModel:
+                  index_rounding=DEFAULT_INDEX_ROUNDING, num_scales=NUM_SCALES, prior=False, vjp=False) -> _NativeModel:
   desc = ModelDesc(struct_size=C.sizeof(ModelDesc), hyper=hyper, synthesis=syn, num_scales=num_scales,
                    index_rounding=_ROUNDING[index_rounding], precision=_PRECISION[precision],
                    prior=_lib.PRIOR_DEEP_FACTORIZED if prior else _lib.PRIOR_NONE)
@@ -66,6 +66,8 @@ def _create_model(ctx: Context, hyper: TransformDesc, syn: TransformDesc, weight
     w = np.ascontiguousarray(weights[name], dtype=np.float32)
     shp = (C.c_int64 * w.ndim)(*w.shape)
     check(lib.sntc_model_load_weights(h, name.encode(), w.ctypes.data_as(C.POINTER(C.c_float)), shp, w.ndim))
+  if vjp:   # decoder backward: the backward layers are packed from the host weights at finalize
+    check(lib.sntc_model_enable_vjp(h, 1))
   check(lib.sntc_model_finalize(h))
   return m
 
@@ -89,8 +91,10 @@ class Model:
   factorized-prior model (``factorized/models.py``: no z, no scale indexes, DOWNSAMPLE_FACTOR 16)."""
 
   def __init__(self, transform_config, bottleneck_size=None, hyperprior=True, profile=False, device=0,
-               precision="fp32", index_rounding=DEFAULT_INDEX_ROUNDING, ctx: Context | None = None, prior=False, **_ignored_training_kwargs):
+               precision="fp32", index_rounding=DEFAULT_INDEX_ROUNDING, ctx: Context | None = None, prior=False, vjp=False,
+               **_ignored_training_kwargs):
     self._transform_config = transform_config
+    self._vjp = bool(vjp)      # also build the decoder backward (synthesis_vjp / hyper_synthesis_vjp)
     self._with_prior = bool(prior) and hyperprior    # self._prior = tfc.NoisyDeepFactorized(...)   mshyper/models.py:135
     self._profile = profile
     self.precision = precision
@@ -169,7 +173,8 @@ class Model:
     hyper = (self._hyper_synthesis.desc(self._hyper_synthesis.in_channels) if self._hyper_synthesis is not None
              else TransformDesc(kind=_lib.T_NONE))
     syn = self._synthesis.desc(self._bottleneck_size)
-    self._native = _create_model(self._ctx, hyper, syn, self._weights, self.precision, self.index_rounding, prior=self._with_prior)
+    self._native = _create_model(self._ctx, hyper, syn, self._weights, self.precision, self.index_rounding, prior=self._with_prior,
+                                 vjp=self._vjp)
     if self._profile:   # stage times come from CUDA events around eagerly launched kernels: no graph replay
       check(lib.sntc_model_enable_graphs(self._native.handle, 0))
 
@@ -370,6 +375,34 @@ class Model:
     check(lib.sntc_synthesis(self._native.handle, y.byref(), o.byref(), None))
     self._ctx.sync()
     return out
+
+
+  # ---------------------------------------------------------------------------------------------
+  # decoder backward: what tape.gradient propagates through the two transforms in itinf_train_step
+  # (mshyper/models.py:401-408).  Model(..., vjp=True).
+  def _vjp_call(self, fn, transform, x, grad_out, return_out):
+    if not self._vjp:
+      raise RuntimeError("construct the model with vjp=True to use the decoder backward")
+    self._ensure_native()
+    xt = as_tensor(x, self._ctx.device)
+    B, h, w, _ = xt.shape
+    up = transform.upsample
+    gt = as_tensor(grad_out, self._ctx.device)
+    gin = empty_like_kind(self._ctx, x, tuple(xt.shape), np.float32)
+    out = empty_like_kind(self._ctx, x, (B, h * up, w * up, transform.out_channels), np.float32) if return_out else None
+    check(fn(self._native.handle, xt.byref(), gt.byref(), as_tensor(gin, self._ctx.device).byref(),
+             as_tensor(out, self._ctx.device).byref() if return_out else None, None))
+    self._ctx.sync()
+    return (gin, out) if return_out else gin
+
+  def synthesis_vjp(self, y_hat, grad_out, return_out=False):
+    """J^T grad_out of self._synthesis at y_hat: grad_out is d loss / d synthesis(y_hat) on the full padded grid [B, Hp, Wp, 3]
+    (zeros where unpad_images cropped, mshyper/models.py:297-298); returns d loss / d y_hat [B, hy, wy, Cy] (and the forward output)."""
+    return self._vjp_call(lib.sntc_synthesis_vjp, self._synthesis, y_hat, grad_out, return_out)
+
+  def hyper_synthesis_vjp(self, z_hat, grad_out, return_out=False):
+    """J^T grad_out of self._hyper_synthesis at z_hat: grad_out [B, hy, wy, 2*Cy] = d loss / d (mu || raw sigma) (mshyper/models.py:273-275)."""
+    return self._vjp_call(lib.sntc_hyper_synthesis_vjp, self._hyper_synthesis, z_hat, grad_out, return_out)
 
 
 class FactorizedModel(Model):

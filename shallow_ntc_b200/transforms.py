@@ -101,7 +101,7 @@ class Transform:
     self._model = None
 
   # -- standalone call --------------------------------------------------------------------------
-  def _bind(self, cin, device=0):
+  def _bind(self, cin, device=0, vjp=False):
     from .tensors import Context
     from .models import _create_model
     if self.in_channels is None:
@@ -110,7 +110,8 @@ class Transform:
       self._ctx = Context(device)
     hyper = self.desc(self.in_channels) if self.role == "hyper_synthesis" else TransformDesc(kind=_lib.T_NONE)
     syn = self.desc(self.in_channels) if self.role == "synthesis" else TransformDesc(kind=_lib.T_NONE)
-    self._model = _create_model(self._ctx, hyper, syn, self._weights, precision=self.precision)
+    self._model = _create_model(self._ctx, hyper, syn, self._weights, precision=self.precision, vjp=vjp)
+    self._has_vjp = vjp
 
   def __call__(self, x, training=None):
     from .tensors import as_tensor, empty_like_kind
@@ -125,6 +126,20 @@ class Transform:
     check(fn(self._model.handle, xr.byref(), outr.byref(), None))
     self._ctx.sync()
     return out
+
+  def vjp(self, x, grad_out):
+    """J(x)^T grad_out: what ``tape.gradient`` propagates through ``layer(x)`` (the iterative-inference step of the reference,
+    ``mshyper/models.py:401-408``).  ``grad_out`` has the shape of ``layer(x)``; returns an array of the shape of ``x``.
+    The body of a ``tf.custom_gradient`` around ``__call__``."""
+    from .tensors import as_tensor, empty_like_kind
+    xr = as_tensor(x)
+    if self._model is None or not getattr(self, "_has_vjp", False):   # the backward layers are packed on first use
+      self._bind(xr.shape[-1], vjp=True)
+    gin = empty_like_kind(self._ctx, x if not hasattr(x, "__dlpack__") or isinstance(x, np.ndarray) else None, tuple(xr.shape), np.float32)
+    fn = lib.sntc_hyper_synthesis_vjp if self.role == "hyper_synthesis" else lib.sntc_synthesis_vjp
+    check(fn(self._model.handle, xr.byref(), as_tensor(grad_out).byref(), as_tensor(gin).byref(), None, None))
+    self._ctx.sync()
+    return gin
 
 
 # ---------------------------------------------------------------------------------------------

@@ -76,3 +76,89 @@ def test_conv_transpose_input_grad_geometries():
     y = O.conv_transpose_scatter(x, w, None, s, p)
     gx = O.conv_transpose_input_grad(g, w, s, p)
     assert abs(float((g * y).sum()) - float((gx * x).sum())) < 1e-9
+
+
+# --------------------------------------------------------------------------------------------------
+# -m gpu: libsntc's decoder backward against the autograd oracle
+
+GPU_CASES = [   # (class, ctor kwargs, input channels, latent h x w, batch)
+  ("HyperSynthesis", dict(bottleneck_size=64), 64, (5, 7), 2),
+  ("HyperSynthesis", dict(bottleneck_size=64, activation_type="leaky_relu"), 64, (4, 3), 1),
+  ("JPEGLikeHyperSynthesis", dict(bottleneck_size=32), 64, (3, 5), 2),
+  ("HyperSynthesisSmall", dict(bottleneck_size=64), 64, (6, 5), 1),
+  ("JPEGLikeSynthesis", dict(kernel_size=18, strides=16), 64, (3, 4), 2),
+  ("JPEGLikeSynthesis", dict(kernel_size=18, strides=16, use_offset=True, use_bias=False), 64, (2, 3), 1),
+  ("TwoLayerSynthesis", dict(channels=(12, 3)), 64, (3, 4), 2),
+  ("TwoLayerSynthesis", dict(channels=(24, 3), activation_type="relu"), 64, (2, 3), 1),
+  ("TwoLayerSynthesis", dict(channels=(12, 3), activation_type="gdn"), 64, (2, 3), 1),
+  ("TwoLayerResSynthesis", dict(channels=(12, 3)), 64, (4, 3), 2),
+  ("TwoLayerResSynthesis", dict(channels=(12, 3), activation_type="leaky_relu"), 64, (2, 2), 1),
+  ("MBT2018Synthesis", dict(channels_base=96), 64, (3, 4), 1),
+  ("BLS2017Synthesis", dict(num_filters=128), 128, (3, 2), 1),
+  ("CNNSynthesis", dict(channels_base=64, activation_type="igdn"), 64, (2, 3), 1),
+  ("CNNSynthesis", dict(channels_base=64), 64, (2, 2), 2),
+]
+
+
+def _rel(a, b):
+  return float(np.abs(a - b).max() / max(1e-30, np.abs(b).max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+@pytest.mark.parametrize("cls,kw,cin,hw,B", GPU_CASES)
+def test_transform_vjp_matches_autograd(gpu_ctx, cls, kw, cin, hw, B, precision):
+  """Transform.vjp (sntc_synthesis_vjp / sntc_hyper_synthesis_vjp through the C ABI) == J^T g of the float64 autograd oracle:
+  every registry class, fp32 band GEMMs and the tcgen05 band GEMMs of the tensor-core precision."""
+  t, wts, x, g, okw = small_case(cls, kw, cin, hw, B=B)
+  t._ctx = gpu_ctx
+  t.precision = precision
+  t.load_weights(wts)
+  x32, g32 = x.astype(np.float32), g.astype(np.float32)
+  before = gpu_ctx.launch_counts
+  gin = t.vjp(x32, g32)
+  after = gpu_ctx.launch_counts
+  out, want = V.transform_vjp(cls, wts, x32.astype(np.float64), g32.astype(np.float64), okw)
+  assert gin.shape == x.shape and gin.dtype == np.float32
+  err = _rel(gin, want)
+  tol = 2e-5 if precision == "fp32" else 1e-4     # relative to max |grad|; the split-fp16 product carries ~2^-22 per MAC
+  assert err < tol, (cls, precision, err)
+  if precision == "tc":   # the wide backward layers (s*s*Cout >= 64 input channels) must have run on the tensor cores
+    assert after["band_tc"] > before["band_tc"], (before, after)
+  else:
+    assert after["band_tc"] == before["band_tc"]
+  # the forward value of the same pass
+  fwd = t(x32)
+  assert _rel(fwd, out) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_model_decoder_vjp_headline_shapes(gpu_ctx, precision):
+  """Model(vjp=True).synthesis_vjp / hyper_synthesis_vjp on the headline architecture (two_layer_syn, 320 channels) for one
+  128 x 192 image: the two heavy pieces of tape.gradient in itinf_train_step (mshyper/models.py:401-408)."""
+  from shallow_ntc_b200 import build_config
+  model = build_config("two_layer_syn", precision=precision, ctx=gpu_ctx, vjp=True)
+  cfg = model._transform_config["synthesis"]
+  wts = synthetic.make_weights(model.variable_shapes(), "stress", synthesis_cls=cfg["cls"])
+  model.load_weights(wts)
+  H, W = 128, 192
+  zs, ys = model.latent_shapes(1, H, W)
+  rng = np.random.default_rng(2)
+  y = (rng.standard_normal(ys) * 2).astype(np.float32)
+  z = np.rint(rng.standard_normal(zs) * 1.5).astype(np.float32)
+  gx = rng.standard_normal((1, H, W, 3)).astype(np.float32)
+  gh = rng.standard_normal((1, ys[1], ys[2], 2 * ys[3])).astype(np.float32)
+  gy, out = model.synthesis_vjp(y, gx, return_out=True)
+  kw = {k: v for k, v in cfg.items() if k not in ("cls", "channels", "kernel_sizes")}
+  o_ref, gy_ref = V.transform_vjp(cfg["cls"], wts, y.astype(np.float64), gx.astype(np.float64), kw)
+  tol = 2e-5 if precision == "fp32" else 1e-4
+  assert _rel(gy, gy_ref) < tol and _rel(out, o_ref) < 2e-5, (_rel(gy, gy_ref), _rel(out, o_ref))
+  gz = model.hyper_synthesis_vjp(z, gh)
+  _, gz_ref = V.transform_vjp("HyperSynthesis", wts, z.astype(np.float64), gh.astype(np.float64), {})
+  assert _rel(gz, gz_ref) < tol, _rel(gz, gz_ref)
+  # a model built without vjp=True refuses loudly
+  plain = build_config("two_layer_syn", precision=precision, ctx=gpu_ctx)
+  plain.load_weights(wts)
+  with pytest.raises(RuntimeError):
+    plain.synthesis_vjp(y, gx)
