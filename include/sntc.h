@@ -203,9 +203,10 @@ int sntc_synthesis(sntc_model* m, const sntc_tensor* y_hat, sntc_tensor* out, vo
  * reaches the latents through self._hyper_synthesis(z) (:273) and self._synthesis(y, training=True) (:297).  These two calls are
  * the vector-Jacobian products a tf.custom_gradient around the transform-level calls above returns:
  *   grad_in [B,h,w,Cin] = J_f(x)^T grad_out,   grad_out [B, h*up, w*up, Cout] = d loss / d f(x) on the FULL (padded) output grid
- *   (zeros where unpad_images cropped).  `out` (nullable) receives f(x) of the same pass (fp32 kernels).
- * The input-gradient of every transposed conv runs as a forward stride-1 band GEMM on a space-to-depth of the gradient (tcgen05
- * for models created with a tensor-core precision); GDN1 / relu / leaky_relu adjoints are pointwise kernels.
+ *   (zeros where unpad_images cropped).  `out` (nullable) receives f(x) of the same pass.
+ * The input-gradient of every transposed conv runs as a forward stride-1 band GEMM on a space-to-depth of the gradient; for models
+ * created with a tensor-core precision both the forward layers and these backward layers run on tcgen05 (fp32 results kept for the
+ * adjoints); GDN1 / relu / leaky_relu adjoints are pointwise kernels.
  * sntc_model_enable_vjp(m, 1) must precede sntc_model_finalize (the backward layers are packed from the host weights);
  * TwoLayerResSynthesis(res_type="d2s") has no backward (SNTC_E_UNSUPPORTED). */
 int sntc_model_enable_vjp(sntc_model* m, int on);

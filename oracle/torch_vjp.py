@@ -16,11 +16,11 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-DT = torch.float64
+NP_DT = np.float64     # tools/vjp_bench.py times the float32 version as the CPU stand-in
 
 
 def _t(a):
-  return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+  return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=NP_DT)))
 
 
 def _nchw(x):

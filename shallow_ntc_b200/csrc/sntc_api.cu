@@ -1234,9 +1234,12 @@ static int launch_act_bwd(sntc_ctx* ctx, const ActBwdParams& P, cudaStream_t s) 
   return SNTC_OK;
 }
 
-static int vjp_run(sntc_model* m, VjpPlan& P, const float* x, const float* gout, float* gin, float* out, int B, int h, int w, cudaStream_t s) {
+static int vjp_run(sntc_model* m, VjpPlan& P, bool is_hyper, const float* x, const float* gout, float* gin, float* out, int B, int h, int w, cudaStream_t s) {
   sntc_ctx* ctx = m->ctx;
   Transform& t = P.fwd;
+  // forward layers that the model itself runs on the tensor cores do so here too (same packed weights, fp32 result kept)
+  Transform& mt = is_hyper ? m->hyper : m->syn;
+  std::vector<TcConv>& ftc = is_hyper ? m->tc.hyper : m->tc.syn;
   const size_t nops = t.ops.size();
   if (P.acts.size() < nops) P.acts.resize(nops);
   std::vector<int> ih(nops), iw(nops), ic(nops);
@@ -1259,7 +1262,28 @@ static int vjp_run(sntc_model* m, VjpPlan& P, const float* x, const float* gout,
       }
       TRY(P.acts[i].ensure((size_t)B * ch * c.s * cw * c.s * c.cout * 4));
       ProfScope ps(m, s, "vjp.forward." + c.sources[0].kernel.substr(0, c.sources[0].kernel.size() - 7), conv_macs(c, B, ch, cw));
-      TRY(run_conv_f32(ctx, c, in, B, ch, cw, (float*)P.acts[i].p, nullptr, s));
+      if (is_tc(m->desc.precision) && op.conv < (int)ftc.size() && ftc[op.conv].ok && !c.append_ones) {
+        const size_t n = (size_t)B * ch * cw * c.cin;
+        TRY(P.pl[0].ensure(n * 2)); TRY(P.pl[1].ensure(n * 2));
+        split_planes_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, s>>>(in, (__half*)P.pl[0].p, (__half*)P.pl[1].p, n / 8, nullptr);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        TcConvOut o;
+        o.f32 = (float*)P.acts[i].p;
+        std::string err;
+        if (tc_run_conv(ctx->tc, mt.convs[op.conv], ftc[op.conv], (const __half*)P.pl[0].p, (const __half*)P.pl[1].p, B, ch, cw, o, s, &ctx->launches, &err) != TC_OK)
+          return fail(SNTC_E_CUDA, "vjp forward (tensor-core path): " + err);
+        ctx->kinds[SNTC_LAUNCH_BAND_TC]++;
+      } else if (is_tc(m->desc.precision) && !is_hyper && op.conv < (int)m->tail_tz.size() && m->tail_tz[op.conv].ok) {
+        TailTzOut to;                     // the two-layer tail (12 -> 3 channels): window-GEMM tcgen05 kernel, fp32 output
+        to.f32 = (float*)P.acts[i].p;
+        std::string err;
+        if (tail_tz_run(ctx->tc, mt.convs[op.conv], m->tail_tz[op.conv], in, B, ch, cw, to, false, s, &ctx->launches, &err, true) != 0)
+          return fail(SNTC_E_CUDA, "vjp forward (window-GEMM tail): " + err);
+        ctx->kinds[SNTC_LAUNCH_TAIL_TC]++;
+      } else {
+        TRY(run_conv_f32(ctx, c, in, B, ch, cw, (float*)P.acts[i].p, nullptr, s));
+      }
       ch *= c.s; cw *= c.s; cc = c.cout;
     } else if (op.type == OP_GDN) {
       const GdnLayer& g = t.gdns[op.gdn];
@@ -1371,7 +1395,7 @@ static int vjp_entry(sntc_model* m, bool is_hyper, const sntc_tensor* x, const s
   TRY(stage_in(m, grad_out, tensor_elems(grad_out) * 4, P.st_g, s, &dg));
   TRY(stage_out(m, grad_in, tensor_elems(grad_in) * 4, P.st_gin, &dgin));
   if (out) TRY(stage_out(m, out, tensor_elems(out) * 4, P.st_out, &dout));
-  TRY(vjp_run(m, P, (const float*)dx, (const float*)dg, (float*)dgin, (float*)dout, B, h, w, s));
+  TRY(vjp_run(m, P, is_hyper, (const float*)dx, (const float*)dg, (float*)dgin, (float*)dout, B, h, w, s));
   TRY(unstage_out(grad_in, tensor_elems(grad_in) * 4, dgin, s, &need_sync));
   if (out) TRY(unstage_out(out, tensor_elems(out) * 4, dout, s, &need_sync));
   if (need_sync) CU_TRY(cudaStreamSynchronize(s));

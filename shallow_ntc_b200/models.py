@@ -380,7 +380,7 @@ class Model:
   # ---------------------------------------------------------------------------------------------
   # decoder backward: what tape.gradient propagates through the two transforms in itinf_train_step
   # (mshyper/models.py:401-408).  Model(..., vjp=True).
-  def _vjp_call(self, fn, transform, x, grad_out, return_out):
+  def _vjp_call(self, fn, transform, x, grad_out, return_out, grad_in=None, sync=True):
     if not self._vjp:
       raise RuntimeError("construct the model with vjp=True to use the decoder backward")
     self._ensure_native()
@@ -388,21 +388,22 @@ class Model:
     B, h, w, _ = xt.shape
     up = transform.upsample
     gt = as_tensor(grad_out, self._ctx.device)
-    gin = empty_like_kind(self._ctx, x, tuple(xt.shape), np.float32)
+    gin = grad_in if grad_in is not None else empty_like_kind(self._ctx, x, tuple(xt.shape), np.float32)
     out = empty_like_kind(self._ctx, x, (B, h * up, w * up, transform.out_channels), np.float32) if return_out else None
     check(fn(self._native.handle, xt.byref(), gt.byref(), as_tensor(gin, self._ctx.device).byref(),
              as_tensor(out, self._ctx.device).byref() if return_out else None, None))
-    self._ctx.sync()
+    if sync:
+      self._ctx.sync()
     return (gin, out) if return_out else gin
 
-  def synthesis_vjp(self, y_hat, grad_out, return_out=False):
+  def synthesis_vjp(self, y_hat, grad_out, return_out=False, **kw):
     """J^T grad_out of self._synthesis at y_hat: grad_out is d loss / d synthesis(y_hat) on the full padded grid [B, Hp, Wp, 3]
     (zeros where unpad_images cropped, mshyper/models.py:297-298); returns d loss / d y_hat [B, hy, wy, Cy] (and the forward output)."""
-    return self._vjp_call(lib.sntc_synthesis_vjp, self._synthesis, y_hat, grad_out, return_out)
+    return self._vjp_call(lib.sntc_synthesis_vjp, self._synthesis, y_hat, grad_out, return_out, **kw)
 
-  def hyper_synthesis_vjp(self, z_hat, grad_out, return_out=False):
+  def hyper_synthesis_vjp(self, z_hat, grad_out, return_out=False, **kw):
     """J^T grad_out of self._hyper_synthesis at z_hat: grad_out [B, hy, wy, 2*Cy] = d loss / d (mu || raw sigma) (mshyper/models.py:273-275)."""
-    return self._vjp_call(lib.sntc_hyper_synthesis_vjp, self._hyper_synthesis, z_hat, grad_out, return_out)
+    return self._vjp_call(lib.sntc_hyper_synthesis_vjp, self._hyper_synthesis, z_hat, grad_out, return_out, **kw)
 
 
 class FactorizedModel(Model):

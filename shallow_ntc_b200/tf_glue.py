@@ -10,6 +10,8 @@ dependency; TF 2.10 is not installable in the build container, so everything her
   * ``b200_model_from(tf_model, model_config)``  one call: config dict + weights -> ``shallow_ntc_b200.Model``
   * ``from_tf`` / ``to_tf``          zero-copy tensor hand-off through DLPack capsules (``tf.experimental.dlpack``)
   * ``evaluate_like_reference``      ``Model.evaluate`` (``mshyper/models.py:415-433``) with the decode half on the GPU path
+  * ``differentiable(layer)``        ``tf.custom_gradient`` around a B200 transform (forward ``layer(x)``, backward ``layer.vjp``):
+                                     keeps the ``GradientTape`` of ``itinf_train_step`` (``mshyper/models.py:401-408``) working
 
 Variable conventions (always the EFFECTIVE, de-reparameterised values): Keras ``Conv2DTranspose.kernel`` [kh,kw,Cout,Cin],
 tfc ``SignalConv2D.kernel`` [kh,kw,Cin,Cout] (the spatial-domain kernel property, not the RDFT variable), ``GDN.beta`` [C],
@@ -165,6 +167,30 @@ def to_tf(arr):
   """DeviceArray / DeviceView / numpy produced by the decode -> tf.Tensor, zero-copy."""
   from .tensors import to_dlpack
   return _tf().experimental.dlpack.from_dlpack(to_dlpack(arr))
+
+
+def differentiable(layer, tf=None):
+  """``tf.custom_gradient`` around a B200 transform: forward ``layer(x)``, gradient ``layer.vjp(x, dy)`` (libsntc's
+  ``sntc_synthesis_vjp`` / ``sntc_hyper_synthesis_vjp``).  With the two transforms of a model wrapped like this,
+  ``itinf_train_step`` (``mshyper/models.py:401-408``: ``tape.gradient(loss, latent_rvs.trainable_variables)`` through
+  ``frame_loss_given_latent_rvs(..., training=True)``) runs unchanged -- the rate terms, ``sga_round`` and the optimizer stay
+  TensorFlow, the decoder forward and backward run on the GPU path.  Eager mode (what ``itinf.py`` uses); inside a
+  ``tf.function`` wrap the returned callable in ``tf.py_function``.  ``tf`` is injectable for the stand-in tests."""
+  tf = tf or _tf()
+
+  @tf.custom_gradient
+  def call(x):
+    xn = _np(x)
+    y = layer(xn)
+
+    def grad(dy):
+      return tf.convert_to_tensor(layer.vjp(xn, _np(dy)))
+    return tf.convert_to_tensor(y), grad
+
+  def wrapped(x, training=None):     # the reference calls self._synthesis(y, training=training) and self._hyper_synthesis(z)
+    return call(x)
+  wrapped.__wrapped__ = layer
+  return wrapped
 
 
 def symbols_of(tf_model, image):

@@ -182,3 +182,38 @@ def test_dlpack_export_is_zero_copy_and_owns_its_producer():
   del r, cap
   gc.collect()
   assert len(_DL_LIVE) == n0
+
+
+def test_differentiable_wraps_forward_and_vjp_in_a_custom_gradient():
+  """tf_glue.differentiable: forward = layer(x), gradient = layer.vjp(x, dy) (itinf_train_step, mshyper/models.py:401-408),
+  with a stand-in for the two TensorFlow entry points it touches."""
+  seen = {}
+
+  class FakeTf:
+    @staticmethod
+    def custom_gradient(fn):
+      def run(x):
+        y, g = fn(x)
+        seen["grad"] = g
+        return y
+      return run
+
+    @staticmethod
+    def convert_to_tensor(a):
+      return np.asarray(a)
+
+  class Layer:
+    def __call__(self, x, training=None):
+      return 2.0 * x
+
+    def vjp(self, x, dy):
+      seen["vjp_x"] = x
+      return 2.0 * dy
+
+  f = tf_glue.differentiable(Layer(), tf=FakeTf)
+  x = np.arange(6, dtype=np.float32).reshape(1, 1, 2, 3)
+  y = f(x, training=True)
+  assert np.array_equal(y, 2 * x)
+  dy = np.ones_like(x)
+  assert np.array_equal(seen["grad"](dy), 2 * dy) and np.array_equal(seen["vjp_x"], x)
+  assert isinstance(f.__wrapped__, Layer)

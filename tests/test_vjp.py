@@ -153,7 +153,7 @@ def test_model_decoder_vjp_headline_shapes(gpu_ctx, precision):
   kw = {k: v for k, v in cfg.items() if k not in ("cls", "channels", "kernel_sizes")}
   o_ref, gy_ref = V.transform_vjp(cfg["cls"], wts, y.astype(np.float64), gx.astype(np.float64), kw)
   tol = 2e-5 if precision == "fp32" else 1e-4
-  assert _rel(gy, gy_ref) < tol and _rel(out, o_ref) < 2e-5, (_rel(gy, gy_ref), _rel(out, o_ref))
+  assert _rel(gy, gy_ref) < tol and _rel(out, o_ref) < tol, (_rel(gy, gy_ref), _rel(out, o_ref))
   gz = model.hyper_synthesis_vjp(z, gh)
   _, gz_ref = V.transform_vjp("HyperSynthesis", wts, z.astype(np.float64), gh.astype(np.float64), {})
   assert _rel(gz, gz_ref) < tol, _rel(gz, gz_ref)
