@@ -162,3 +162,43 @@ def test_model_decoder_vjp_headline_shapes(gpu_ctx, precision):
   plain.load_weights(wts)
   with pytest.raises(RuntimeError):
     plain.synthesis_vjp(y, gx)
+
+
+@pytest.mark.gpu
+def test_vjp_error_behaviour(gpu_ctx):
+  """Loud failures, never a silent fallback: no backward plan without sntc_model_enable_vjp, none for res_type='d2s', shapes
+  are validated, an empty batch is a no-op; device-resident tensors give the same gradient as host tensors."""
+  from shallow_ntc_b200 import Model, SntcError, _lib
+  from shallow_ntc_b200._lib import lib
+  from shallow_ntc_b200.tensors import as_tensor
+  elic = dict(cls="ElicAnalysis", channels=(192, 192, 192, 64))
+  syn = dict(cls="TwoLayerResSynthesis", channels=(12, 3), strides=(8, 2), kernel_sizes=(13, 5), activation_type="igdn")
+  rng = np.random.default_rng(4)
+
+  def build(syn_cfg, **kw):
+    m = Model(dict(analysis=elic, synthesis=syn_cfg), precision="fp32", ctx=gpu_ctx, **kw)
+    m.load_weights(synthetic.make_weights(m.variable_shapes(), "stress", synthesis_cls="TwoLayerResSynthesis"))
+    return m
+  y = rng.standard_normal((1, 2, 3, 64)).astype(np.float32)
+  g = rng.standard_normal((1, 32, 48, 3)).astype(np.float32)
+  # C level: a finalized model without the plan
+  plain = build(syn)
+  plain._ensure_native()
+  gin = np.empty_like(y)
+  rc = lib.sntc_synthesis_vjp(plain._native.handle, as_tensor(y).byref(), as_tensor(g).byref(), as_tensor(gin).byref(), None, None)
+  assert rc == -3 and b"sntc_model_enable_vjp" in lib.sntc_last_error()        # SNTC_E_STATE
+  assert lib.sntc_model_enable_vjp(plain._native.handle, 1) == -3                  # too late: the host weights are gone
+  # d2s has no backward
+  d2s = build(dict(syn, res_type="d2s"), vjp=True)
+  with pytest.raises(SntcError, match="d2s"):
+    d2s.synthesis_vjp(y, g)
+  m = build(syn, vjp=True)
+  with pytest.raises(SntcError, match="grad_out"):
+    m.synthesis_vjp(y, np.ascontiguousarray(g[:, :16]))
+  with pytest.raises(SntcError, match="channel"):
+    m.synthesis_vjp(np.ascontiguousarray(y[..., :32]), g)
+  empty = m.synthesis_vjp(y[:0], g[:0])
+  assert empty.shape == (0, 2, 3, 64)
+  host = m.synthesis_vjp(y, g)
+  dev = m.synthesis_vjp(gpu_ctx.to_device(y), gpu_ctx.to_device(g))
+  assert np.array_equal(host, dev.to_host())

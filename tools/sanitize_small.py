@@ -41,3 +41,22 @@ for hcfg in (dict(cls="JPEGLikeHyperSynthesis", bottleneck_size=320, kernel_size
   print(hcfg["cls"], "ok", flush=True)
 b = np.clip(a.astype(int) + 9, 0, 255).astype(np.uint8)
 print("lpips", L.Lpips(ctx, L.random_weights())(np.ascontiguousarray(a[:, :64, :80]), np.ascontiguousarray(b[:, :64, :80])))
+# round 2, later: TwoLayerResSynthesis(res_type="d2s") and the decoder backward (forward + backward of both transforms, fp32 and tc)
+cfg = dict(analysis=dict(cls="ElicAnalysis", channels=(192, 192, 192, 320)),
+           synthesis=dict(cls="TwoLayerResSynthesis", channels=(12, 3), strides=(8, 2), kernel_sizes=(13, 5), activation_type="igdn", res_type="d2s"))
+md = Model(cfg, precision="tc", ctx=ctx)
+md.load_weights(synthetic.make_weights(md.variable_shapes(), "stress", synthesis_cls="TwoLayerResSynthesis"))
+zs, ys = md.latent_shapes(1, 70, 90)
+z, q = synthetic.make_latents(zs, ys)
+md.decompress(z, q, (70, 90))
+print("d2s ok", flush=True)
+rng = np.random.default_rng(1)
+for name, prec in (("two_layer_syn", "tc"), ("two_layer_syn", "fp32"), ("mbt2018", "tc"), ("bls2017", "tc")):
+  mv = build_config(name, precision=prec, ctx=ctx, vjp=True)
+  mv.load_weights(synthetic.make_weights(mv.variable_shapes(), "stress", synthesis_cls=mv._transform_config["synthesis"]["cls"]))
+  zs, ys = mv.latent_shapes(1, 64, 80)
+  up = mv._synthesis.upsample
+  gy = mv.synthesis_vjp(rng.standard_normal(ys).astype(np.float32), rng.standard_normal((1, ys[1] * up, ys[2] * up, 3)).astype(np.float32))
+  if zs is not None:
+    mv.hyper_synthesis_vjp(rng.standard_normal(zs).astype(np.float32), rng.standard_normal((1, ys[1], ys[2], 2 * ys[3])).astype(np.float32))
+  print("vjp", name, prec, "ok", float(np.abs(gy).max()), flush=True)
