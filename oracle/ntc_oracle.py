@@ -4,14 +4,21 @@ This module is the checker, never the product: only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
 reference`` legs may import it.  ``shallow_ntc_b200`` never does.
 
-PARITY UNPINNED at the TensorFlow / tensorflow-compression boundary: the
-reference (mandt-lab/shallow-ntc) has no tests or golden vectors for this path
+PARITY UNPINNED at the TensorFlow / tensorflow-compression boundary, with two exceptions
+listed first below: the reference (mandt-lab/shallow-ntc) has no tests for this path
 and its arithmetic lives in third-party packages that are absent from
 ``/root/reference`` and cannot be installed offline (``requirements.txt:6-9``:
 tensorflow==2.10.0, tensorflow_compression==2.10.0,
 tensorflow_probability==0.18.0).  What IS pinned, and checked in
 ``tests/test_oracle.py``:
 
+* OUTPUTS THE REFERENCE ITSELF RECORDED: (i) the PNG images embedded in the output cells of
+  ``notebooks/vis_syn_filters.ipynb`` (real TF-2.10 runs of the trained jpegl model; extracted by
+  ``tests/golden/make_golden_notebook.py`` into ``tests/golden/notebook_jpegl_responses.npz``): the response of one active latent
+  pixel covers rows / columns 0..16 of the 2 x 2-latent image in all 100 recorded channels, on a constant background -- this
+  pins the alignment of A1 for Keras ``Conv2DTranspose(18, 16, 'SAME')`` (p = 1; p = 0 or 2 contradict the recording) and that
+  the 1 x 1 and 2 x 2 latent grids show the same kernel taps; (ii) LPIPS: the values ``lpips_tf2/test.py:17-19`` records for the
+  image pairs it ships (``tests/test_lpips.py``);
 * the reference's own structural known-answers (``results/all_params.csv``,
   ``results/flops_per_pixel.csv``, ``notebooks/get_flops.ipynb``): parameter
   counts, FLOPs/pixel and tensor shapes of every transform restated here;

@@ -110,6 +110,30 @@ def test_jpegl_linearity(gpu_ctx):
   assert nz[:, 0].min() >= 15 and nz[:, 0].max() <= 32 and nz[:, 1].min() >= 31 and nz[:, 1].max() <= 48
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_single_pixel_response_matches_what_the_reference_recorded(gpu_ctx, precision):
+  """REFERENCE-HELD fixture (tests/golden/notebook_jpegl_responses.npz, made from the PNG outputs embedded in
+  notebooks/vis_syn_filters.ipynb cell 44: real TF-2.10 runs of the trained jpegl model): one active latent pixel at (0, 0) of a 2 x 2
+  grid gives a response on rows / columns 0..16 of the 32 x 32 image and one constant pixel value elsewhere.  The CUDA path, same
+  experiment through floats_to_pixels: identical support, constant background."""
+  import os
+  from shallow_ntc_b200 import synthetic
+  ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "notebook_jpegl_responses.npz"))["cell44"].astype(int)
+  mask_ref = (ref != ref[:, -1:, -1:, :]).any(-1).any(0)
+  model, wts, z, q = make_case("jpegl", 1, 32, 32, "stress", precision, gpu_ctx)
+  rng = np.random.default_rng(0)
+  wts = dict(wts)
+  wts["synthesis.conv.kernel"] = (0.002 * (rng.standard_normal(wts["synthesis.conv.kernel"].shape) + 3.0)).astype(np.float32)   # no zero taps
+  model.load_weights(wts)
+  e = np.zeros((1, 2, 2, 320), np.float32)
+  e[0, 0, 0, 7] = 30.0
+  x = model.synthesis(e)[0]
+  px = np.clip(np.rint((x + 0.5) * 255.0), 0, 255).astype(int)                      # data_lib.floats_to_pixels
+  bg = px[-1, -1]
+  assert np.array_equal((px != bg).any(-1), mask_ref)
+  assert np.array_equal(bg, np.clip(np.rint((wts["synthesis.conv.bias"] + 0.5) * 255.0), 0, 255).astype(int))
+
+
 def test_argument_errors_are_loud(gpu_ctx):
   from shallow_ntc_b200 import SntcError
   model, wts, z, q = make_case("two_layer_syn", 1, 64, 64, "init", "fp32", gpu_ctx)

@@ -136,6 +136,43 @@ def test_linearity_and_single_pixel_support():
   assert nz.max() <= 16     # 18x18 patch starting at -1: rows/cols 0..16 survive the SAME crop
 
 
+def test_conv_transpose_alignment_matches_outputs_the_reference_recorded():
+  """REFERENCE-HELD fixture (tests/golden/make_golden_notebook.py): the PNG outputs embedded in notebooks/vis_syn_filters.ipynb, real
+  TF-2.10 runs of the trained jpegl model (JPEGLikeSynthesis(kernel_size=18, strides=16)).  Cell 44: one active latent pixel at (0, 0)
+  of a 2 x 2 grid -> the response covers rows / columns 0..16 in all 100 recorded channels, on a constant background.  That is
+  Conv2DTranspose(padding='SAME') with p = max(k - s, 0) // 2 = 1 (assumption A1 of the oracle); p = 0 would give 0..17, p = 2 0..15."""
+  import os
+  d = np.load(os.path.join(os.path.dirname(__file__), "golden", "notebook_jpegl_responses.npz"))
+  c44, c41 = d["cell44"].astype(int), d["cell41"].astype(int)
+  assert c44.shape == (100, 32, 32, 3) and c41.shape == (100, 16, 16, 3)
+  bg = c44[:, -1:, -1:, :]
+  mask_ref = (c44 != bg).any(-1)                                   # [100, 32, 32]
+  assert not mask_ref[:, 17:, :].any() and not mask_ref[:, :, 17:].any()          # nothing beyond row / column 16
+  assert mask_ref[:, 16, :17].any(-1).all() and mask_ref[:, :17, 16].any(-1).all()   # and row / column 16 IS touched, in every channel
+  assert len(np.unique(bg.reshape(-1, 3), axis=0)) == 1             # the background is one pixel value (floats_to_pixels of the bias)
+  # the 1 x 1 grid of cell 41 (response minus g0) shows the SAME kernel taps as the top-left 16 x 16 of cell 44: the two differ by a
+  # per-channel constant (255 * bias) up to the rounding of each, wherever neither saturates
+  diff = c44[:, :16, :16] - c41
+  free = (c44[:, :16, :16] > 0) & (c44[:, :16, :16] < 255) & (c41 > 0) & (c41 < 255)
+  for ch in range(3):
+    v = np.unique(diff[..., ch][free[..., ch]])
+    assert len(v) == 2 and v[1] - v[0] == 1, v
+  # the oracle, same experiment, dense random kernel: identical support; the neighbouring paddings do not reproduce it
+  m = build_config("jpegl")
+  w = synthetic.make_weights(m.variable_shapes(), "stress")
+  rng = np.random.default_rng(0)
+  w["synthesis.conv.kernel"] = (rng.standard_normal(w["synthesis.conv.kernel"].shape) + 3.0).astype(np.float32)   # no zero taps
+  e = np.zeros((1, 2, 2, 320)); e[0, 0, 0, 7] = 30.0
+  bias = np.asarray(w["synthesis.conv.bias"], np.float64)
+  mask = (O.jpeg_like_synthesis(w, e, strides=16)[0] != bias).any(-1)
+  assert np.array_equal(mask, mask_ref.any(0)) and all(np.array_equal(mask, mr) or not (mr & ~mask).any() for mr in mask_ref)
+  e1 = np.zeros((1, 1, 1, 320)); e1[0, 0, 0, 7] = 30.0
+  assert np.array_equal(O.jpeg_like_synthesis(w, e, strides=16)[0, :16, :16], O.jpeg_like_synthesis(w, e1, strides=16)[0])   # same taps
+  for p_wrong in (0, 2):
+    out = O.conv_transpose_scatter(e, w["synthesis.conv.kernel"], w["synthesis.conv.bias"], 16, p_wrong)
+    assert not np.array_equal((out[0] != bias).any(-1), mask_ref.any(0))
+
+
 # ---- tiers, glue, epilogue ---------------------------------------------------------------------
 def test_t1_float32_gemm_form_agrees_with_t0():
   m = build_config("two_layer_syn")
