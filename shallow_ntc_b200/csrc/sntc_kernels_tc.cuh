@@ -53,6 +53,7 @@ struct alignas(64) TcBandDev {
 
 struct TcParams {
   const TcBandDev* bands; int nbands; int total_items;
+  int snake;          // tc_unit_item: alternate the direction of successive waves (band-major order only)
   int ipg;            // > 0: items are m-tile-group major (item = group * ipg + slot, bands[].item_begin = first slot of the band:
                       // a unit walks through all bands, so heavy-MMA and heavy-epilogue items alternate); 0: band major
                       // (items of band i start at bands[i].item_begin * groups).  The band table itself never depends on the batch.
@@ -300,6 +301,14 @@ struct TcItem {
 };
 
 // CG = CTAs per work item (1, or 2 for a cta_group::2 pair).  Items of a band: (m-tile group, n-tile), n-tile fastest.
+// k-th work item of persistent unit `unit0`.  snake != 0: successive waves run in opposite directions -- the items are sorted
+// heaviest band first, so the unit that drew the heaviest item of one wave draws the lightest of the next (hyper layer 0 at
+// batch 24: 96 items on 74 units, longest unit 45 + 20 -> 30 + 20 k-blocks).  >= total_items: the unit is done (a partial wave
+// is the last one).  Which unit computes an item never changes its arithmetic.
+__device__ __forceinline__ int tc_unit_item(int unit0, int nunits, int k, int snake) {
+  return k * nunits + ((snake && (k & 1)) ? nunits - 1 - unit0 : unit0);
+}
+
 template <int CG>
 __device__ __forceinline__ TcItem tc_decode_item(const TcParams& P, int item, int rank) {
   TcItem it;
@@ -858,7 +867,9 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     // ===== TMA producer: the whole warp runs the (uniform) loop, one elected lane issues the copies.
     // Every CTA loads its own A tile and its own rows of W. =====
     uint32_t st = 0, ph = 0;   // smem ring position: runs across work items
-    for (int item = unit0; item < P.total_items; item += nunits) {
+    for (int kw = 0;; ++kw) {
+      const int item = tc_unit_item(unit0, nunits, kw, P.snake);
+      if (item >= P.total_items) break;
       const TcItem it = tc_decode_item<CG>(P, item, rank);
       const TcBandDev& bd = P.bands[it.band];
       const int Ty = bd.Ty, Tx = bd.Tx;
@@ -867,7 +878,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
       const uint32_t tx_bytes = (uint32_t)CG * ((use_alo ? 2u : 1u) * a_bytes + (use_blo ? 2u : 1u) * (uint32_t)wrows * 128);
       const int cx0 = bd.mlox + it.ix0, cy0 = bd.mloy + it.iy0;
       int kcol = 0;
-      const int jt = (item - unit0) / nunits;
+      const int jt = kw;
       long long* tr = (P.trace && leader && jt < TC_TRACE_ITEMS) ? P.trace + ((size_t)unit0 * TC_TRACE_ITEMS + jt) * 8 : nullptr;
       if (tr && lane == 0) { tr[0] = clock64(); tr[7] = item; }
       for (int jy = 0; jy < Ty; ++jy)
@@ -903,7 +914,9 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
       // descriptor = fixed high word | (smem address >> 4) in the low word; +2 per K=16 step inside the swizzle row
       const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       uint32_t st = 0, ph = 0, j = 0;
-      for (int item = unit0; item < P.total_items; item += nunits, ++j) {
+      for (;; ++j) {
+        const int item = tc_unit_item(unit0, nunits, (int)j, P.snake);
+        if (item >= P.total_items) break;
         const TcItem it = tc_decode_item<CG>(P, item, 0);
         const TcBandDev& bd = P.bands[it.band];
         const int ntaps = bd.Ty * bd.Tx;
@@ -961,7 +974,9 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     const int r = ew * 32 + lane;               // row of the tile = cell
     const float* sbias = sconst;
     uint32_t j = 0;
-    for (int item = unit0; item < P.total_items; item += nunits, ++j) {
+    for (;; ++j) {
+      const int item = tc_unit_item(unit0, nunits, (int)j, P.snake);
+      if (item >= P.total_items) break;
       const TcItem it = tc_decode_item<CG>(P, item, rank);
       const TcBandDev& bdg = P.bands[it.band];
       const TcBandRegs bd{bdg.N, bdg.nphx, bdg.phy0, bdg.phx0, bdg.oshift};
@@ -1513,6 +1528,8 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   int per_group = 0;
   for (auto& bd : bands) per_group += bd.ntiles;
   if (order_mode) P.ipg = per_group;
+  static const int snake_env = tc_env_int("SNTC_TC_SNAKE", 1);
+  P.snake = (!order_mode && snake_env) ? 1 : 0;
   const int item = per_group * groups;
   cudaError_t e = cudaSuccess;
   P.bands = d_bands; P.nbands = nbands; P.total_items = item;
