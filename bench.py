@@ -449,7 +449,8 @@ def main():
   # would otherwise sit between the kernels of the timed region
   model.profile_layers(True)
   tp0 = time.perf_counter()
-  for i in range(min(max(args.steps, 20), 50)):
+  prof_steps = min(max(args.steps, 20), 50)
+  for i in range(prof_steps):
     step_dev(i)
   ctx.sync()
   tp1 = time.perf_counter()
@@ -563,7 +564,8 @@ def main():
                 config=dict(workload=workload,
                             images_per_gpu=B, precision=precision, index_rounding=model.index_rounding,
                             l2="inputs rotate over %d distinct batches; per-step working set > 126 MB L2" % args.rotate,
-                            layers_ms={k: round(v["ms"] / max(v["n"], 1), 4) for k, v in prof.items()},
+                            layers_ms={k: round(v["ms"] / prof_steps, 4) for k, v in prof.items()},   # per step (a layer may take several launches)
+                            layer_launches_per_step={k: round(v["n"] / prof_steps, 2) for k, v in prof.items() if v["n"] != prof_steps},
                             launches_by_family=kinds,
                             mean_psnr_db=float(qsum[0] / qsum[4]), mean_bpp_synthetic=float((qsum[2] + qsum[3]) / qsum[4] / (H * W)),
                             ms_per_step_with_rate_term=ms_rd, host_enqueue_ms_per_step=round(host_ms, 4),
