@@ -311,7 +311,13 @@ static void mark_final_op(Transform& t, int precision) {
   if (c.cout <= 3 && maxN < 64 && (c.s == 1 || c.s == 2 || c.s == 4)) {
     // tensor-core precision and a TMA-addressable input (deep decoders: 192 / 256 channels): all s*s output residues of a
     // cell become ONE band (N = s*s*cout) of the tcgen05 band GEMM; SNTC_TC_FINAL=0 keeps the CUDA-core cell kernel
-    if (is_tc(precision) && tc_conv_supported(c) && c.s > 1 && tc_env_int("SNTC_TC_FINAL", 1)) finish_conv_merged(c);
+    // SNTC_TC_COL2IM (default 1): wide inputs take the col2im form instead (one 1x1 GEMM per input pixel + overlap-add epilogue)
+    if (is_tc(precision) && tc_conv_supported(c) && col2im_eligible(c) && tc_env_int("SNTC_TC_FINAL", 1) && tc_env_int("SNTC_TC_COL2IM", 1)) {
+      c.col2im = true;
+      c.c2i.clear();
+      c.c2i.push_back(make_col2im_conv(c));
+      c.c2i_kp = c.c2i[0].c2i_kp;
+    } else if (is_tc(precision) && tc_conv_supported(c) && c.s > 1 && tc_env_int("SNTC_TC_FINAL", 1)) finish_conv_merged(c);
     else last.type = OP_CONVT_RGB;
   }
 }
@@ -896,6 +902,14 @@ static bool gdn_on_tc(sntc_model* m, Transform& t, bool is_hyper, size_t i) {
   return op.type == OP_GDN && op.gdn < (int)m->tc.syn_gdn.size() && m->tc.syn_gdn[op.gdn].ok;
 }
 
+// tc_run_conv for a layer of a transform: a final layer in col2im form runs its 1x1 contraction with the overlap-add epilogue.
+static int run_tc_layer(sntc_ctx* ctx, const ConvLayer& c, TcConv& tcv, const __half* hi, const __half* lo, int B, int h, int w, TcConvOut o,
+                        cudaStream_t s, std::string* err) {
+  if (!c.col2im) return tc_run_conv(ctx->tc, c, tcv, hi, lo, B, h, w, o, s, &ctx->launches, err);
+  o.col2im = true; o.c2i_k = c.k; o.c2i_s = c.s; o.c2i_p = c.p; o.c2i_kp = c.c2i_kp; o.c2i_cout = c.cout; o.c2i_bias = c.d_bias;
+  return tc_run_conv(ctx->tc, c.c2i[0], tcv, hi, lo, B, h, w, o, s, &ctx->launches, err);
+}
+
 // Runs `t` on `cur` [B,h,w,Cin].  Conv layers run on the tensor cores when the model was created with
 // SNTC_PRECISION_TC_F16X3 (and the layer is TMA-addressable), otherwise on the fp32 CUDA-core kernels;
 // pointwise stages and the tiny final conv always run on CUDA cores.  Intermediates ping-pong in the
@@ -1074,7 +1088,7 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
           }
         }
         ProfScope ps(m, s, skip_next ? lbl + "+activation" : lbl, conv_macs(c, B, ch, cw));
-        if (tc_run_conv(ctx->tc, c, tcv, cur.hi, cur.lo, B, ch, cw, o, s, &ctx->launches, &err) != TC_OK)
+        if (run_tc_layer(ctx, c, tcv, cur.hi, cur.lo, B, ch, cw, o, s, &err) != TC_OK)
           return fail(SNTC_E_CUDA, "tensor-core path: " + err);
         ctx->kinds[SNTC_LAUNCH_BAND_TC]++;
         ch *= c.s; cw *= c.s; cc = c.cout;
@@ -1314,7 +1328,7 @@ static int vjp_run(sntc_model* m, VjpPlan& P, bool is_hyper, const float* x, con
         TcConvOut o;
         o.f32 = (float*)P.acts[i].p;
         std::string err;
-        if (tc_run_conv(ctx->tc, mt.convs[op.conv], ftc[op.conv], (const __half*)P.pl[0].p, (const __half*)P.pl[1].p, B, ch, cw, o, s, &ctx->launches, &err) != TC_OK)
+        if (run_tc_layer(ctx, mt.convs[op.conv], ftc[op.conv], (const __half*)P.pl[0].p, (const __half*)P.pl[1].p, B, ch, cw, o, s, &err) != TC_OK)
           return fail(SNTC_E_CUDA, "vjp forward (tensor-core path): " + err);
         ctx->kinds[SNTC_LAUNCH_BAND_TC]++;
       } else if (is_tc(m->desc.precision) && !is_hyper && op.conv < (int)m->tail_tz.size() && m->tail_tz[op.conv].ok) {

@@ -30,7 +30,7 @@
 namespace sntc {
 
 enum { TC_OK = 0, TC_NOT_HANDLED = 1, TC_ERROR = 2 };
-enum { TC_EPI_PLAIN = 0, TC_EPI_HYPER_FINAL = 1, TC_EPI_TWO_LAYER = 2 };
+enum { TC_EPI_PLAIN = 0, TC_EPI_HYPER_FINAL = 1, TC_EPI_TWO_LAYER = 2, TC_EPI_COL2IM = 3 };
 
 constexpr int TC_BM = 128;        // cells per tile (UMMA M)
 constexpr int TC_BK = 64;         // fp16 channels per k-block (128 bytes = one swizzle row)
@@ -59,6 +59,10 @@ struct TcParams {
                       // (items of band i start at bands[i].item_begin * groups).  The band table itself never depends on the batch.
   int B, hin, win, s, p;
   int TH, TW, tiles_y, tiles_x;
+  int tile_step_y, tile_step_x, tile_off;   // m-tile (ty, tx) starts at cell (ty * step_y + off, tx * step_x + off): TH / TW / 0, or overlapping tiles (col2im)
+  // TC_EPI_COL2IM (ConvLayer::col2im): the GEMM is the per-input-pixel contraction P[n, (g, a_y, a_x)] of a final layer ConvT(k, s, p) to
+  // c2i_cout channels, c2i_kp columns per channel; cout / bias below are those of the FINAL layer, hout = hin * s
+  int c2i_k, c2i_s, c2i_p, c2i_kp;
   int kblocks;        // 64-channel blocks per tap
   int last_kmma;      // MMAs (K=16 each) in the last block of a tap (1..4)
   int cout, bn_max, stages;
@@ -313,27 +317,31 @@ template <int CG>
 __device__ __forceinline__ TcItem tc_decode_item(const TcParams& P, int item, int rank) {
   TcItem it;
   int bi = 0, nt, mg;
+  // unsigned divisions (no sign fix-up code); the per-item decode matters for layers with short items (col2im final layer)
   if (P.ipg > 0) {
-    mg = item / P.ipg;
+    mg = (int)((unsigned)item / (unsigned)P.ipg);
     const int slot = item - mg * P.ipg;
     for (int i = 1; i < P.nbands; ++i)
       if (slot >= P.bands[i].item_begin) bi = i;
     nt = slot - P.bands[bi].item_begin;
+  } else if (P.nbands == 1 && P.bands[0].ntiles == 1) {
+    nt = 0; mg = item;
   } else {
     const int groups = (P.mtiles + CG - 1) / CG;
     for (int i = 1; i < P.nbands; ++i)
       if (item >= P.bands[i].item_begin * groups) bi = i;
-    const int local = item - P.bands[bi].item_begin * groups;
-    nt = local % P.bands[bi].ntiles; mg = local / P.bands[bi].ntiles;
+    const unsigned local = (unsigned)(item - P.bands[bi].item_begin * groups), ntl = (unsigned)P.bands[bi].ntiles;
+    mg = (int)(local / ntl); nt = (int)(local - (unsigned)mg * ntl);
   }
   const TcBandDev& bd = P.bands[bi];
   int mt = mg * CG + rank;
   it.dup = mt >= P.mtiles;
   if (it.dup) mt = P.mtiles - 1;
-  int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y;
+  const unsigned q1 = (unsigned)mt / (unsigned)P.tiles_x, bq = q1 / (unsigned)P.tiles_y;
+  const int tx = mt - (int)q1 * P.tiles_x, ty = (int)(q1 - bq * (unsigned)P.tiles_y);
   it.band = bi;
-  it.b = mt / (P.tiles_x * P.tiles_y);
-  it.iy0 = ty * P.TH; it.ix0 = tx * P.TW;
+  it.b = (int)bq;
+  it.iy0 = ty * P.tile_step_y + P.tile_off; it.ix0 = tx * P.tile_step_x + P.tile_off;
   it.n0 = nt * bd.BN;
   it.nrows = min(bd.BN, bd.N - it.n0);
   it.mma_n = (it.nrows + 15) & ~15;
@@ -803,6 +811,134 @@ __device__ __forceinline__ void tc_epi_two_layer_wide(const TcParams& P, const T
   }
 }
 
+// Gather phase of the col2im epilogue for compile-time (K, S, PD).  ROWS = false: one work item = (interior cell, channel) -> its S x S
+// output samples; every tap of the 3 x 3 neighbour cells is read exactly once and every validity test is a compile-time constant
+// (k5 s2: 25 loads + 25 adds -> 4 samples; 84 cells x 3 channels = 252 items on the 256 epilogue threads).  ROWS = true: one work
+// item = (cell, channel, output row phase fy) -> S samples (k9 s4, one channel per n-tile: 336 items instead of 84).
+template <int K, int S, int PD, bool ROWS>
+__device__ __forceinline__ void tc_c2i_gather(const TcParams& P, const TcItem& it, const float* sbias, const float* sP, int PS, int et) {
+  constexpr int KP = (K * K + 31) / 32 * 32;
+  constexpr int NR = ROWS ? S : 1;
+  if (it.dup) return;
+  const int G = it.nrows / KP, g0 = it.n0 / KP;
+  constexpr unsigned iw = 14;                    // col2im tiles are 8 x 16 cells (tc_run_conv): 6 x 14 interior
+  const int nwork = (P.TH - 2) * (int)iw * G * NR;
+  const size_t row_u8 = (size_t)P.W * P.cout, row_f32 = (size_t)P.wout * P.cout;
+  for (int wi = et; wi < nwork; wi += 32 * TC_EPI_WARPS) {
+    unsigned q = (unsigned)wi;
+    const int fy0 = ROWS ? (int)(q % S) : 0; if (ROWS) q /= S;
+    int g;
+    if (G == 3) { g = (int)(q % 3u); q /= 3u; } else if (G == 1) { g = 0; } else { g = (int)(q % (unsigned)G); q /= (unsigned)G; }
+    const int cx = 1 + (int)(q % iw), cy = 1 + (int)(q / iw);
+    const int my = it.iy0 + cy, mx = it.ix0 + cx;
+    if (my >= P.hin || mx >= P.win) continue;
+    const float* cell = sP + (size_t)(cy * P.TW + cx) * PS + g * KP;
+    float acc[ROWS ? 1 : S][S];
+#pragma unroll
+    for (int a = 0; a < (ROWS ? 1 : S); ++a)
+#pragma unroll
+      for (int b = 0; b < S; ++b) acc[a][b] = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const float* src = cell + (ptrdiff_t)(dy * P.TW + dx) * PS;
+#pragma unroll
+        for (int a = 0; a < (ROWS ? 1 : S); ++a) {
+          const int ay = (ROWS ? fy0 : a) + PD - S * dy;          // compile-time unless ROWS
+          if (ay < 0 || ay >= K) continue;
+#pragma unroll
+          for (int fx = 0; fx < S; ++fx) {
+            const int ax = fx + PD - S * dx;                        // compile-time
+            if (ax >= 0 && ax < K) acc[a][fx] += src[ay * K + ax];
+          }
+        }
+      }
+    }
+    const int co = g0 + g, oy0 = S * my + fy0, ox0 = S * mx;
+    const float bias = sbias[co];
+    float* of = P.out_f32 ? P.out_f32 + (((size_t)it.b * P.hout + oy0) * P.wout + ox0) * P.cout + co : nullptr;
+    const size_t qi = (((size_t)it.b * P.H + oy0) * P.W + ox0) * P.cout + co;
+#pragma unroll
+    for (int a = 0; a < (ROWS ? 1 : S); ++a) {
+#pragma unroll
+      for (int fx = 0; fx < S; ++fx) {
+        const float x = fmaf(acc[a][fx], P.inv_scale, bias);
+        if (of) of[a * row_f32 + (size_t)fx * P.cout] = x;
+        if ((P.out_u8 || P.out_crop) && oy0 + a < P.H && ox0 + fx < P.W) {
+          const size_t o = qi + a * row_u8 + (size_t)fx * P.cout;
+          if (P.out_u8) P.out_u8[o] = float_to_pixel(x);
+          if (P.out_crop) P.out_crop[o] = x;
+        }
+      }
+    }
+  }
+}
+
+// any (k, s, p) with a one-cell halo: one work item per output sample
+__device__ __forceinline__ void tc_c2i_gather_any(const TcParams& P, const TcItem& it, const float* sbias, const float* sP, int PS, int et) {
+  const int k = P.c2i_k, s = P.c2i_s, p = P.c2i_p, KP = P.c2i_kp;
+  const int G = it.nrows / KP, g0 = it.n0 / KP;
+  const int IW = (P.TW - 2) * s, nout = (P.TH - 2) * s * IW * G;
+  if (!it.dup) {
+    for (int e = et; e < nout; e += 32 * TC_EPI_WARPS) {
+      const int g = e % G, q = e / G;
+      const int oxl = q % IW, oyl = q / IW;
+      const int cy = 1 + oyl / s, cx = 1 + oxl / s, fy = oyl % s, fx = oxl % s;
+      const int my = it.iy0 + cy, mx = it.ix0 + cx;
+      if (my >= P.hin || mx >= P.win) continue;
+      float acc = 0.f;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int ay = fy + p - s * dy;
+        if (ay < 0 || ay >= k) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int ax = fx + p - s * dx;
+          if (ax < 0 || ax >= k) continue;
+          acc += sP[(size_t)((cy + dy) * P.TW + (cx + dx)) * PS + g * KP + ay * k + ax];
+        }
+      }
+      const int co = g0 + g, oy = s * my + fy, ox = s * mx + fx;
+      const float x = fmaf(acc, P.inv_scale, sbias[co]);
+      if (P.out_f32) P.out_f32[(((size_t)it.b * P.hout + oy) * P.wout + ox) * P.cout + co] = x;
+      if ((P.out_u8 || P.out_crop) && oy < P.H && ox < P.W) {
+        const size_t qi = (((size_t)it.b * P.H + oy) * P.W + ox) * P.cout + co;
+        if (P.out_u8) P.out_u8[qi] = float_to_pixel(x);
+        if (P.out_crop) P.out_crop[qi] = x;
+      }
+    }
+  }
+}
+
+// ---- col2im epilogue (TC_EPI_COL2IM): overlap-add of the per-input-pixel products of a final layer ----
+// The accumulator row of tile cell (cy, cx) holds P[n, (g, a_y, a_x)] for the channels g of this n-tile.  The 8 epilogue warps
+// stage the tile in shared memory (row stride odd: conflict-free), then every thread sums, for its output samples of the
+// INTERIOR cells (1 .. TH-2, 1 .. TW-2), the <= 3 x 3 neighbour terms in a fixed order:
+//     out[s m + f, g] = bias[g] + sum_{d in {-1,0,1}^2, a = f + p - s d in [0,k)^2} P[m + d, (g, a)]
+// (cells outside the image were zero-filled by TMA, so their P is 0 = no contribution).  Which tile a cell belongs to never
+// changes the sum: bit-identical across batch sizes and band splits.
+__device__ __forceinline__ void tc_epi_col2im(const TcParams& P, const TcItem& it, const float* sbias, float* sP, uint32_t trow, int r, int eh, int EH, int et) {
+  const int PS = P.bn_max + 1;
+  {
+    uint32_t raw[32];
+    for (int c = 32 * eh; c < it.mma_n; c += 32 * EH) {
+      tcx::tmem_ld32_nowait(trow + (uint32_t)c, raw);
+      tcx::tmem_ld_wait();
+      float* dst = sP + (size_t)r * PS + c;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c + i < it.mma_n) dst[i] = __uint_as_float(raw[i]);
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
+  if (P.c2i_k == 5 && P.c2i_s == 2 && P.c2i_p == 2) tc_c2i_gather<5, 2, 2, false>(P, it, sbias, sP, PS, et);          // tfc SignalConv2D 5x5 up 2 (mbt2018)
+  else if (P.c2i_k == 5 && P.c2i_s == 2 && P.c2i_p == 1) tc_c2i_gather<5, 2, 1, false>(P, it, sbias, sP, PS, et);     // Keras ConvT 5x5 s2 (CNNSynthesis)
+  else if (P.c2i_k == 9 && P.c2i_s == 4 && P.c2i_p == 4) tc_c2i_gather<9, 4, 4, true>(P, it, sbias, sP, PS, et);     // tfc 9x9 up 4 (bls2017)
+  else tc_c2i_gather_any(P, it, sbias, sP, PS, et);
+  asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");   // the staging tile is free for the next item
+}
+
 // ------------------------------------------------------------------------------------------------
 // Persistent layer kernel: every CTA (CG = 1) or CTA pair (CG = 2, one cluster = two SMs of a TPC) loops over
 // the layer's work items (band, m-tile group, n-tile); the smem ring and the two TMEM accumulators run across
@@ -990,7 +1126,9 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
       tcx::tc_fence_after();
       if (tr) tr[5] = clock64();
       const uint32_t trow = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(ew * 32) << 16);
-      if (P.epi == TC_EPI_TWO_LAYER && nk > 0) {
+      if (P.epi == TC_EPI_COL2IM) {
+        tc_epi_col2im(P, it, sbias, sconst + ((P.cout + 3) & ~3), trow, r, eh, EH, (int)threadIdx.x - 128);
+      } else if (P.epi == TC_EPI_TWO_LAYER && nk > 0) {
         if (P.C1 == 48) {
           const float* sg = sconst + ((P.cout + 3) & ~3);
           if (P.has_res) tc_epi_two_layer_wide<48, true>(P, bd, it, sbias, sg, sg + 48 * 48, trow, it.b, my, mx, cell_ok, eh, EH);
@@ -1289,7 +1427,8 @@ inline bool tc_conv_supported(const ConvLayer& c) {
 }
 
 // `pixel_cols` > 0: n-tiles must hold whole output pixels of that many columns (fused two-layer epilogue).
-inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& hw, TcConv& t, int pixel_cols, std::vector<void*>& owned, std::string* err) {
+inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& hw, TcConv& t, int pixel_cols, std::vector<void*>& owned, std::string* err,
+                         int bn_cap_override = 0, int extra_reserve = 0) {
   t.cin = c.cin;
   t.kblocks = (c.cin + TC_BK - 1) / TC_BK;
   int rem = c.cin - (t.kblocks - 1) * TC_BK;
@@ -1370,7 +1509,7 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
     nbands = (int)bands.size();
     if (bn_max > TC_ACC_COLS) { *err = "n-tile wider than a TMEM accumulator"; return false; }
     int stage_bytes = 2 * TC_BM * 128 + 2 * (bn_max / t.cg) * 128;
-    const int reserve = 2048 + (c.cout + (pixel_cols >= 48 ? 48 * 48 + 48 + 8 : 700)) * 4;   // alignment slack + barriers + epilogue constants (bias | gamma | beta)
+    const int reserve = extra_reserve + 2048 + (c.cout + (pixel_cols >= 48 ? 48 * 48 + 48 + 8 : 700)) * 4;   // alignment slack + barriers + epilogue constants (bias | gamma | beta)
     stages = std::min(8, (227 * 1024 - reserve) / stage_bytes);
     if (stages < 2) { *err = "not enough shared memory for a 2-stage pipeline"; return false; }
     int prefix = 0;
@@ -1380,7 +1519,7 @@ inline bool tc_pack_conv(TcDriver& drv, const ConvLayer& c, const HostWeights& h
     if (nbands > 0 && cudaMemcpy(d_bands, bands.data(), sizeof(TcBandDev) * nbands, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy (band table) failed"; return false; }
     return true;
   };
-  if (!build_tiling(tc_bn_max(), t.bands, t.nbands, t.bn_max, t.stages, t.d_bands)) return false;
+  if (!build_tiling(bn_cap_override > 0 ? bn_cap_override : tc_bn_max(), t.bands, t.nbands, t.bn_max, t.stages, t.d_bands)) return false;
   const int narrow_cap = std::max(64 / unit * unit, unit);
   if (narrow_cap < t.bn_max && !build_tiling(narrow_cap, t.narrow.bands, t.narrow.nbands, t.narrow.bn_max, t.narrow.stages, t.narrow.d_bands)) return false;
   t.ok = t.nbands > 0;
@@ -1399,6 +1538,11 @@ inline bool tc_finalize(TcDriver& drv, TcModelState& st, Transform* hyper, Trans
     for (size_t i = 0; i < t->convs.size(); ++i) {
       const ConvLayer& c = t->convs[i];
       if (!tc_conv_supported(c)) continue;
+      if (c.col2im) {   // final layer in col2im form: pack its 1x1 contraction; n-tiles hold whole channels (<= 96 columns)
+        if (!tc_pack_conv(drv, c.c2i[0], hw, out[i], c.c2i_kp, owned, err, 96, TC_BM * 97 * 4)) return false;
+        out[i].fused_two_layer = false;
+        continue;
+      }
       // two-layer synthesis layer 1 followed by the pointwise IGDN(+res) stage: fuse it when C1 is 12 or 24
       int pixel_cols = 0;
       for (size_t oi = 0; oi + 1 < t->ops.size(); ++oi) {
@@ -1477,6 +1621,8 @@ struct TcConvOut {
   // GDN stages (see TcParams): pooled planes out / norm-pool GEMM epilogue
   int plane_xform = A_NONE; int gdn_mode = G_NONE; const float* gx = nullptr;
   unsigned pass_mask = 3u; const unsigned* alo_flag = nullptr;   // see TcParams
+  // col2im final layer (ConvLayer::col2im): the layer passed to tc_run_conv is its 1x1 contraction c2i[0]; these describe the ConvT
+  bool col2im = false; int c2i_k = 0, c2i_s = 1, c2i_p = 0, c2i_kp = 0, c2i_cout = 0; const float* c2i_bias = nullptr;
 };
 
 inline void tc_choose_patch(int h, int w, int* TH, int* TW) {
@@ -1504,12 +1650,19 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
                        const TcConvOut& o, cudaStream_t s, uint64_t* launches, std::string* err) {
   int TH, TW;
   tc_choose_patch(h, w, &TH, &TW);
+  if (o.col2im) { TH = 8; TW = 16; }   // overlapping tiles: 6 x 14 interior cells + a one-cell halo
   CUtensorMap mapAhi, mapAlo;
   if (!tc_make_map_4d(drv, &mapAhi, (void*)in_hi, c.cin, w, h, B, TW, TH, err)) return TC_ERROR;
   if (!tc_make_map_4d(drv, &mapAlo, (void*)in_lo, c.cin, w, h, B, TW, TH, err)) return TC_ERROR;
   TcParams P{};
   P.B = B; P.hin = h; P.win = w; P.s = c.s; P.p = c.p;
   P.TH = TH; P.TW = TW; P.tiles_y = (h + TH - 1) / TH; P.tiles_x = (w + TW - 1) / TW;
+  P.tile_step_y = TH; P.tile_step_x = TW; P.tile_off = 0;
+  if (o.col2im) {
+    P.tile_step_y = TH - 2; P.tile_step_x = TW - 2; P.tile_off = -1;
+    P.tiles_y = (h + P.tile_step_y - 1) / P.tile_step_y; P.tiles_x = (w + P.tile_step_x - 1) / P.tile_step_x;
+    P.c2i_k = o.c2i_k; P.c2i_s = o.c2i_s; P.c2i_p = o.c2i_p; P.c2i_kp = o.c2i_kp;
+  }
   const int mtiles = P.tiles_x * P.tiles_y * B;
   const int groups = (mtiles + t.cg - 1) / t.cg;
   P.mtiles = mtiles;
@@ -1538,6 +1691,10 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   P.inv_scale = 1.f / t.scale; P.bias = c.d_bias; P.act = c.act;
   P.hout = h * c.s - c.out_crop; P.wout = w * c.s - c.out_crop;
   P.epi = o.hyper_final ? TC_EPI_HYPER_FINAL : (o.two_layer ? TC_EPI_TWO_LAYER : TC_EPI_PLAIN);
+  if (o.col2im) {
+    if (o.hyper_final || o.two_layer || o.hi || o.gdn_mode != G_NONE || !o.c2i_bias) { *err = "col2im layer: unsupported epilogue combination"; return TC_ERROR; }
+    P.epi = TC_EPI_COL2IM; P.hout = h * o.c2i_s; P.wout = w * o.c2i_s; P.cout = o.c2i_cout; P.bias = o.c2i_bias;
+  }
   P.out_hi = o.hi; P.out_lo = o.lo; P.out_f32 = o.f32; P.out_u8 = o.u8; P.out_crop = o.crop; P.H = o.H; P.W = o.W;
   P.q = o.q; P.q_kind = o.q_kind; P.Cy = o.Cy; P.max_index = o.max_index; P.trunc = o.trunc ? 1 : 0; P.y_hat = o.y_hat; P.idx = o.idx;
   P.C1 = o.C1; P.has_res = o.has_res ? 1 : 0; P.tl_act = o.tl_act; P.tl_inverse = o.tl_inverse ? 1 : 0;
@@ -1562,9 +1719,9 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
     // n-tiles must start on a 16-column boundary and the mma width is a multiple of 32 only when BN is: chunks are 32 wide,
     // the last one may be half-used
     for (auto& bd : bands) ok = ok && bd.BN % 16 == 0;
-    P.vec16 = ok ? 1 : 0;
+    P.vec16 = (ok && !o.col2im) ? 1 : 0;
   }
-  P.rgb_runs = (c.cout == 3 && o.u8 && !o.f32 && !o.crop && !o.hi && !o.hyper_final && !o.two_layer && tc_env_int("SNTC_TC_RGB_RUNS", 1)) ? 1 : 0;
+  P.rgb_runs = (!o.col2im && c.cout == 3 && o.u8 && !o.f32 && !o.crop && !o.hi && !o.hyper_final && !o.two_layer && tc_env_int("SNTC_TC_RGB_RUNS", 1)) ? 1 : 0;
   if ((o.plane_xform != A_NONE || o.gdn_mode != G_NONE) && !P.vec16) {
     *err = "GDN stage on the tensor cores: needs C % 16 == 0 and 32-byte aligned tensors"; return TC_ERROR;
   }
@@ -1573,6 +1730,7 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
     *err = "rate term: needs Cy % 16 == 0, 32-byte aligned tensors and a large enough slot buffer"; return TC_ERROR;
   }
   size_t smem = (size_t)stages * (2 * TC_BM * 128 + 2 * (bn_max / t.cg) * 128) + 1024 + 64 * 8 + (size_t)((o.two_layer ? o.C1 * o.C1 + o.C1 : 0) + c.cout + 8) * 4;
+  if (o.col2im) smem += (size_t)TC_BM * (bn_max + 1) * 4;   // staging tile of the overlap-add epilogue
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns
   if (smem > 227 * 1024) { *err = "shared memory budget exceeded"; return TC_ERROR; }
   int units = std::min(drv.num_sms / t.cg, P.total_items);

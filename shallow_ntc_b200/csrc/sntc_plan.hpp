@@ -27,7 +27,9 @@ enum KernelLayout { LAYOUT_KERAS_OI = 0 /* [kh,kw,Cout,Cin] */, LAYOUT_TFC_IO = 
                     //   out[2y+dy, 2x+dx, co] = sum_c in[y, x, (2 dy + dx) Cin/4 + c] * K[0, 0, c, co]      (NHWC / DCR order)
                     LAYOUT_D2S_1X1 = 2,
                     // the input-gradient of another layer written as a stride-1 layer of this plan (make_backward_conv)
-                    LAYOUT_BACKWARD = 3 };
+                    LAYOUT_BACKWARD = 3,
+                    // the per-input-pixel contraction of a final layer in col2im form (make_col2im_conv)
+                    LAYOUT_COL2IM = 4 };
 enum GdnKind { GDN_NONE = 0, GDN_1 = 1 /* beta + |x| gamma */, GDN_CLASSIC = 2 /* sqrt(beta + x^2 gamma) */ };
 
 struct Band1D {
@@ -79,6 +81,11 @@ struct ConvLayer {
   // r = o mod s of a cell (o = s*i + r), with a uniform tap window d = i - n in [dlo, dlo + T): a = r + p + s*d
   // (taps outside [0,k) are zero weights).  N = s*s*cout instead of a handful of 3-column bands.
   bool merged = false; int dlo = 0;
+  // col2im form of a final layer with tiny Cout and a wide input (deep decoders: ConvT(5, 2, 192 -> 3), ConvT(9, 4, 256 -> 3)) on the
+  // tensor-core path: ONE 1x1 GEMM per input pixel, P[n, (co, a_y, a_x)] = sum_ci in[n, ci] W[a, co, ci] (c2i[0], K = Cin: the input
+  // is read once instead of once per tap), and an overlap-add epilogue out[o] = sum_{n in 3x3} P[n, a = o + p - s n] over
+  // overlapping tiles (sntc_kernels_tc.cuh, TC_EPI_COL2IM).  c2i_kp = columns reserved per output channel (k*k rounded up to 32).
+  bool col2im = false; int c2i_kp = 0; std::vector<ConvLayer> c2i;
   int out_crop = 0;          // the output grid is h*s - out_crop rows / columns (backward layers: the input carries T-1 extra rows)
   std::vector<ConvLayer> bwd_src;   // LAYOUT_BACKWARD: copy of the forward layer whose input-gradient this layer computes
   int act = SNTC_ACT_NONE;   // only NONE / RELU / LEAKY_RELU are fused into the conv
@@ -200,6 +207,31 @@ inline ConvLayer make_backward_conv(const ConvLayer& f) {
   c.sources[0].cout = c.cout;
   c.bwd_src.push_back(f);
   c.bwd_src[0].bwd_src.clear();
+  finish_conv(c);
+  return c;
+}
+
+// Final layers the col2im form serves: every output depends on the 3x3 neighbourhood of its cell at most.
+inline bool col2im_eligible(const ConvLayer& c) {
+  if (c.append_ones || c.cout > 4 || c.cout < 1 || (c.s != 2 && c.s != 4) || c.act != SNTC_ACT_NONE) return false;
+  if (c.cin % 8 != 0 || c.cin < 64) return false;
+  const int hi = (c.s - 1 + c.p) / c.s;                               // n_max - i
+  const int lo = -ceil_div_floor(c.p - c.k + 1, c.s);                 // i - n_min
+  // all output channels must fit ONE n-tile of <= 96 columns (k5: 3 x 32): with one n-tile per channel (k9 s4: 3 x 96) the input is
+  // read and staged once per channel and the merged form wins (bls2017 4K final layer: 1.04 vs 0.93 ms)
+  return hi <= 1 && lo <= 1 && c.cout * ((c.k * c.k + 31) / 32 * 32) <= 96;
+}
+
+inline ConvLayer make_col2im_conv(const ConvLayer& f) {
+  ConvLayer c;
+  const int kp = (f.k * f.k + 31) / 32 * 32;
+  c.k = 1; c.s = 1; c.p = 0; c.cin = f.cin; c.cout = f.cout * kp;
+  c.layout = LAYOUT_COL2IM; c.has_bias = false; c.act = SNTC_ACT_NONE;
+  for (auto& s : f.sources) c.sources.push_back({s.kernel, std::string(), 0});
+  c.sources[0].cout = c.cout;
+  c.bwd_src.push_back(f);
+  c.bwd_src[0].bwd_src.clear(); c.bwd_src[0].c2i.clear();
+  c.c2i_kp = kp;
   finish_conv(c);
   return c;
 }
@@ -397,6 +429,12 @@ inline float conv_w(const ConvLayer& c, const HostWeights& hw, int ay, int ax, i
     const int fay = f.s * dy + r / f.s, fax = f.s * dx + r % f.s;
     if (fay >= f.k || fax >= f.k) return 0.f;
     return conv_w(f, hw, fay, fax, cof, co);
+  }
+  if (c.layout == LAYOUT_COL2IM) {     // see make_col2im_conv: column (g, t), t = a_y * k + a_x < k*k
+    const ConvLayer& f = c.bwd_src[0];
+    const int g = co / c.c2i_kp, tt = co - g * c.c2i_kp;
+    if (tt >= f.k * f.k) return 0.f;
+    return conv_w(f, hw, tt / f.k, tt % f.k, g, ci);
   }
   int base = 0;
   for (auto& s : c.sources) {
