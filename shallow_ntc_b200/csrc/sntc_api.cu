@@ -1036,9 +1036,17 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
           const GdnLayer& g = t.gdns[t.ops[i + 1].gdn];
           __half *hi, *lo;
           next_planes(&hi, &lo);
-          float* dst = next_buf();
-          o.hi = hi; o.lo = lo; o.f32 = dst; o.plane_xform = g.kind == GDN_1 ? A_ABS : A_SQUARE;
-          nxt.hi = hi; nxt.lo = lo; nxt.f32 = dst;
+          o.hi = hi; o.lo = lo; o.plane_xform = g.kind == GDN_1 ? A_ABS : A_SQUARE;
+          nxt.hi = hi; nxt.lo = lo;
+          // GDN1: no fp32 copy of x -- the |x| planes carry sign(x) in the LSB of lo and the GDN epilogue rebuilds x from them
+          // (SNTC_TC_GDN_SIGN=0: x as a separate fp32 tensor, as the classic (x^2) form always does)
+          static const bool gdn_sign = tc_env_int("SNTC_TC_GDN_SIGN", 1) != 0;
+          if (g.kind == GDN_1 && gdn_sign) {
+            o.sign_in_lo = true;
+          } else {
+            float* dst = next_buf();
+            o.f32 = dst; nxt.f32 = dst;
+          }
         } else {
           float* dst = next_buf();
           o.f32 = dst; nxt.f32 = dst;
@@ -1155,14 +1163,16 @@ static int run_transform(sntc_model* m, Transform& t, bool is_hyper, Cur cur, in
       ch *= c.s; cw *= c.s; cc = c.cout;
       cur = Cur{}; cur.f32 = dst;
     } else if (op.type == OP_GDN) {
-      if (!cur.f32) return fail(SNTC_E_STATE, "executor: GDN needs an fp32 input");
       const GdnLayer& gl = t.gdns[op.gdn];
+      if (!cur.f32 && !(cur.hi && gdn_on_tc(m, t, is_hyper, i) && gl.kind == GDN_1))
+        return fail(SNTC_E_STATE, "executor: GDN needs an fp32 input");
       if (cur.hi && gdn_on_tc(m, t, is_hyper, i)) {
         // ---- norm pool on the tensor cores: [pixels x C] (planes of |x| / x^2) * gamma, epilogue x * norm ----
         TcGdn& tg = m->tc.syn_gdn[op.gdn];
         TcConvOut o;
         Cur nxt;
         o.gx = cur.f32;
+        if (!cur.f32) { o.gx_hi = cur.hi; o.gx_lo = cur.lo; }   // planes with sign(x) in the LSB of lo (see the conv above)
         o.gdn_mode = gl.kind == GDN_1 ? (gl.inverse ? G_MUL : G_DIV) : (gl.inverse ? G_MUL_SQRT : G_DIV_SQRT);
         if (!last && op_on_tc(m, t, is_hyper, i + 1)) {
           __half *hi, *lo;
@@ -1345,7 +1355,27 @@ static int vjp_run(sntc_model* m, VjpPlan& P, bool is_hyper, const float* x, con
     } else if (op.type == OP_GDN) {
       const GdnLayer& g = t.gdns[op.gdn];
       TRY(P.acts[i].ensure((size_t)B * ch * cw * g.C * 4));
-      TRY(run_gdn_f32(ctx, g, cur, (size_t)B * ch * cw, (float*)P.acts[i].p, s));
+      if (is_tc(m->desc.precision) && !is_hyper && op.gdn < (int)m->tc.syn_gdn.size() && m->tc.syn_gdn[op.gdn].ok) {
+        // the model's tensor-core norm pool: planes of |x| (x^2) -> [pixels x C] * gamma, epilogue x * norm
+        TcGdn& tg = m->tc.syn_gdn[op.gdn];
+        const size_t n = (size_t)B * ch * cw * g.C;
+        TRY(P.pl[0].ensure(n * 2)); TRY(P.pl[1].ensure(n * 2));
+        split_planes_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, s>>>(cur, (__half*)P.pl[0].p, (__half*)P.pl[1].p, n / 8, nullptr,
+                                                                           g.kind == GDN_1 ? A_ABS : A_SQUARE);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        TcConvOut o;
+        o.f32 = (float*)P.acts[i].p; o.gx = cur;
+        o.gdn_mode = g.kind == GDN_1 ? (g.inverse ? G_MUL : G_DIV) : (g.inverse ? G_MUL_SQRT : G_DIV_SQRT);
+        std::string err;
+        ProfScope ps(m, s, "vjp.forward." + g.beta.substr(0, g.beta.size() - 5), (double)B * ch * cw * g.C * g.C);
+        if (tc_run_conv(ctx->tc, tg.conv, tg.tc, (const __half*)P.pl[0].p, (const __half*)P.pl[1].p, B, ch, cw, o, s, &ctx->launches, &err) != TC_OK)
+          return fail(SNTC_E_CUDA, "vjp forward (tensor-core GDN): " + err);
+        ctx->kinds[SNTC_LAUNCH_BAND_TC]++;
+      } else {
+        ProfScope ps(m, s, "vjp.forward." + g.beta.substr(0, g.beta.size() - 5), (double)B * ch * cw * g.C * g.C);
+        TRY(run_gdn_f32(ctx, g, cur, (size_t)B * ch * cw, (float*)P.acts[i].p, s));
+      }
     } else if (op.type == OP_ACT_RES) {
       const int C = cc / 2;
       if (C > 64) return fail(SNTC_E_UNSUPPORTED, "two-layer hidden width > 64");

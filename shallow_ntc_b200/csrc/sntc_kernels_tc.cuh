@@ -87,6 +87,8 @@ struct TcParams {
   //   plane_xform: the fp16 planes receive f(x) (A_ABS / A_SQUARE = the GDN pooling input) while out_f32 receives x;
   //   gdn_mode: this GEMM *is* the GDN norm pool (1x1, gamma): out = gx * norm | gx / norm, norm = acc + beta (or its sqrt)
   int plane_xform, gdn_mode; const float* gx;
+  int sign_in_lo;                            // plane_xform == A_ABS: the lo plane carries sign(x) in its mantissa LSB (store16_planes_abs_sign)
+  const __half* gx_hi; const __half* gx_lo;  // gdn_mode with gx == nullptr: x = +-(hi + lo) from such planes (the GEMM's own A operand)
   int vec16;          // fast epilogue: cout % 16 == 0, Cy % 16 == 0 and every epilogue tensor 32-byte aligned
   int rgb_runs;       // final layer to 3 channels whose only destination is the uint8 image: byte-run epilogue (tc_epi_rgb_chunk)
   // TC_EPI_TWO_LAYER constants as kernel parameters: with the loops over (i, j) fully unrolled every gamma / beta / bias
@@ -407,6 +409,37 @@ __device__ __forceinline__ void store16_planes(__half* hi, __half* lo, size_t of
   tcx::stg256(hi + off, h);
   tcx::stg256(lo + off, l);
 }
+// Planes of |v| whose lo halves carry sign(v) in their mantissa LSB (TcParams::sign_in_lo): the GDN stage that follows pools |x| on
+// the tensor cores and rebuilds x = +-(hi + lo) in its epilogue from the very planes its TMA loads just pulled through L2, so x
+// never makes a separate fp32 round trip through HBM.  The LSB moves |x| by <= 1 ulp(lo) <= 2^-21 |x| (the split product already
+// drops lo*lo, 2^-22).
+__device__ __forceinline__ void store16_planes_abs_sign(__half* hi, __half* lo, size_t off, const float* v) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float c0 = fminf(fabsf(v[2 * i]), 65504.f), c1 = fminf(fabsf(v[2 * i + 1]), 65504.f);
+    const __half2 hh = __floats2half2_rn(c0, c1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(c0 - hf.x, c1 - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = (*reinterpret_cast<const uint32_t*>(&ll) & 0xFFFEFFFEu) | (__float_as_uint(v[2 * i]) >> 31) | ((__float_as_uint(v[2 * i + 1]) >> 31) << 16);
+  }
+  tcx::stg256(hi + off, h);
+  tcx::stg256(lo + off, l);
+}
+// x[16] back from such planes
+__device__ __forceinline__ void load16_planes_abs_sign(const __half* hi, const __half* lo, size_t off, float* x) {
+  uint32_t h[8], l[8];
+  tcx::ldg256_nc(hi + off, h);
+  tcx::ldg256_nc(lo + off, l);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i])), lf = __half22float2(*reinterpret_cast<const __half2*>(&l[i]));
+    const float a0 = hf.x + lf.x, a1 = hf.y + lf.y;
+    x[2 * i] = (l[i] & 1u) ? -a0 : a0;
+    x[2 * i + 1] = (l[i] & 0x10000u) ? -a1 : a1;
+  }
+}
 __device__ __forceinline__ void store16_f32(float* o, const float* v) {
   tcx::stg256(o, reinterpret_cast<const uint32_t*>(v));
   tcx::stg256(o + 8, reinterpret_cast<const uint32_t*>(v) + 8);
@@ -444,8 +477,12 @@ struct TcBandRegs { int N, nphx, phy0, phx0, oshift; };
 template <int GM>
 __device__ __forceinline__ void tc_epi_gdn16(const TcParams& P, const float* sbias, size_t off, int co, const uint32_t* raw) {
   float x[16], v[16];
-  tcx::ldg256_nc(P.gx + off, reinterpret_cast<uint32_t*>(x));
-  tcx::ldg256_nc(P.gx + off + 8, reinterpret_cast<uint32_t*>(x) + 8);
+  if (P.gx) {
+    tcx::ldg256_nc(P.gx + off, reinterpret_cast<uint32_t*>(x));
+    tcx::ldg256_nc(P.gx + off + 8, reinterpret_cast<uint32_t*>(x) + 8);
+  } else {
+    load16_planes_abs_sign(P.gx_hi, P.gx_lo, off, x);   // the pooling planes themselves (L2-hot: this CTA's TMA just loaded them)
+  }
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const float4 bb = *reinterpret_cast<const float4*>(sbias + co + 4 * g);
@@ -530,8 +567,12 @@ __device__ __forceinline__ float tc_epi_vec16(const TcParams& P, const float* sb
   for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], P.act);
   if (P.gdn_mode != G_NONE) {   // v = beta + f(x) gamma: scale the layer input x by the norm
     float x[16];
-    tcx::ldg256_nc(P.gx + pix * P.cout + co, reinterpret_cast<uint32_t*>(x));
-    tcx::ldg256_nc(P.gx + pix * P.cout + co + 8, reinterpret_cast<uint32_t*>(x) + 8);
+    if (P.gx) {
+      tcx::ldg256_nc(P.gx + pix * P.cout + co, reinterpret_cast<uint32_t*>(x));
+      tcx::ldg256_nc(P.gx + pix * P.cout + co + 8, reinterpret_cast<uint32_t*>(x) + 8);
+    } else {
+      load16_planes_abs_sign(P.gx_hi, P.gx_lo, pix * P.cout + co, x);
+    }
     const bool root = P.gdn_mode == G_MUL_SQRT || P.gdn_mode == G_DIV_SQRT, mul = P.gdn_mode == G_MUL || P.gdn_mode == G_MUL_SQRT;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -541,7 +582,10 @@ __device__ __forceinline__ float tc_epi_vec16(const TcParams& P, const float* sb
   }
   if (P.out_f32) store16_f32(P.out_f32 + pix * P.cout + co, v);
   if (P.out_hi) {
-    if (P.plane_xform == A_ABS) {
+    if (P.plane_xform == A_ABS && P.sign_in_lo) {
+      store16_planes_abs_sign(P.out_hi, P.out_lo, pix * P.cout + co, v);
+      return 0.f;
+    } else if (P.plane_xform == A_ABS) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = fabsf(v[i]);
     } else if (P.plane_xform == A_SQUARE) {
@@ -1251,7 +1295,8 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
 
 // f32 NHWC -> fp16 hi/lo planes (input of the first tensor-core layer).  lo_flag (nullable, zeroed by the caller) is set
 // to 1 when any lo element is non-zero: an all-zero lo plane (integer-valued symbols) lets the layer skip its a_lo * w_hi pass.
-__global__ void split_planes_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t n8, unsigned* lo_flag) {
+__global__ void split_planes_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t n8, unsigned* lo_flag,
+                                    int xform = A_NONE) {   // xform: the planes receive |x| / x^2 (pooling input of a GDN stage)
   tcx::pdl_launch_dependents();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool nz = false;
@@ -1261,7 +1306,7 @@ __global__ void split_planes_kernel(const float* __restrict__ x, __half* __restr
     __align__(16) __half h[8];
     __align__(16) __half l[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { split_f16(v[k], h[k], l[k]); nz = nz || (__half_as_ushort(l[k]) & 0x7FFFu) != 0; }
+    for (int k = 0; k < 8; ++k) { split_f16(a_xform(v[k], xform), h[k], l[k]); nz = nz || (__half_as_ushort(l[k]) & 0x7FFFu) != 0; }
     *reinterpret_cast<uint4*>(hi + i * 8) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(lo + i * 8) = *reinterpret_cast<const uint4*>(l);
   }
@@ -1620,6 +1665,7 @@ struct TcConvOut {
   const float* h_gamma = nullptr; const float* h_beta = nullptr;   // host copies ([C1][C1], [C1]) -> kernel parameters
   // GDN stages (see TcParams): pooled planes out / norm-pool GEMM epilogue
   int plane_xform = A_NONE; int gdn_mode = G_NONE; const float* gx = nullptr;
+  bool sign_in_lo = false; const __half* gx_hi = nullptr; const __half* gx_lo = nullptr;   // see TcParams
   unsigned pass_mask = 3u; const unsigned* alo_flag = nullptr;   // see TcParams
   // col2im final layer (ConvLayer::col2im): the layer passed to tc_run_conv is its 1x1 contraction c2i[0]; these describe the ConvT
   bool col2im = false; int c2i_k = 0, c2i_s = 1, c2i_p = 0, c2i_kp = 0, c2i_cout = 0; const float* c2i_bias = nullptr;
@@ -1711,11 +1757,14 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
   }
   P.rate_slots = o.rate_slots; P.rate_slot_img = o.rate_slot_img; P.rc = o.rc; P.sigma_out = o.sigma_out;
   P.plane_xform = o.plane_xform; P.gdn_mode = o.gdn_mode; P.gx = o.gx;
+  P.sign_in_lo = o.sign_in_lo ? 1 : 0; P.gx_hi = o.gx_hi; P.gx_lo = o.gx_lo;
+  if (o.gdn_mode != G_NONE && !o.gx && !(o.gx_hi && o.gx_lo)) { *err = "GDN stage: no source for x"; return TC_ERROR; }
+  if (o.sign_in_lo && (o.plane_xform != A_ABS || !o.hi)) { *err = "sign_in_lo needs |x| planes"; return TC_ERROR; }
   P.pass_mask = o.pass_mask & 3u; P.alo_flag = o.alo_flag;
   {
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
     bool ok = c.cout % 16 == 0 && (!o.hyper_final || o.Cy % 16 == 0) && !o.two_layer && !o.u8 && !o.crop;
-    ok = ok && al(o.hi) && al(o.lo) && al(o.f32) && al(o.q) && al(o.y_hat) && al(o.idx) && al(o.gx) && al(o.sigma_out);
+    ok = ok && al(o.hi) && al(o.lo) && al(o.f32) && al(o.q) && al(o.y_hat) && al(o.idx) && al(o.gx) && al(o.sigma_out) && al(o.gx_hi) && al(o.gx_lo);
     // n-tiles must start on a 16-column boundary and the mma width is a multiple of 32 only when BN is: chunks are 32 wide,
     // the last one may be half-used
     for (auto& bd : bands) ok = ok && bd.BN % 16 == 0;
