@@ -59,6 +59,7 @@ struct TcParams {
                       // (items of band i start at bands[i].item_begin * groups).  The band table itself never depends on the batch.
   int B, hin, win, s, p;
   int TH, TW, tiles_y, tiles_x;
+  int TB;             // images per m-tile (TH * TW * TB = 128): small latent grids pack several images into one tile (tc_choose_patch)
   int tile_step_y, tile_step_x, tile_off;   // m-tile (ty, tx) starts at cell (ty * step_y + off, tx * step_x + off): TH / TW / 0, or overlapping tiles (col2im)
   // TC_EPI_COL2IM (ConvLayer::col2im): the GEMM is the per-input-pixel contraction P[n, (g, a_y, a_x)] of a final layer ConvT(k, s, p) to
   // c2i_cout channels, c2i_kp columns per channel; cout / bias below are those of the FINAL layer, hout = hin * s
@@ -342,7 +343,7 @@ __device__ __forceinline__ TcItem tc_decode_item(const TcParams& P, int item, in
   const unsigned q1 = (unsigned)mt / (unsigned)P.tiles_x, bq = q1 / (unsigned)P.tiles_y;
   const int tx = mt - (int)q1 * P.tiles_x, ty = (int)(q1 - bq * (unsigned)P.tiles_y);
   it.band = bi;
-  it.b = (int)bq;
+  it.b = (int)bq * P.TB;   // first image of the tile
   it.iy0 = ty * P.tile_step_y + P.tile_off; it.ix0 = tx * P.tile_step_x + P.tile_off;
   it.n0 = nt * bd.BN;
   it.nrows = min(bd.BN, bd.N - it.n0);
@@ -1153,17 +1154,19 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     constexpr int EH = TC_EPI_WARPS / 4;
     const int r = ew * 32 + lane;               // row of the tile = cell
     const float* sbias = sconst;
+    const int r_x = r % P.TW, r_q = r / P.TW, r_y = r_q % P.TH, r_b = r_q / P.TH;   // tile row -> (image, y, x) of the TMA box
     uint32_t j = 0;
     for (;; ++j) {
       const int item = tc_unit_item(unit0, nunits, (int)j, P.snake);
       if (item >= P.total_items) break;
-      const TcItem it = tc_decode_item<CG>(P, item, rank);
+      TcItem it = tc_decode_item<CG>(P, item, rank);
+      it.b += r_b;                                   // this thread's image (tiles of TB > 1 images: rows [b][y][x])
       const TcBandDev& bdg = P.bands[it.band];
       const TcBandRegs bd{bdg.N, bdg.nphx, bdg.phy0, bdg.phx0, bdg.oshift};
       const int nk = bdg.Ty * bdg.Tx * P.kblocks;
       const uint32_t buf = j & 1u;
-      const int iy = it.iy0 + r / P.TW, ix = it.ix0 + r % P.TW;
-      const bool cell_ok = iy < P.hin && ix < P.win && !it.dup;
+      const int iy = it.iy0 + r_y, ix = it.ix0 + r_x;
+      const bool cell_ok = iy < P.hin && ix < P.win && it.b < P.B && !it.dup;
       const int my = bdg.mloy + iy, mx = bdg.mlox + ix;
       long long* tr = (P.trace && leader && warp == 4 && lane == 0 && j < TC_TRACE_ITEMS) ? P.trace + ((size_t)unit0 * TC_TRACE_ITEMS + j) * 8 : nullptr;
       tcx::mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1u);
@@ -1225,7 +1228,7 @@ band_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
             if (lane == 0) {
               const size_t slot = ((size_t)item * CG + rank) * TC_EPI_WARPS + (warp - 4);
               P.rate_slots[slot] = d;
-              P.rate_slot_img[slot] = it.dup ? -1 : it.b;
+              P.rate_slot_img[slot] = (it.dup || it.b >= P.B) ? -1 : it.b;
             }
           }
         } else if (P.rgb_runs && bd.nphx * 3 >= 32 && nk > 0) {
@@ -1455,10 +1458,10 @@ inline bool tc_make_map_2d(TcDriver& drv, CUtensorMap* map, void* base, uint64_t
   return true;
 }
 
-inline bool tc_make_map_4d(TcDriver& drv, CUtensorMap* map, void* base, int C, int w, int h, int B, int TW, int TH, std::string* err) {
+inline bool tc_make_map_4d(TcDriver& drv, CUtensorMap* map, void* base, int C, int w, int h, int B, int TW, int TH, std::string* err, int TB = 1) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)w * C * 2, (cuuint64_t)h * w * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = drv.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1671,20 +1674,30 @@ struct TcConvOut {
   bool col2im = false; int c2i_k = 0, c2i_s = 1, c2i_p = 0, c2i_kp = 0, c2i_cout = 0; const float* c2i_bias = nullptr;
 };
 
-inline void tc_choose_patch(int h, int w, int* TH, int* TW) {
+// m-tile = TB images x TH x TW cells (= 128 rows of the TMA box, order [b][y][x]); TH * TW is a multiple of 32 so that an epilogue
+// warp (32 consecutive rows) stays inside one image.  Fewest tiles wins; ties keep one image per tile and the historical order.
+// 24 latent grids of 8 x 12 (hyper layer 0 of 768x512 images): 8 x 16 x 1 wastes a quarter of every tile (24 tiles), 8 x 4 x 4 tiles
+// exactly (18) -- one wave of work items instead of two.  SNTC_TC_BATCH_TILES=0 keeps TB = 1.
+inline void tc_choose_patch(int h, int w, int B, int* TH, int* TW, int* TB) {
   static const int cand[8][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {64, 2}, {1, 128}, {128, 1}};
+  static const bool batch_tiles = tc_env_int("SNTC_TC_BATCH_TILES", 1) != 0;
   long best = -1;
-  for (auto& c : cand) {
-    long cost = (long)((h + c[0] - 1) / c[0]) * ((w + c[1] - 1) / c[1]);
-    if (best < 0 || cost < best) { best = cost; *TH = c[0]; *TW = c[1]; }
-  }
+  for (int tb = 1; tb <= (batch_tiles ? 4 : 1); tb *= 2)
+    for (auto& c : cand) {
+      if (c[0] % tb != 0 && c[1] % tb != 0) continue;
+      // split the y extent of the 128-row candidate by tb when possible, else the x extent
+      const int th = c[0] % tb == 0 ? c[0] / tb : c[0], tw = c[0] % tb == 0 ? c[1] : c[1] / tb;
+      if (th * tw % 32 != 0) continue;
+      long cost = (long)((h + th - 1) / th) * ((w + tw - 1) / tw) * ((B + tb - 1) / tb);
+      if (best < 0 || cost < best) { best = cost; *TH = th; *TW = tw; *TB = tb; }
+    }
 }
 
 // Number of bits_y partial slots the hyper-final epilogue of this layer writes for a [B,h,w] input.
 inline size_t tc_rate_slots(const TcConv& t, int B, int h, int w, int num_sms) {
-  int TH, TW;
-  tc_choose_patch(h, w, &TH, &TW);
-  const int mtiles = ((h + TH - 1) / TH) * ((w + TW - 1) / TW) * B;
+  int TH, TW, TB;
+  tc_choose_patch(h, w, B, &TH, &TW, &TB);
+  const int mtiles = ((h + TH - 1) / TH) * ((w + TW - 1) / TW) * ((B + TB - 1) / TB);
   const int groups = (mtiles + t.cg - 1) / t.cg;
   size_t items = 0;
   for (auto& bd : (tc_use_narrow(t, mtiles, num_sms) ? t.narrow.bands : t.bands)) items += (size_t)groups * bd.ntiles;
@@ -1694,12 +1707,12 @@ inline size_t tc_rate_slots(const TcConv& t, int B, int h, int w, int num_sms) {
 // One persistent launch for all bands of one conv layer.  Input: fp16 planes [B,h,w,cin].
 inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __half* in_hi, const __half* in_lo, int B, int h, int w,
                        const TcConvOut& o, cudaStream_t s, uint64_t* launches, std::string* err) {
-  int TH, TW;
-  tc_choose_patch(h, w, &TH, &TW);
-  if (o.col2im) { TH = 8; TW = 16; }   // overlapping tiles: 6 x 14 interior cells + a one-cell halo
+  int TH, TW, TB;
+  tc_choose_patch(h, w, B, &TH, &TW, &TB);
+  if (o.col2im) { TH = 8; TW = 16; TB = 1; }   // overlapping tiles: 6 x 14 interior cells + a one-cell halo
   CUtensorMap mapAhi, mapAlo;
-  if (!tc_make_map_4d(drv, &mapAhi, (void*)in_hi, c.cin, w, h, B, TW, TH, err)) return TC_ERROR;
-  if (!tc_make_map_4d(drv, &mapAlo, (void*)in_lo, c.cin, w, h, B, TW, TH, err)) return TC_ERROR;
+  if (!tc_make_map_4d(drv, &mapAhi, (void*)in_hi, c.cin, w, h, B, TW, TH, err, TB)) return TC_ERROR;
+  if (!tc_make_map_4d(drv, &mapAlo, (void*)in_lo, c.cin, w, h, B, TW, TH, err, TB)) return TC_ERROR;
   TcParams P{};
   P.B = B; P.hin = h; P.win = w; P.s = c.s; P.p = c.p;
   P.TH = TH; P.TW = TW; P.tiles_y = (h + TH - 1) / TH; P.tiles_x = (w + TW - 1) / TW;
@@ -1709,7 +1722,8 @@ inline int tc_run_conv(TcDriver& drv, const ConvLayer& c, TcConv& t, const __hal
     P.tiles_y = (h + P.tile_step_y - 1) / P.tile_step_y; P.tiles_x = (w + P.tile_step_x - 1) / P.tile_step_x;
     P.c2i_k = o.c2i_k; P.c2i_s = o.c2i_s; P.c2i_p = o.c2i_p; P.c2i_kp = o.c2i_kp;
   }
-  const int mtiles = P.tiles_x * P.tiles_y * B;
+  P.TB = TB;
+  const int mtiles = P.tiles_x * P.tiles_y * ((B + TB - 1) / TB);
   const int groups = (mtiles + t.cg - 1) / t.cg;
   P.mtiles = mtiles;
   // item order: m-tile-group major for the two-layer layer (its per-pixel IGDN epilogue is as long as the MMAs of a light

@@ -406,3 +406,37 @@ def test_cuda_graph_replay_of_small_batches_is_bit_identical(gpu_ctx, name, monk
   monkeypatch.setenv("SNTC_GRAPH", "0")
   got = model.decompress(*args(dz, dq), out=out)
   assert np.array_equal(got["image"].to_host(), host["image"])
+
+
+@pytest.mark.parametrize("name,B,H,W", [("mbt2018", 3, 100, 150), ("two_layer_syn", 5, 97, 149), ("bls2017", 2, 90, 130)])
+def test_repeated_decodes_and_shards_are_bit_identical_on_the_tensor_path(gpu_ctx, name, B, H, W):
+  """Race / ordering check of the tensor-core kernels with shared-memory hand-offs between warps (col2im overlap-add epilogue with
+  its named barriers, window-GEMM tail conversion stage, TMEM double buffering): 8 repeats of one decode are bit-identical, float
+  outputs included, and a shard equals its slice of the batch (different tiles / work-item assignment, same sums)."""
+  model, wts, z, q = make_case(name, B, H, W, "stress", "tc", gpu_ctx)
+  first = model.decompress(z, q, (H, W), return_float=True)
+  for _ in range(7):
+    again = model.decompress(z, q, (H, W), return_float=True)
+    assert np.array_equal(first["image"], again["image"]) and np.array_equal(first["float"], again["float"])
+    if model.hyperprior:
+      assert np.array_equal(first["idx"], again["idx"])
+  zz = z[1:2] if z is not None else None
+  part = model.decompress(zz, q[1:2], (H, W), return_float=True)
+  assert np.array_equal(part["image"], first["image"][1:2]) and np.array_equal(part["float"], first["float"][1:2])
+
+
+def test_vjp_is_deterministic_and_batch_independent(gpu_ctx):
+  """Same for the decoder backward (s2d + tcgen05 backward layers + adjoint kernels): repeats are bit-identical and the gradient of
+  image b does not depend on its batch neighbours."""
+  from shallow_ntc_b200 import build_config
+  model = build_config("two_layer_syn", precision="tc", ctx=gpu_ctx, vjp=True)
+  wts = synthetic.make_weights(model.variable_shapes(), "stress", synthesis_cls="TwoLayerResSynthesis")
+  model.load_weights(wts)
+  zs, ys = model.latent_shapes(3, 64, 128)
+  rng = np.random.default_rng(8)
+  y = rng.standard_normal(ys).astype(np.float32)
+  g = rng.standard_normal((3, 64, 128, 3)).astype(np.float32)
+  a = model.synthesis_vjp(y, g)
+  for _ in range(4):
+    assert np.array_equal(a, model.synthesis_vjp(y, g))
+  assert np.array_equal(a[1:2], model.synthesis_vjp(y[1:2], g[1:2]))
