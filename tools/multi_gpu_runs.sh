@@ -5,15 +5,15 @@
 N=${1:-2}
 run() {  # name port args...
   name=$1; port=$2; shift 2
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port bench.py --gpus $N --steps 20 --warmup 5 "$@" \
-    > gpurun_out/r02_scale_${N}gpu_${name}.json 2> gpurun_out/r02_scale_${N}gpu_${name}.err
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --no-io-stage "$@" \
+    > gpurun_out/r02_scale_${N}gpu_${name}_v5.json 2> gpurun_out/r02_scale_${N}gpu_${name}_v5.err
   python - <<PY
 import json
 try:
-  d = json.load(open("gpurun_out/r02_scale_${N}gpu_${name}.json"))
+  d = json.load(open("gpurun_out/r02_scale_${N}gpu_${name}_v5.json"))
   print("${name}", "N=%d" % d["n_gpus"], "value %.0f Mpx/s" % d["value"], "ms/step %.3f" % d["ms_per_step"], "e2e %.0f" % d["e2e"]["value"], d["scaling"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 except Exception as e:
-  print("${name} FAILED", e); print(open("gpurun_out/r02_scale_${N}gpu_${name}.err").read()[-1500:])
+  print("${name} FAILED", e); print(open("gpurun_out/r02_scale_${N}gpu_${name}_v5.err").read()[-1500:])
 PY
 }
 run headline 29531
